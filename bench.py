@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the mip-pyramid hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): full mip chain of a synthetic
+16384x16384 sRGBA8 image, 15 levels, 1 431 655 764 algorithmic bytes (level 0 read once + every other level
+written once).  A "step" is one full-chain generation.  Two distinct 1.43 GB chains are alternated, each far
+larger than the 126 MB L2, so level 0 is never cache resident.  At N > 1 every rank runs the same step on its own
+image (independent units, no data-path collective): weak scaling, value = N * bytes / max-over-ranks time.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own CPU generator
+(cpuGenerateMipmaps_sRGBA compiled in place from /root/reference into oracle/_ref, else our C port of it) on
+the host cores; that leg and the `cpu_baseline` object are the only places this file touches oracle/.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W = H = 16384
+METRIC = "mip_chain_effective_GBps_16384x16384_srgba8"
+UNIT = "GB/s"
+
+
+def algorithmic_bytes(w, h, first_level=0, last_level=None, bpt=4):
+    total, lvl = 0, 0
+    while True:
+        lw, lh = max(1, w >> lvl), max(1, h >> lvl)
+        if lvl >= first_level and (last_level is None or lvl <= last_level):
+            total += lw * lh * bpt
+        if lw == 1 and lh == 1:
+            break
+        lvl += 1
+    return total
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        return [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows[-3:]]
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    @staticmethod
+    def summarise(rows):
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(float(r[0])) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 4 + i and r[4 + i].lower().startswith("active")
+                                                         for r in rows)]
+        mx = [int(float(r[1])) for r in rows if r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def _load_cpu_generator():
+    """('reference', fn) from oracle/_ref when present, else ('port', fn) from our C restatement."""
+    P = C.c_void_p
+    ref = os.path.join(ROOT, "oracle", "_ref", "libnvpyr_ref.so")
+    if os.path.exists(ref):
+        lib = C.CDLL(ref)
+        lib.ref_storage_create.restype = P
+        lib.ref_storage_create.argtypes = [C.c_uint32, C.c_uint32, P]
+        lib.ref_storage_generate.argtypes = [P]
+        lib.ref_storage_destroy.argtypes = [P]
+
+        def make(level0, w, h):
+            s = lib.ref_storage_create(w, h, level0.ctypes.data)
+            return (lambda: lib.ref_storage_generate(s)), (lambda: lib.ref_storage_destroy(s))
+        return "reference", make
+    so = os.path.join(ROOT, "oracle", "libnvpyr_oracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    lib = C.CDLL(so)
+    lib.nvo_cpu_chain.argtypes = [C.c_int, P, C.c_uint32, C.c_uint32]
+    lib.nvo_chain_texels.restype = C.c_uint64
+
+    def make(level0, w, h):
+        import numpy as np
+        buf = np.zeros(4 * lib.nvo_chain_texels(w, h, lib.nvo_level_count(w, h)), dtype=np.uint8)
+        buf[:level0.size] = level0
+        return (lambda: lib.nvo_cpu_chain(0, buf.ctypes.data, w, h)), (lambda: None)
+    return "port", make
+
+
+def cpu_baseline_single(sample_edge=8192):
+    """The reference's CPU generator on ONE host thread (how the reference itself runs it, one std::thread
+    per image, demo_app/mipmaps_app.cpp:651-652) over a bounded sample of the workload."""
+    import numpy as np
+    kind, make = _load_cpu_generator()
+    rng = np.random.default_rng(0)
+    l0 = rng.integers(0, 256, 4 * sample_edge * sample_edge, dtype=np.uint8)
+    run, free = make(l0, sample_edge, sample_edge)
+    t = time.perf_counter()
+    run()
+    dt = time.perf_counter() - t
+    free()
+    by = algorithmic_bytes(sample_edge, sample_edge)
+    return {"value": by / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"one {sample_edge}x{sample_edge} sRGBA8 full chain (1/{(W // sample_edge) ** 2} of the "
+                      f"16384^2 workload's texels), {dt:.2f} s on one host thread"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference CPU generator, one image per host thread, all host cores."""
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    kind, make = _load_cpu_generator()
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    edge = 2048  # per-thread sample image; cores * steps of them stay within a few minutes
+    rng = np.random.default_rng(0)
+    jobs = [make(rng.integers(0, 256, 4 * edge * edge, dtype=np.uint8), edge, edge) for _ in range(cores)]
+
+    def step():
+        ts = [threading.Thread(target=j[0]) for j in jobs]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    [j[1]() for j in jobs]
+    by = algorithmic_bytes(edge, edge) * cores * args.steps
+    value = by / dt / 1e9
+    sample = (f"each step = {cores} independent {edge}x{edge} sRGBA8 full chains, one per host thread "
+              f"(the reference's own thread-per-image parallelism); same bytes-per-texel metric as the 16384^2 workload")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "synthetic 16384x16384 sRGBA8 full mip chain (BASELINE configs[2]); CPU arm runs a "
+                               "bounded sample", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import vk_compute_mipmaps_b200 as nv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pipes = nv.PyramidPipelines()
+    chain_bytes = nv.chain_bytes(W, H)
+    assert chain_bytes == algorithmic_bytes(W, H) == 1431655764
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    bufs = []
+    for _ in range(2):  # two distinct chains, alternated (each >> L2)
+        b = torch.empty(chain_bytes, dtype=torch.uint8, device=dev)
+        b[:4 * W * H] = torch.randint(0, 256, (4 * W * H,), dtype=torch.uint8, device=dev, generator=gen)
+        bufs.append(b)
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        nv.cmd_pyramid_dispatch(stream, pipes, W, H, image=bufs[i & 1])
+
+    # ---- whole-chain timing (value) ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    for i in range(max(3, args.warmup)):
+        step(i)
+    barrier()
+    launches0 = nv.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    launches = nv.launch_count() - launches0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_per_step = ms_total / args.steps
+    value = world * chain_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- dominant kernel alone: the 6-level fast kernel on level 0 (levelCount = 7 -> exactly one launch) ----
+    k_bytes = algorithmic_bytes(W, H, 0, 6)
+    for i in range(3):
+        nv.cmd_pyramid_dispatch(stream, pipes, W, H, 7, image=bufs[i & 1])
+    torch.cuda.synchronize()
+    l0 = nv.launch_count()
+    kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev0.record(stream)
+    for i in range(args.steps):
+        nv.cmd_pyramid_dispatch(stream, pipes, W, H, 7, image=bufs[i & 1])
+    kev1.record(stream)
+    torch.cuda.synchronize()
+    assert nv.launch_count() - l0 == args.steps
+    k_ms = kev0.elapsed_time(kev1) / args.steps
+    t_wall2 = time.time()
+
+    # ---- end to end through the host-buffer entry point (nvpyrGenerateHost): H2D level 0 + D2H chain ----
+    e2e = None
+    if rank == 0 or world > 1:
+        e_steps = max(2, min(args.steps, 5))
+        h_in = torch.empty(4 * W * H, dtype=torch.uint8).pin_memory()
+        h_out = torch.empty(chain_bytes, dtype=torch.uint8).pin_memory()
+        h_in.copy_(bufs[0][:4 * W * H])
+        torch.cuda.synchronize()
+        a_in, a_out = h_in.numpy(), h_out.numpy()
+        nv.generate_host(a_in, W, H, out=a_out)  # warm-up (allocates the library's device scratch)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            nv.generate_host(a_in, W, H, out=a_out)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * chain_bytes * e_steps / float(dt.item()) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": 4 * W * H, "d2h_bytes_per_step": chain_bytes, "steps": e_steps,
+               "ms_per_step": 1e3 * float(dt.item()) / e_steps,
+               "api": "nvpyrGenerateHost (pinned host level 0 in, pinned host packed chain out)"}
+        # sanity: the downloaded chain is what the device path produced
+        assert bool((h_out[:4096] == bufs[0][:4096].cpu()).all())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    sampler.stop()
+    clocks = ClockSampler.summarise(sampler.window(t_wall0, t_wall2))
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = k_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("fast6_srgba8_16384_bytes_per_launch")
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_single()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "synthetic 16384x16384 sRGBA8 full mip chain, 15 levels, uniform random bytes "
+                               "(BASELINE configs[2])",
+                   "algorithmic_bytes_per_step": chain_bytes, "us_per_chain": 1e3 * ms_per_step,
+                   "l2_policy": "inputs larger than L2: two distinct 1.43 GB chains alternated",
+                   "per_rank": "one chain per step per rank, no collective", "launches_per_chain": launches / args.steps},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "fastKernel<Srgba8,6> (level 0 -> levels 1..6)",
+                     "algorithmic_bytes_per_launch": k_bytes, "us_per_launch": 1e3 * k_ms, "peak_source": peak_src},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__), "--gpus",
+               str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        return subprocess.call(cmd)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

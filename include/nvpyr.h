@@ -1,0 +1,186 @@
+/*
+ * nvpyr.h -- C ABI of the B200-native mip-pyramid generator.
+ *
+ * Drop-in boundary for ONE path of nvpro-samples/vk_compute_mipmaps: "fill mip
+ * levels 1..N-1 of an image from level 0" -- what the reference does with
+ *     nvproCmdPyramidDispatch(cmdBuf, pipelines, baseWidth, baseHeight, mipLevels)
+ *     (reference nvpro_pyramid/nvpro_pyramid_dispatch.hpp:54-59, :109-188, :294-304)
+ * plus the two compute shaders it dispatches (nvpro_pyramid/nvpro_pyramid.glsl with
+ * nvpro_pyramid/srgba8_mipmap_preamble.glsl).  Plain C types only; the stream
+ * argument is a CUstream/cudaStream_t passed as an opaque pointer.
+ *
+ * Differences from the Vulkan original, by construction:
+ *   - commands are ENQUEUED on a CUDA stream instead of recorded into a
+ *     VkCommandBuffer; stream order replaces the inter-dispatch pipeline barriers
+ *     (dispatch.hpp:180-186);
+ *   - the image is a LINEAR buffer in device memory, packed exactly like the
+ *     reference's MipmapStorage / staging buffer (include/mipmap_storage.hpp:35-39,
+ *     :53-76; include/scoped_image.hpp:436-453): level i starts at texel offset
+ *     sum_{j<i} W_j*H_j, rows are tight, W_i = max(1, W >> i), texel = R,G,B,A;
+ *   - errors are returned, never asserted (dispatch.hpp:169,172 assert).
+ *
+ * Every entry point is reentrant and uses the CURRENT CUDA device.
+ */
+#ifndef NVPYR_H_
+#define NVPYR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define NVPYR_API __declspec(dllexport)
+#else
+#define NVPYR_API __attribute__((visibility("default")))
+#endif
+
+#define NVPYR_VERSION 100 /* 0.1.0 */
+#define NVPYR_MAX_LEVELS 32u
+#define NVPYR_MAX_STEPS 40u
+
+typedef enum nvpyrStatus
+{
+  NVPYR_SUCCESS             = 0,
+  NVPYR_ERROR_INVALID_VALUE = 1, /* null pointer, zero extent, levelCount > max, misaligned base */
+  NVPYR_ERROR_UNSUPPORTED   = 2, /* unknown format / flag, device is not sm_100 */
+  NVPYR_ERROR_CUDA          = 3, /* a CUDA call failed; see nvpyrGetLastCudaError */
+  NVPYR_ERROR_OUT_OF_MEMORY = 4
+} nvpyrStatus;
+
+typedef struct nvpyrExtent2D
+{
+  uint32_t width;
+  uint32_t height;
+} nvpyrExtent2D;
+
+/* Texel formats = shipped instances of the load/reduce/store functor set
+ * (the reference's NVPRO_PYRAMID_* macro set, nvpro_pyramid.glsl:27-120). */
+typedef enum nvpyrFormat
+{
+  NVPYR_FORMAT_SRGBA8  = 0, /* srgba8_mipmap_preamble.glsl: decode sRGB, average in float32, encode */
+  NVPYR_FORMAT_RGBA32F = 1  /* identity load/store, same reductions; 16 bytes per texel */
+} nvpyrFormat;
+
+typedef enum nvpyrFlags
+{
+  NVPYR_FLAG_NONE = 0,
+  /* Never use the fast pipeline (== NvproPyramidPipelines::fastPipeline = VK_NULL_HANDLE,
+   * minimal_app's -force-no-fast-pipeline, minimal_mipmaps.cpp:42-43,357-360). */
+  NVPYR_FLAG_FORCE_GENERAL = 1u << 0,
+  /* Run the premultiply-alpha pre-pass of include/scoped_image.hpp:233-255 on level 0
+   * (in place) before generating. sRGBA8 only. */
+  NVPYR_FLAG_PREMULTIPLY_ALPHA = 1u << 1
+} nvpyrFlags;
+
+typedef struct CUstream_st* nvpyrStream; /* == cudaStream_t == CUstream */
+
+/* ------------------------------------------------------------------ layout */
+
+/* floor(log2(max(W,H))) + 1 -- the default of dispatch.hpp:122-132. 0 if an extent is 0. */
+NVPYR_API uint32_t nvpyrGetLevelCount(nvpyrExtent2D extent);
+/* max(1, W >> level) x max(1, H >> level); mipmap_storage.hpp:67-69. */
+NVPYR_API nvpyrStatus nvpyrGetLevelExtent(nvpyrExtent2D extent, uint32_t level, nvpyrExtent2D* out);
+/* Texel offset of `level` in the packed chain; mipmap_storage.hpp:56-73. */
+NVPYR_API nvpyrStatus nvpyrGetLevelOffsetTexels(nvpyrExtent2D extent, uint32_t level, uint64_t* out);
+/* Bytes of a packed chain of levelCount levels (0 = all). */
+NVPYR_API nvpyrStatus nvpyrGetChainBytes(nvpyrExtent2D extent, uint32_t levelCount, nvpyrFormat format,
+                                         uint64_t* out);
+
+/* -------------------------------------------------------------------- plan */
+
+/* One dispatch of the reference-equivalent schedule (what nvproCmdPyramidDispatch would
+ * record): defines the float "carry groups" that are observable in the output bits. */
+typedef struct nvpyrPlanStep
+{
+  uint32_t pipeline;     /* 1 = fast (nvproPyramidDefaultFastDispatcher, dispatch.hpp:195-242),
+                            0 = general (nvproPyramidDefaultGeneralDispatcher, :247-292) */
+  uint32_t inputLevel;   /* NvproPyramidState::currentLevel */
+  uint32_t levelCount;   /* levels filled by the dispatch */
+  uint32_t srcWidth;     /* NvproPyramidState::currentX */
+  uint32_t srcHeight;    /* NvproPyramidState::currentY */
+  uint32_t workgroups;   /* groupCountX the reference passes to vkCmdDispatch */
+  uint32_t pushConstant; /* inputLevel << 5 | levelCount (dispatch.hpp:77, glsl:157-162) */
+  uint32_t bindPipeline; /* reference records vkCmdBindPipeline before this dispatch */
+  uint32_t barrierAfter; /* reference records a pipeline barrier after this dispatch */
+} nvpyrPlanStep;
+
+typedef struct nvpyrPlanOptions
+{
+  uint32_t flags;                /* NVPYR_FLAG_FORCE_GENERAL honoured */
+  uint32_t fastDivisibility;     /* template arg DivisibilityRequirement; 0 = default 4 */
+  uint32_t fastMaxLevels;        /* template arg MaxLevels (<= 6);        0 = default 6 */
+} nvpyrPlanOptions;
+
+/* Host only, no CUDA.  options may be NULL.  *count receives the number of steps. */
+NVPYR_API nvpyrStatus nvpyrGetPlan(nvpyrExtent2D extent, uint32_t levelCount, const nvpyrPlanOptions* options,
+                                   nvpyrPlanStep* steps, uint32_t maxSteps, uint32_t* count);
+
+/* ---------------------------------------------------------------- dispatch */
+
+/* Replaces nvproCmdPyramidDispatch(cmdBuf, pipelines, baseWidth, baseHeight, mipLevels)
+ * (dispatch.hpp:54-59) for an sRGBA8 image with both pipelines available.
+ *   srcLevel0  device pointer to the packed chain (level 0 filled, 16-byte aligned);
+ *              levels 1..levelCount-1 are written behind it
+ *   levelCount 0 = all levels (dispatch.hpp:122-132)
+ * Asynchronous on `stream`. */
+NVPYR_API nvpyrStatus nvpyrDispatch(void* srcLevel0, uint32_t levelCount, nvpyrExtent2D extent, nvpyrStream stream);
+
+typedef struct nvpyrDispatchDesc
+{
+  uint32_t      structSize; /* sizeof(nvpyrDispatchDesc) */
+  nvpyrFormat   format;
+  uint32_t      flags; /* nvpyrFlags */
+  nvpyrExtent2D extent;
+  uint32_t      levelCount; /* 0 = all */
+  void*         base;       /* packed chain; may be NULL if levels[] is given */
+  /* Optional override of the packed layout (the analogue of the reference's per-level
+   * image views, scoped_image.hpp:331-344): levels[i] != NULL gives the address of
+   * level i, rowPitchBytes[i] its pitch (0 = tight). */
+  void*       levels[NVPYR_MAX_LEVELS];
+  uint32_t    rowPitchBytes[NVPYR_MAX_LEVELS];
+  uint32_t    fastDivisibility; /* 0 = 4 */
+  uint32_t    fastMaxLevels;    /* 0 = 6 */
+  nvpyrStream stream;
+} nvpyrDispatchDesc;
+
+NVPYR_API nvpyrStatus nvpyrDispatchEx(const nvpyrDispatchDesc* desc);
+
+/* Independent images (no data crosses images or GPUs); descs[i].stream is honoured. */
+NVPYR_API nvpyrStatus nvpyrDispatchBatch(const nvpyrDispatchDesc* descs, uint32_t count);
+
+/* Premultiply-alpha pre-pass alone (scoped_image.hpp:233-255), in place when in == out. */
+NVPYR_API nvpyrStatus nvpyrPremultiplyAlpha(const void* in, void* out, uint64_t texels, nvpyrStream stream);
+
+/* Whole round trip with HOST buffers, the shape of minimal_app (minimal_mipmaps.cpp:59-241):
+ * upload level 0, generate, download the packed chain.  Synchronous.  hostChain receives all
+ * levelCount levels (level 0 included, as the reference's download does). */
+NVPYR_API nvpyrStatus nvpyrGenerateHost(const void* hostLevel0, void* hostChain, nvpyrExtent2D extent,
+                                        uint32_t levelCount, nvpyrFormat format, uint32_t flags);
+
+/* ------------------------------------------------- Vulkan external memory  */
+
+typedef struct nvpyrExternalMemory_t* nvpyrExternalMemory;
+/* Imports a VK_KHR_external_memory_fd (OPAQUE_FD) allocation backing a linear VkBuffer and maps
+ * `size` bytes at `offset`; the fd is owned by the library on success (cudaImportExternalMemory). */
+NVPYR_API nvpyrStatus nvpyrImportExternalMemoryFd(int fd, uint64_t allocationSize, uint64_t offset, uint64_t size,
+                                                  nvpyrExternalMemory* outHandle, void** outDevicePtr);
+NVPYR_API nvpyrStatus nvpyrReleaseExternalMemory(nvpyrExternalMemory handle);
+
+/* -------------------------------------------------------------------- misc */
+
+NVPYR_API const char* nvpyrGetErrorString(nvpyrStatus status);
+/* Last CUDA error code seen by this thread inside the library (cudaError_t value), 0 if none. */
+NVPYR_API int nvpyrGetLastCudaError(void);
+/* Number of kernels the library has launched in this process (for launch accounting). */
+NVPYR_API uint64_t nvpyrGetLaunchCount(void);
+/* Frees per-device cached tables. */
+NVPYR_API nvpyrStatus nvpyrShutdown(void);
+NVPYR_API uint32_t    nvpyrGetVersion(void);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* NVPYR_H_ */

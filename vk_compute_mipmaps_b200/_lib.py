@@ -1,0 +1,97 @@
+"""ctypes binding of libnvpyr.so (C ABI in include/nvpyr.h).
+
+The product path has NO fallback: if the CUDA library has not been built
+(``python -c "import __graft_entry__ as g; g.build()"``) importing this module
+raises.  Nothing here touches ``oracle/``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnvpyr.so")
+
+NVPYR_MAX_LEVELS = 32
+NVPYR_MAX_STEPS = 40
+
+SUCCESS, ERROR_INVALID_VALUE, ERROR_UNSUPPORTED, ERROR_CUDA, ERROR_OUT_OF_MEMORY = range(5)
+FORMAT_SRGBA8, FORMAT_RGBA32F = 0, 1
+FLAG_NONE, FLAG_FORCE_GENERAL, FLAG_PREMULTIPLY_ALPHA = 0, 1, 2
+
+
+class Extent2D(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32)]
+
+
+class PlanStep(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "pipeline", "inputLevel", "levelCount", "srcWidth", "srcHeight",
+        "workgroups", "pushConstant", "bindPipeline", "barrierAfter")]
+
+
+class PlanOptions(C.Structure):
+    _fields_ = [("flags", C.c_uint32), ("fastDivisibility", C.c_uint32), ("fastMaxLevels", C.c_uint32)]
+
+
+class DispatchDesc(C.Structure):
+    _fields_ = [
+        ("structSize", C.c_uint32),
+        ("format", C.c_int),
+        ("flags", C.c_uint32),
+        ("extent", Extent2D),
+        ("levelCount", C.c_uint32),
+        ("base", C.c_void_p),
+        ("levels", C.c_void_p * NVPYR_MAX_LEVELS),
+        ("rowPitchBytes", C.c_uint32 * NVPYR_MAX_LEVELS),
+        ("fastDivisibility", C.c_uint32),
+        ("fastMaxLevels", C.c_uint32),
+        ("stream", C.c_void_p),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. "
+            "Run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    u32, u64, vp, st = C.c_uint32, C.c_uint64, C.c_void_p, C.c_int
+    sigs = {
+        "nvpyrGetLevelCount": (u32, [Extent2D]),
+        "nvpyrGetLevelExtent": (st, [Extent2D, u32, C.POINTER(Extent2D)]),
+        "nvpyrGetLevelOffsetTexels": (st, [Extent2D, u32, C.POINTER(u64)]),
+        "nvpyrGetChainBytes": (st, [Extent2D, u32, C.c_int, C.POINTER(u64)]),
+        "nvpyrGetPlan": (st, [Extent2D, u32, C.POINTER(PlanOptions), C.POINTER(PlanStep), u32, C.POINTER(u32)]),
+        "nvpyrDispatch": (st, [vp, u32, Extent2D, vp]),
+        "nvpyrDispatchEx": (st, [C.POINTER(DispatchDesc)]),
+        "nvpyrDispatchBatch": (st, [C.POINTER(DispatchDesc), u32]),
+        "nvpyrPremultiplyAlpha": (st, [vp, vp, u64, vp]),
+        "nvpyrGenerateHost": (st, [vp, vp, Extent2D, u32, C.c_int, u32]),
+        "nvpyrImportExternalMemoryFd": (st, [C.c_int, u64, u64, u64, C.POINTER(vp), C.POINTER(vp)]),
+        "nvpyrReleaseExternalMemory": (st, [vp]),
+        "nvpyrGetErrorString": (C.c_char_p, [st]),
+        "nvpyrGetLastCudaError": (C.c_int, []),
+        "nvpyrGetLaunchCount": (u64, []),
+        "nvpyrShutdown": (st, []),
+        "nvpyrGetVersion": (u32, []),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+lib = _load()
+
+
+class NvpyrError(RuntimeError):
+    def __init__(self, status, where):
+        self.status = status
+        msg = lib.nvpyrGetErrorString(status).decode()
+        if status == ERROR_CUDA:
+            msg += f" (cudaError {lib.nvpyrGetLastCudaError()})"
+        super().__init__(f"{where}: {msg}")
+
+
+def check(status, where):
+    if status != SUCCESS:
+        raise NvpyrError(status, where)

@@ -1,0 +1,47 @@
+"""Sharding of a batch of independent textures over ranks (one process per GPU).
+
+A single mip chain is never sharded (levels are serially dependent, SURVEY.md
+section 8e); a batch is: texture k belongs to rank ``k % world``.  No data-path
+collective exists -- torch.distributed is used by callers only to agree on a
+start barrier and to gather timings / checksums.
+"""
+
+
+def shard_indices(num_textures, rank, world_size):
+    """Indices of the textures rank ``rank`` owns (round robin)."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank/world_size")
+    return list(range(rank, num_textures, world_size))
+
+
+def shard_counts(num_textures, world_size):
+    return [len(range(r, num_textures, world_size)) for r in range(world_size)]
+
+
+def fnv1a64(data):
+    """Order-sensitive checksum of a bytes-like object (numpy uint8 array ok).
+
+    Computed with numpy in blocks; used to compare shards' outputs across ranks
+    ("checksum of checksums") without moving the textures.
+    """
+    import numpy as np
+    a = np.frombuffer(memoryview(data), dtype=np.uint8)
+    # 64-bit polynomial hash, vectorised: sum(a[i] * P^(n-1-i)) mod 2^64
+    P = np.uint64(1099511628211)
+    h = np.uint64(14695981039346656037)
+    block = 1 << 16
+    pw = np.empty(block, dtype=np.uint64)
+    acc = np.uint64(1)
+    with np.errstate(over="ignore"):
+        for i in range(block - 1, -1, -1):
+            pw[i] = acc
+            acc = acc * P
+        pblock = acc  # P^block
+        for s in range(0, a.size, block):
+            c = a[s:s + block].astype(np.uint64)
+            k = c.size
+            if k == block:
+                h = h * pblock + np.sum(c * pw, dtype=np.uint64)
+            else:
+                h = h * (P ** np.uint64(k)) + np.sum(c * pw[block - k:], dtype=np.uint64)
+    return int(h)

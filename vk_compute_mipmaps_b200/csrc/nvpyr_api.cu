@@ -1,0 +1,619 @@
+// nvpyr_api.cu -- C ABI (include/nvpyr.h) over the planner and the sm_100a kernels.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "../../include/nvpyr.h"
+#include "nvpyr_kernels.cuh"
+#include "nvpyr_plan.hpp"
+#include "srgb_tables.inc"
+
+namespace nvpyr {
+namespace {
+
+thread_local int      g_lastCudaError = 0;
+std::atomic<uint64_t> g_launchCount{0};
+
+#define NVPYR_CUDA(call)                                                                                          \
+  do                                                                                                              \
+  {                                                                                                               \
+    cudaError_t e_ = (call);                                                                                      \
+    if(e_ != cudaSuccess)                                                                                         \
+    {                                                                                                             \
+      g_lastCudaError = int(e_);                                                                                  \
+      return e_ == cudaErrorMemoryAllocation ? NVPYR_ERROR_OUT_OF_MEMORY : NVPYR_ERROR_CUDA;                      \
+    }                                                                                                             \
+  } while(0)
+
+// ---------------------------------------------------------------- host tables
+float bitsToFloat(uint32_t b)
+{
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+}
+
+// Builds the encode bucket table of nvpyr_functors.cuh from the 255 pinned thresholds.
+// Returns false if a bucket would hold two thresholds (cannot happen with the pinned data;
+// checked anyway so a regenerated table cannot silently break the encode).
+bool buildHostTables(DeviceTables& t)
+{
+  for(int c = 0; c < 256; ++c)
+    t.decode[c] = bitsToFloat(NVPYR_SRGB_DECODE_BITS[c]);
+  const uint32_t* thr = NVPYR_SRGB_ENCODE_THRESHOLD_BITS;  // thr[c-1] = first bits with code >= c
+  if(thr[0] <= kEncMinBits || thr[254] > kEncMaxBits)
+    return false;
+  uint32_t code = 0;  // number of thresholds <= bucket start
+  for(uint32_t key = kEncMinKey; key <= kEncMaxKey; ++key)
+  {
+    const uint32_t lo = key << kEncShift, hi = lo + (1u << kEncShift);  // [lo, hi)
+    while(code < 255 && thr[code] <= lo)
+      ++code;
+    uint32_t entry = code << 16;
+    if(code < 255 && thr[code] < hi)
+    {
+      if(code + 1 < 255 && thr[code + 1] < hi)
+        return false;
+      entry += 0x10000u - (thr[code] - lo);
+    }
+    t.encode[key - kEncMinKey] = entry - lo;  // pre-biased: kernel adds the full bit pattern
+  }
+  return true;
+}
+
+// ------------------------------------------------------------ device context
+struct DeviceContext
+{
+  int           device   = -1;
+  int           smCount  = 0;
+  DeviceTables* tables   = nullptr;
+  void*         scratch  = nullptr;  // nvpyrGenerateHost staging chain
+  size_t        scratchBytes = 0;
+  std::mutex    scratchMutex;
+};
+
+std::mutex                  g_ctxMutex;
+std::vector<DeviceContext*> g_ctx;
+
+nvpyrStatus getContext(DeviceContext** out)
+{
+  int dev = 0;
+  NVPYR_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_ctxMutex);
+  for(DeviceContext* c : g_ctx)
+    if(c->device == dev)
+    {
+      *out = c;
+      return NVPYR_SUCCESS;
+    }
+  cudaDeviceProp prop;
+  NVPYR_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if(prop.major != 10)
+    return NVPYR_ERROR_UNSUPPORTED;  // kernels are built for sm_100a only
+  static DeviceTables host;
+  if(!buildHostTables(host))
+    return NVPYR_ERROR_UNSUPPORTED;
+  DeviceTables* d = nullptr;
+  NVPYR_CUDA(cudaMalloc(&d, sizeof(DeviceTables)));
+  cudaError_t e = cudaMemcpy(d, &host, sizeof(DeviceTables), cudaMemcpyHostToDevice);
+  if(e != cudaSuccess)
+  {
+    cudaFree(d);
+    g_lastCudaError = int(e);
+    return NVPYR_ERROR_CUDA;
+  }
+  DeviceContext* c = new DeviceContext;
+  c->device        = dev;
+  c->smCount       = prop.multiProcessorCount;
+  c->tables        = d;
+  g_ctx.push_back(c);
+  *out = c;
+  return NVPYR_SUCCESS;
+}
+
+// ------------------------------------------------------------------ launches
+template <class K>
+nvpyrStatus persistentGrid(K kernel, size_t smem, int smCount, uint64_t workItems, int* grid)
+{
+  // Opt in to > 48 KB of dynamic shared memory (idempotent, cheap).
+  NVPYR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int perSm = 0;
+  NVPYR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, 256, smem));
+  if(perSm < 1)
+    return NVPYR_ERROR_UNSUPPORTED;
+  uint64_t g = uint64_t(perSm) * uint64_t(smCount);
+  if(g > workItems)
+    g = workItems;
+  *grid = int(g < 1 ? 1 : g);
+  return NVPYR_SUCCESS;
+}
+
+template <class F, int M, bool kVec>
+nvpyrStatus launchFastT(const DeviceContext& ctx, const FastParams& p, cudaStream_t stream)
+{
+  const size_t smem = sizeof(FastSmem<F>);
+  int          grid = 1;
+  nvpyrStatus  st   = persistentGrid(fastKernel<F, M, kVec>, smem, ctx.smCount, uint64_t(p.tilesX) * p.tilesY, &grid);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  fastKernel<F, M, kVec><<<grid, 256, smem, stream>>>(p);
+  NVPYR_CUDA(cudaGetLastError());
+  ++g_launchCount;
+  return NVPYR_SUCCESS;
+}
+
+template <class F>
+nvpyrStatus launchFast(const DeviceContext& ctx, FastParams p, uint32_t M, cudaStream_t stream)
+{
+  p.tables = ctx.tables;
+  if(M == 1)
+  {
+    const size_t   smem  = sizeof(FastSmem<F>);
+    const uint64_t items = (uint64_t(p.lv[1].w) * p.lv[1].h + 255u) / 256u;
+    int            grid  = 1;
+    nvpyrStatus    st    = persistentGrid(fastKernel1<F>, smem, ctx.smCount, items, &grid);
+    if(st != NVPYR_SUCCESS)
+      return st;
+    fastKernel1<F><<<grid, 256, smem, stream>>>(p);
+    NVPYR_CUDA(cudaGetLastError());
+    ++g_launchCount;
+    return NVPYR_SUCCESS;
+  }
+  p.tilesX = (p.lv[0].w + 63u) / 64u;
+  p.tilesY = (p.lv[0].h + 63u) / 64u;
+  // Vector path: 16-byte aligned input rows, output rows of level +1 aligned for a
+  // two-texel store.
+  const uint32_t a1 = 2u * F::kTexelBytes > 16u ? 16u : 2u * F::kTexelBytes;
+  const bool vec = (reinterpret_cast<uintptr_t>(p.lv[0].ptr) % 16u == 0) && (p.lv[0].pitch % 16u == 0)
+                   && (reinterpret_cast<uintptr_t>(p.lv[1].ptr) % a1 == 0) && (p.lv[1].pitch % a1 == 0);
+#define NVPYR_FAST_CASE(m)                                                                                        \
+  case m:                                                                                                         \
+    return vec ? launchFastT<F, m, true>(ctx, p, stream) : launchFastT<F, m, false>(ctx, p, stream);
+  switch(M)
+  {
+    NVPYR_FAST_CASE(2)
+    NVPYR_FAST_CASE(3)
+    NVPYR_FAST_CASE(4)
+    NVPYR_FAST_CASE(5)
+    NVPYR_FAST_CASE(6)
+    default: return NVPYR_ERROR_INVALID_VALUE;
+  }
+#undef NVPYR_FAST_CASE
+}
+
+template <class F>
+nvpyrStatus launchGeneral(const DeviceContext& ctx, GeneralParams p, cudaStream_t stream)
+{
+  p.tables = ctx.tables;
+  if(p.levels == 1)
+  {
+    p.tilesX = (p.lv[1].w + 31u) / 32u;
+    p.tilesY = (p.lv[1].h + 31u) / 32u;
+  }
+  else
+  {
+    p.tilesX = (p.lv[2].w + kGenTile2 - 1) / kGenTile2;
+    p.tilesY = (p.lv[2].h + kGenTile2 - 1) / kGenTile2;
+  }
+  const size_t smem = sizeof(GeneralSmem<F>);
+  int          grid = 1;
+  nvpyrStatus  st   = persistentGrid(generalKernel<F>, smem, ctx.smCount, uint64_t(p.tilesX) * p.tilesY, &grid);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  generalKernel<F><<<grid, 256, smem, stream>>>(p);
+  NVPYR_CUDA(cudaGetLastError());
+  ++g_launchCount;
+  return NVPYR_SUCCESS;
+}
+
+nvpyrStatus launchPremultiply(const DeviceContext& ctx, const void* in, void* out, uint64_t texels,
+                              cudaStream_t stream)
+{
+  const size_t smem = sizeof(Srgba8::Shared);
+  int          grid = 1;
+  nvpyrStatus  st   = persistentGrid(premultiplyKernel, smem, ctx.smCount, (texels + 255u) / 256u, &grid);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  premultiplyKernel<<<grid, 256, smem, stream>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out),
+                                                 texels, ctx.tables);
+  NVPYR_CUDA(cudaGetLastError());
+  ++g_launchCount;
+  return NVPYR_SUCCESS;
+}
+
+// ------------------------------------------------------------------ dispatch
+struct ResolvedDesc
+{
+  nvpyrFormat  format;
+  uint32_t     flags, w, h, levels, texelBytes;
+  LevelView    lv[NVPYR_MAX_LEVELS];
+  dispatcher_t fast;
+  cudaStream_t stream;
+};
+
+nvpyrStatus resolve(const nvpyrDispatchDesc* d, ResolvedDesc& r)
+{
+  if(d == nullptr || d->structSize != sizeof(nvpyrDispatchDesc))
+    return NVPYR_ERROR_INVALID_VALUE;
+  if(d->extent.width == 0 || d->extent.height == 0)
+    return NVPYR_ERROR_INVALID_VALUE;
+  if(d->format != NVPYR_FORMAT_SRGBA8 && d->format != NVPYR_FORMAT_RGBA32F)
+    return NVPYR_ERROR_UNSUPPORTED;
+  if(d->flags & ~uint32_t(NVPYR_FLAG_FORCE_GENERAL | NVPYR_FLAG_PREMULTIPLY_ALPHA))
+    return NVPYR_ERROR_UNSUPPORTED;
+  if((d->flags & NVPYR_FLAG_PREMULTIPLY_ALPHA) && d->format != NVPYR_FORMAT_SRGBA8)
+    return NVPYR_ERROR_UNSUPPORTED;
+  r.format         = d->format;
+  r.flags          = d->flags;
+  r.w              = d->extent.width;
+  r.h              = d->extent.height;
+  r.texelBytes     = d->format == NVPYR_FORMAT_SRGBA8 ? 4u : 16u;
+  r.stream         = reinterpret_cast<cudaStream_t>(d->stream);
+  const uint32_t maxLevels = levelCountFor(r.w, r.h);
+  r.levels                 = d->levelCount == 0 ? maxLevels : d->levelCount;
+  if(r.levels > maxLevels || r.levels > NVPYR_MAX_LEVELS)
+    return NVPYR_ERROR_INVALID_VALUE;
+  r.fast = nullptr;
+  if(!(d->flags & NVPYR_FLAG_FORCE_GENERAL))
+  {
+    r.fast = selectFastDispatcher(d->fastDivisibility, d->fastMaxLevels);
+    if(r.fast == nullptr)
+      return NVPYR_ERROR_UNSUPPORTED;
+  }
+  uint64_t off = 0;
+  for(uint32_t i = 0; i < r.levels; ++i)
+  {
+    LevelView& v = r.lv[i];
+    v.w          = levelDim(r.w, i);
+    v.h          = levelDim(r.h, i);
+    if(d->levels[i] != nullptr)
+    {
+      v.ptr   = static_cast<unsigned char*>(d->levels[i]);
+      v.pitch = d->rowPitchBytes[i] ? d->rowPitchBytes[i] : v.w * r.texelBytes;
+      if(v.pitch < v.w * r.texelBytes)
+        return NVPYR_ERROR_INVALID_VALUE;
+    }
+    else
+    {
+      if(d->base == nullptr)
+        return NVPYR_ERROR_INVALID_VALUE;
+      v.ptr   = static_cast<unsigned char*>(d->base) + off * r.texelBytes;
+      v.pitch = v.w * r.texelBytes;
+    }
+    if(reinterpret_cast<uintptr_t>(v.ptr) % r.texelBytes != 0 || v.pitch % r.texelBytes != 0)
+      return NVPYR_ERROR_INVALID_VALUE;
+    off += uint64_t(v.w) * v.h;
+  }
+  if(d->base != nullptr && reinterpret_cast<uintptr_t>(d->base) % 16u != 0)
+    return NVPYR_ERROR_INVALID_VALUE;
+  return NVPYR_SUCCESS;
+}
+
+template <class F>
+nvpyrStatus runPlan(const DeviceContext& ctx, const ResolvedDesc& r)
+{
+  nvpyrPlanStep steps[NVPYR_MAX_STEPS];
+  const int     n = buildPlan(r.w, r.h, r.levels, defaultGeneralDispatcher, r.fast, steps, NVPYR_MAX_STEPS);
+  if(n < 0)
+    return NVPYR_ERROR_INVALID_VALUE;
+  for(int i = 0; i < n; ++i)
+  {
+    const nvpyrPlanStep& s = steps[i];
+    nvpyrStatus          st;
+    if(s.pipeline == 1)
+    {
+      FastParams p{};
+      for(uint32_t k = 0; k <= s.levelCount; ++k)
+        p.lv[k] = r.lv[s.inputLevel + k];
+      st = launchFast<F>(ctx, p, s.levelCount, r.stream);
+    }
+    else
+    {
+      GeneralParams p{};
+      for(uint32_t k = 0; k <= s.levelCount; ++k)
+        p.lv[k] = r.lv[s.inputLevel + k];
+      p.levels = s.levelCount;
+      st       = launchGeneral<F>(ctx, p, r.stream);
+    }
+    if(st != NVPYR_SUCCESS)
+      return st;
+  }
+  return NVPYR_SUCCESS;
+}
+
+nvpyrStatus dispatchResolved(const ResolvedDesc& r)
+{
+  DeviceContext* ctx = nullptr;
+  nvpyrStatus    st  = getContext(&ctx);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  if(r.flags & NVPYR_FLAG_PREMULTIPLY_ALPHA)
+  {
+    // Level 0 is tight in the packed layout; with a pitched level 0 go row by row.
+    const LevelView& v = r.lv[0];
+    if(v.pitch == v.w * 4u)
+      st = launchPremultiply(*ctx, v.ptr, v.ptr, uint64_t(v.w) * v.h, r.stream);
+    else
+      for(uint32_t y = 0; y < v.h && st == NVPYR_SUCCESS; ++y)
+        st = launchPremultiply(*ctx, v.ptr + size_t(y) * v.pitch, v.ptr + size_t(y) * v.pitch, v.w, r.stream);
+    if(st != NVPYR_SUCCESS)
+      return st;
+  }
+  if(r.levels <= 1)
+    return NVPYR_SUCCESS;
+  return r.format == NVPYR_FORMAT_SRGBA8 ? runPlan<Srgba8>(*ctx, r) : runPlan<Rgba32f>(*ctx, r);
+}
+
+}  // namespace
+}  // namespace nvpyr
+
+using namespace nvpyr;
+
+// ============================================================================
+extern "C" {
+
+uint32_t nvpyrGetLevelCount(nvpyrExtent2D e)
+{
+  return levelCountFor(e.width, e.height);
+}
+
+nvpyrStatus nvpyrGetLevelExtent(nvpyrExtent2D e, uint32_t level, nvpyrExtent2D* out)
+{
+  if(out == nullptr || e.width == 0 || e.height == 0 || level >= levelCountFor(e.width, e.height))
+    return NVPYR_ERROR_INVALID_VALUE;
+  out->width  = levelDim(e.width, level);
+  out->height = levelDim(e.height, level);
+  return NVPYR_SUCCESS;
+}
+
+nvpyrStatus nvpyrGetLevelOffsetTexels(nvpyrExtent2D e, uint32_t level, uint64_t* out)
+{
+  if(out == nullptr || e.width == 0 || e.height == 0 || level > levelCountFor(e.width, e.height))
+    return NVPYR_ERROR_INVALID_VALUE;
+  *out = levelOffsetTexels(e.width, e.height, level);
+  return NVPYR_SUCCESS;
+}
+
+nvpyrStatus nvpyrGetChainBytes(nvpyrExtent2D e, uint32_t levelCount, nvpyrFormat format, uint64_t* out)
+{
+  if(out == nullptr || e.width == 0 || e.height == 0)
+    return NVPYR_ERROR_INVALID_VALUE;
+  if(format != NVPYR_FORMAT_SRGBA8 && format != NVPYR_FORMAT_RGBA32F)
+    return NVPYR_ERROR_UNSUPPORTED;
+  const uint32_t maxLevels = levelCountFor(e.width, e.height);
+  if(levelCount == 0)
+    levelCount = maxLevels;
+  if(levelCount > maxLevels)
+    return NVPYR_ERROR_INVALID_VALUE;
+  *out = levelOffsetTexels(e.width, e.height, levelCount) * (format == NVPYR_FORMAT_SRGBA8 ? 4u : 16u);
+  return NVPYR_SUCCESS;
+}
+
+nvpyrStatus nvpyrGetPlan(nvpyrExtent2D e, uint32_t levelCount, const nvpyrPlanOptions* options, nvpyrPlanStep* steps,
+                         uint32_t maxSteps, uint32_t* count)
+{
+  if(steps == nullptr || count == nullptr || e.width == 0 || e.height == 0)
+    return NVPYR_ERROR_INVALID_VALUE;
+  const uint32_t maxLevels = levelCountFor(e.width, e.height);
+  if(levelCount > maxLevels)
+    return NVPYR_ERROR_INVALID_VALUE;
+  nvpyrPlanOptions o{};
+  if(options)
+    o = *options;
+  dispatcher_t fast = nullptr;
+  if(!(o.flags & NVPYR_FLAG_FORCE_GENERAL))
+  {
+    fast = selectFastDispatcher(o.fastDivisibility, o.fastMaxLevels);
+    if(fast == nullptr)
+      return NVPYR_ERROR_UNSUPPORTED;
+  }
+  const int n = buildPlan(e.width, e.height, levelCount, defaultGeneralDispatcher, fast, steps, maxSteps);
+  if(n < 0)
+    return NVPYR_ERROR_INVALID_VALUE;
+  *count = uint32_t(n);
+  return NVPYR_SUCCESS;
+}
+
+nvpyrStatus nvpyrDispatchEx(const nvpyrDispatchDesc* desc)
+{
+  ResolvedDesc r;
+  nvpyrStatus  st = resolve(desc, r);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  return dispatchResolved(r);
+}
+
+nvpyrStatus nvpyrDispatch(void* srcLevel0, uint32_t levelCount, nvpyrExtent2D extent, nvpyrStream stream)
+{
+  nvpyrDispatchDesc d;
+  memset(&d, 0, sizeof d);
+  d.structSize = sizeof d;
+  d.format     = NVPYR_FORMAT_SRGBA8;
+  d.extent     = extent;
+  d.levelCount = levelCount;
+  d.base       = srcLevel0;
+  d.stream     = stream;
+  return nvpyrDispatchEx(&d);
+}
+
+nvpyrStatus nvpyrDispatchBatch(const nvpyrDispatchDesc* descs, uint32_t count)
+{
+  if(descs == nullptr && count != 0)
+    return NVPYR_ERROR_INVALID_VALUE;
+  // Validate everything before enqueueing anything.
+  std::vector<ResolvedDesc> r(count);
+  for(uint32_t i = 0; i < count; ++i)
+  {
+    nvpyrStatus st = resolve(&descs[i], r[i]);
+    if(st != NVPYR_SUCCESS)
+      return st;
+  }
+  for(uint32_t i = 0; i < count; ++i)
+  {
+    nvpyrStatus st = dispatchResolved(r[i]);
+    if(st != NVPYR_SUCCESS)
+      return st;
+  }
+  return NVPYR_SUCCESS;
+}
+
+nvpyrStatus nvpyrPremultiplyAlpha(const void* in, void* out, uint64_t texels, nvpyrStream stream)
+{
+  if(in == nullptr || out == nullptr)
+    return NVPYR_ERROR_INVALID_VALUE;
+  if(reinterpret_cast<uintptr_t>(in) % 4u || reinterpret_cast<uintptr_t>(out) % 4u)
+    return NVPYR_ERROR_INVALID_VALUE;
+  if(texels == 0)
+    return NVPYR_SUCCESS;
+  DeviceContext* ctx = nullptr;
+  nvpyrStatus    st  = getContext(&ctx);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  return launchPremultiply(*ctx, in, out, texels, reinterpret_cast<cudaStream_t>(stream));
+}
+
+nvpyrStatus nvpyrGenerateHost(const void* hostLevel0, void* hostChain, nvpyrExtent2D extent, uint32_t levelCount,
+                              nvpyrFormat format, uint32_t flags)
+{
+  if(hostLevel0 == nullptr || hostChain == nullptr)
+    return NVPYR_ERROR_INVALID_VALUE;
+  uint64_t    bytes = 0;
+  nvpyrStatus st    = nvpyrGetChainBytes(extent, levelCount, format, &bytes);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  DeviceContext* ctx = nullptr;
+  st                 = getContext(&ctx);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  std::lock_guard<std::mutex> lock(ctx->scratchMutex);
+  if(ctx->scratchBytes < bytes)
+  {
+    if(ctx->scratch)
+      cudaFree(ctx->scratch);
+    ctx->scratch      = nullptr;
+    ctx->scratchBytes = 0;
+    NVPYR_CUDA(cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratchBytes = bytes;
+  }
+  const uint64_t level0Bytes = uint64_t(extent.width) * extent.height * (format == NVPYR_FORMAT_SRGBA8 ? 4u : 16u);
+  cudaStream_t   stream      = cudaStreamPerThread;
+  NVPYR_CUDA(cudaMemcpyAsync(ctx->scratch, hostLevel0, level0Bytes, cudaMemcpyHostToDevice, stream));
+  nvpyrDispatchDesc d;
+  memset(&d, 0, sizeof d);
+  d.structSize = sizeof d;
+  d.format     = format;
+  d.flags      = flags;
+  d.extent     = extent;
+  d.levelCount = levelCount;
+  d.base       = ctx->scratch;
+  d.stream     = reinterpret_cast<nvpyrStream>(stream);
+  st           = nvpyrDispatchEx(&d);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  NVPYR_CUDA(cudaMemcpyAsync(hostChain, ctx->scratch, bytes, cudaMemcpyDeviceToHost, stream));
+  NVPYR_CUDA(cudaStreamSynchronize(stream));
+  return NVPYR_SUCCESS;
+}
+
+struct nvpyrExternalMemory_t
+{
+  cudaExternalMemory_t mem;
+  void*                ptr;
+};
+
+nvpyrStatus nvpyrImportExternalMemoryFd(int fd, uint64_t allocationSize, uint64_t offset, uint64_t size,
+                                        nvpyrExternalMemory* outHandle, void** outDevicePtr)
+{
+  if(fd < 0 || outHandle == nullptr || outDevicePtr == nullptr || size == 0 || offset + size > allocationSize)
+    return NVPYR_ERROR_INVALID_VALUE;
+  cudaExternalMemoryHandleDesc hd;
+  memset(&hd, 0, sizeof hd);
+  hd.type      = cudaExternalMemoryHandleTypeOpaqueFd;
+  hd.handle.fd = fd;
+  hd.size      = allocationSize;
+  cudaExternalMemory_t mem;
+  NVPYR_CUDA(cudaImportExternalMemory(&mem, &hd));
+  cudaExternalMemoryBufferDesc bd;
+  memset(&bd, 0, sizeof bd);
+  bd.offset = offset;
+  bd.size   = size;
+  void*       ptr = nullptr;
+  cudaError_t e   = cudaExternalMemoryGetMappedBuffer(&ptr, mem, &bd);
+  if(e != cudaSuccess)
+  {
+    cudaDestroyExternalMemory(mem);
+    g_lastCudaError = int(e);
+    return NVPYR_ERROR_CUDA;
+  }
+  nvpyrExternalMemory h = new nvpyrExternalMemory_t{mem, ptr};
+  *outHandle            = h;
+  *outDevicePtr         = ptr;
+  return NVPYR_SUCCESS;
+}
+
+nvpyrStatus nvpyrReleaseExternalMemory(nvpyrExternalMemory handle)
+{
+  if(handle == nullptr)
+    return NVPYR_ERROR_INVALID_VALUE;
+  cudaFree(handle->ptr);
+  cudaError_t e = cudaDestroyExternalMemory(handle->mem);
+  delete handle;
+  if(e != cudaSuccess)
+  {
+    g_lastCudaError = int(e);
+    return NVPYR_ERROR_CUDA;
+  }
+  return NVPYR_SUCCESS;
+}
+
+const char* nvpyrGetErrorString(nvpyrStatus status)
+{
+  switch(status)
+  {
+    case NVPYR_SUCCESS: return "NVPYR_SUCCESS";
+    case NVPYR_ERROR_INVALID_VALUE: return "NVPYR_ERROR_INVALID_VALUE";
+    case NVPYR_ERROR_UNSUPPORTED: return "NVPYR_ERROR_UNSUPPORTED";
+    case NVPYR_ERROR_CUDA: return "NVPYR_ERROR_CUDA";
+    case NVPYR_ERROR_OUT_OF_MEMORY: return "NVPYR_ERROR_OUT_OF_MEMORY";
+  }
+  return "NVPYR_ERROR_UNKNOWN";
+}
+
+int nvpyrGetLastCudaError(void)
+{
+  return g_lastCudaError;
+}
+
+uint64_t nvpyrGetLaunchCount(void)
+{
+  return g_launchCount.load();
+}
+
+nvpyrStatus nvpyrShutdown(void)
+{
+  std::lock_guard<std::mutex> lock(g_ctxMutex);
+  int                         prev = 0;
+  cudaGetDevice(&prev);
+  for(DeviceContext* c : g_ctx)
+  {
+    cudaSetDevice(c->device);
+    cudaFree(c->tables);
+    if(c->scratch)
+      cudaFree(c->scratch);
+    delete c;
+  }
+  g_ctx.clear();
+  cudaSetDevice(prev);
+  return NVPYR_SUCCESS;
+}
+
+uint32_t nvpyrGetVersion(void)
+{
+  return NVPYR_VERSION;
+}
+
+}  // extern "C"

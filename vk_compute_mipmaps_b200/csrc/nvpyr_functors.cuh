@@ -1,0 +1,204 @@
+// nvpyr_functors.cuh -- the user-customisable part of the pyramid generator.
+//
+// The reference configures its GLSL template with preprocessor macros
+// (nvpro_pyramid/nvpro_pyramid.glsl:27-120): NVPRO_PYRAMID_TYPE, _LOAD, _REDUCE,
+// _REDUCE2, _REDUCE4, _LOAD_REDUCE4, _STORE, _SHARED_*.  Here the same contract
+// is a C++ "functor set": a struct with static __device__ members that the
+// kernel templates of nvpyr_kernels.cuh are instantiated with.
+//
+//   struct Functors {
+//     using Value = float4;                       // NVPRO_PYRAMID_TYPE
+//     static constexpr int kTexelBytes;           // storage bytes per texel
+//     struct Shared;                              // per-CTA tables in shared memory
+//     static void sharedInit(Shared&, const DeviceTables*);  // cooperative, once per CTA
+//     static Value load(const Shared&, const void* texel);   // NVPRO_PYRAMID_LOAD
+//     static void  load4(const Shared&, const void* p, Value out[4]);   // 4 texels in a row, 16B-aligned
+//     static void  store(const Shared&, void* texel, Value);            // NVPRO_PYRAMID_STORE
+//     static void  store2(const Shared&, void* p, Value, Value);        // 2 texels in a row, aligned
+//     static Value reduce(float a0, Value v0, float a1, Value v1, float a2, Value v2);  // _REDUCE
+//     static Value reduce2(Value, Value);                               // _REDUCE2
+//     static Value reduce4(Value v00, Value v01, Value v10, Value v11); // _REDUCE4
+//   };
+//
+// Shipped instances: Srgba8 (nvpro_pyramid/srgba8_mipmap_preamble.glsl) and
+// Rgba32f (identity load/store).  All float arithmetic uses the *_rn intrinsics
+// so that nvcc can never contract a*b+c into an FMA: the numerics contract
+//  is float32, round-to-nearest, no contraction, in the pairing order
+// of the reference shader.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nvpyr {
+
+// ---------------------------------------------------------------------------
+// sRGB encode bucket table.
+//
+// srgbFromLinear(x) (shaders/srgb.h:30-41) is monotone, so it is fully described
+// by 255 float thresholds (srgb_tables.inc).  To evaluate it without a search:
+// the float's upper bits (sign/exponent + 8 mantissa bits) select a bucket that
+// contains at most ONE threshold; the entry holds the code at the bucket's lower
+// edge and where inside the bucket the next code starts, pre-biased so that
+//     t = entry[bits >> 15] + bits;   code = (t >> 16) & 0xFF
+// (one shift, one table read, one add).  bits must be clamped to
+// [kEncMinBits, kEncMaxBits] first.
+constexpr uint32_t kEncShift   = 15;
+constexpr uint32_t kEncMinBits = 0x39000000u;  // 2^-13 < threshold of code 1
+constexpr uint32_t kEncMaxBits = 0x3F800000u;  // 1.0f -> code 255
+constexpr uint32_t kEncMinKey  = kEncMinBits >> kEncShift;
+constexpr uint32_t kEncMaxKey  = kEncMaxBits >> kEncShift;
+constexpr uint32_t kEncEntries = kEncMaxKey - kEncMinKey + 1;  // 3329
+
+struct DeviceTables
+{
+  float    decode[256];          // linearFromSrgb(c), shaders/srgb.h:18-28 (pinned bits)
+  uint32_t encode[kEncEntries];  // bucket table described above
+};
+
+__device__ __forceinline__ float4 f4add(float4 a, float4 b)
+{
+  return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+}
+__device__ __forceinline__ float4 f4scale(float s, float4 a)
+{
+  return make_float4(__fmul_rn(s, a.x), __fmul_rn(s, a.y), __fmul_rn(s, a.z), __fmul_rn(s, a.w));
+}
+
+// Reductions shared by both shipped instances (srgba8_mipmap_preamble.glsl:24-25,:35,:37-38).
+struct LinearReduce
+{
+  using Value = float4;
+  // a0*v0 + a1*v1 + a2*v2, left-associated, not contracted.
+  __device__ __forceinline__ static Value reduce(float a0, Value v0, float a1, Value v1, float a2, Value v2)
+  {
+    return f4add(f4add(f4scale(a0, v0), f4scale(a1, v1)), f4scale(a2, v2));
+  }
+  __device__ __forceinline__ static Value reduce2(Value v0, Value v1) { return f4scale(0.5f, f4add(v0, v1)); }
+  // 0.25 * ((v00 + v01) + (v10 + v11)): the caller chooses which neighbours share a
+  // bracket (pairing order differs per site in the reference, SURVEY.md section 8a note 1).
+  __device__ __forceinline__ static Value reduce4(Value v00, Value v01, Value v10, Value v11)
+  {
+    return f4scale(0.25f, f4add(f4add(v00, v01), f4add(v10, v11)));
+  }
+};
+
+// ---------------------------------------------------------------------------
+// sRGBA8: srgba8_mipmap_preamble.glsl
+struct Srgba8 : LinearReduce
+{
+  static constexpr int kTexelBytes = 4;
+
+  struct Shared
+  {
+    // decode table replicated per lane: entry (code, lane) at [code * 32 + lane], so a
+    // warp-wide lookup with arbitrary codes never has a bank conflict.
+    float    decode[256 * 32];
+    uint32_t encode[kEncEntries];
+  };
+
+  __device__ static void sharedInit(Shared& s, const DeviceTables* t)
+  {
+    for(uint32_t i = threadIdx.x; i < 256u * 32u; i += blockDim.x)
+      s.decode[i] = __ldg(&t->decode[i >> 5]);
+    for(uint32_t i = threadIdx.x; i < kEncEntries; i += blockDim.x)
+      s.encode[i] = __ldg(&t->encode[i]);
+  }
+
+  // texelFetch on the sRGB view: RGB through the decode table, alpha = a * (1/255)
+  // (shaders/srgb.h:60, mipmap_storage.hpp:400).
+  __device__ __forceinline__ static Value decodeWord(const Shared& s, uint32_t w)
+  {
+    const uint32_t lane = threadIdx.x & 31u;
+    Value          v;
+    v.x = s.decode[((w & 0xFFu) << 5) | lane];
+    v.y = s.decode[(((w >> 8) & 0xFFu) << 5) | lane];
+    v.z = s.decode[(((w >> 16) & 0xFFu) << 5) | lane];
+    v.w = __fmul_rn(float(w >> 24), 1.0f / 255.0f);
+    return v;
+  }
+
+  template <bool kClampHigh>
+  __device__ __forceinline__ static uint32_t encodeChannel(const Shared& s, float x)
+  {
+    uint32_t b = __float_as_uint(x);
+    b          = max(b, kEncMinBits);
+    if(kClampHigh)
+      b = min(b, kEncMaxBits);
+    return s.encode[(b >> kEncShift) - kEncMinKey] + b;  // code in bits 16..23
+  }
+
+  // srgbFromLinearVec, srgba8_mipmap_preamble.glsl:122-128.  kClampHigh = false is
+  // valid when every channel is known to be <= 1 (2x2 box reductions of values <= 1).
+  template <bool kClampHigh>
+  __device__ __forceinline__ static uint32_t encodeWord(const Shared& s, Value v)
+  {
+    const uint32_t r = encodeChannel<kClampHigh>(s, v.x);
+    const uint32_t g = encodeChannel<kClampHigh>(s, v.y);
+    const uint32_t b = encodeChannel<kClampHigh>(s, v.z);
+    // uint(a * 255 + 0.5), clamped to 255.
+    const float    af = __fadd_rn(__fmul_rn(v.w, 255.0f), 0.5f);
+    uint32_t       a  = __float2uint_rz(af);
+    a                 = min(a, 255u);
+    const uint32_t rg = __byte_perm(r, g, 0x0062);  // byte0 = r.byte2, byte1 = g.byte2
+    const uint32_t ba = __byte_perm(b, a, 0x0042);  // byte0 = b.byte2, byte1 = a.byte0
+    return __byte_perm(rg, ba, 0x5410);
+  }
+
+  __device__ __forceinline__ static Value load(const Shared& s, const void* p)
+  {
+    return decodeWord(s, *reinterpret_cast<const uint32_t*>(p));
+  }
+  __device__ __forceinline__ static void load4(const Shared& s, const void* p, Value out[4])
+  {
+    const uint4 w = *reinterpret_cast<const uint4*>(p);
+    out[0]        = decodeWord(s, w.x);
+    out[1]        = decodeWord(s, w.y);
+    out[2]        = decodeWord(s, w.z);
+    out[3]        = decodeWord(s, w.w);
+  }
+  template <bool kClampHigh = true>
+  __device__ __forceinline__ static void store(const Shared& s, void* p, Value v)
+  {
+    *reinterpret_cast<uint32_t*>(p) = encodeWord<kClampHigh>(s, v);
+  }
+  template <bool kClampHigh = true>
+  __device__ __forceinline__ static void store2(const Shared& s, void* p, Value v0, Value v1)
+  {
+    *reinterpret_cast<uint2*>(p) = make_uint2(encodeWord<kClampHigh>(s, v0), encodeWord<kClampHigh>(s, v1));
+  }
+};
+
+// ---------------------------------------------------------------------------
+// RGBA32F: the template of nvpro_pyramid.glsl:27-49 instantiated with identity
+// load/store (the reference ships no such shader).
+struct Rgba32f : LinearReduce
+{
+  static constexpr int kTexelBytes = 16;
+  struct Shared
+  {
+    int unused;
+  };
+  __device__ static void sharedInit(Shared&, const DeviceTables*) {}
+  __device__ __forceinline__ static Value load(const Shared&, const void* p)
+  {
+    return *reinterpret_cast<const float4*>(p);
+  }
+  __device__ __forceinline__ static void load4(const Shared&, const void* p, Value out[4])
+  {
+    const float4* q = reinterpret_cast<const float4*>(p);
+    out[0] = q[0], out[1] = q[1], out[2] = q[2], out[3] = q[3];
+  }
+  template <bool kClampHigh = true>
+  __device__ __forceinline__ static void store(const Shared&, void* p, Value v)
+  {
+    *reinterpret_cast<float4*>(p) = v;
+  }
+  template <bool kClampHigh = true>
+  __device__ __forceinline__ static void store2(const Shared&, void* p, Value v0, Value v1)
+  {
+    float4* q = reinterpret_cast<float4*>(p);
+    q[0] = v0, q[1] = v1;
+  }
+};
+
+}  // namespace nvpyr

@@ -1,0 +1,380 @@
+// nvpyr_kernels.cuh -- sm_100a kernels of the mip-pyramid generator.
+//
+// Two pipelines, like the reference (nvpro_pyramid/nvpro_pyramid.glsl):
+//
+//  fastKernel<F, M>     M = 2..6 levels from one input level whose edges are
+//                       multiples of 2^M (glsl:216-532).  One CTA owns a 64x64
+//                       input tile (a partial one at the right/bottom edge); a
+//                       thread owns a 4x4 block: levels +1 and +2 in registers,
+//                       +3 with warp shuffles, +4..+6 by one warp after a single
+//                       barrier through a 1 KB shared tile.  Persistent grid.
+//  fastKernel1<F>       M = 1 (only at the end of a chain).
+//  generalKernel<F>     1 or 2 levels from an input level of ANY size with the
+//                       energy-conserving 1/2/3-tap separable kernel
+//                       (glsl:543-882); level +1 is carried to level +2 as
+//                       float32 through shared memory.
+//
+// The thread<->texel mapping is ours (row-major 16x16 threads, coalesced 16-byte
+// loads) -- NOT the reference's Morton order -- but every output texel is produced
+// by the same float32 expression tree as in the reference shader, including which
+// neighbours share a bracket in 0.25*((a+b)+(c+d)) at each level ("pairing"), so
+// the stored bits are identical to the shader-order oracle.
+#pragma once
+#include "nvpyr_functors.cuh"
+
+namespace nvpyr {
+
+struct LevelView
+{
+  unsigned char* ptr;
+  uint32_t       pitch;  // bytes
+  uint32_t       w, h;
+};
+
+// Pairing of the 2x2 reduction that produces level (input + k) in an M-level fast
+// step.  false = "vertical": (UL+LL)+(UR+LR); true = "horizontal": (UL+UR)+(LL+LR).
+//   k = 1            software LOAD_REDUCE4, glsl:180-188            vertical
+//   k = 2, M = 6     the thread's own 2x2 of level +1, glsl:321-342 vertical
+//   next two levels  subgroup shuffles xor 1,2,3 / 4,8,12, glsl:366-391  horizontal
+//   last one or two  shared-memory tail, glsl:487-491,:509-526      vertical
+__host__ __device__ constexpr bool fastPairingIsHorizontal(int k, int M)
+{
+  return M == 6 ? (k == 3 || k == 4) : (k == 2 || k == 3);
+}
+
+template <class F>
+__device__ __forceinline__ typename F::Value reduce4Paired(bool horizontal, typename F::Value ul,
+                                                           typename F::Value ur, typename F::Value ll,
+                                                           typename F::Value lr)
+{
+  return horizontal ? F::reduce4(ul, ur, ll, lr) : F::reduce4(ul, ll, ur, lr);
+}
+
+__device__ __forceinline__ float4 shflXor(float4 v, int mask)
+{
+  return make_float4(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask),
+                     __shfl_xor_sync(0xffffffffu, v.z, mask), __shfl_xor_sync(0xffffffffu, v.w, mask));
+}
+
+struct FastParams
+{
+  LevelView           lv[7];  // lv[0] = input level, lv[k] = input + k
+  uint32_t            tilesX, tilesY;
+  const DeviceTables* tables;
+};
+
+template <class F>
+struct FastSmem
+{
+  typename F::Shared tables;
+  float4             l3[2][8][8];  // level +3 of the current tile, double buffered
+};
+
+// kVec: all row starts of lv[0] are 16-byte aligned and those of lv[1] are
+// aligned for a 2-texel store.
+template <class F, int M, bool kVec>
+__global__ void __launch_bounds__(256) fastKernel(const FastParams p)
+{
+  static_assert(M >= 2 && M <= 6, "fastKernel handles 2..6 levels");
+  using V = typename F::Value;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  FastSmem<F>& sm = *reinterpret_cast<FastSmem<F>*>(smemRaw);
+  F::sharedInit(sm.tables, p.tables);
+  __syncthreads();
+
+  const uint32_t tid = threadIdx.x, tx = tid & 15u, ty = tid >> 4;
+  const uint32_t W = p.lv[0].w, H = p.lv[0].h;
+  const uint32_t numTiles = p.tilesX * p.tilesY;
+  uint32_t       parity   = 0;
+
+  for(uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, parity ^= 1u)
+  {
+    const uint32_t tileX = tile % p.tilesX, tileY = tile / p.tilesX;
+    const uint32_t x0 = tileX * 64u + tx * 4u, y0 = tileY * 64u + ty * 4u;
+    // Edges are multiples of 2^M >= 4: a 4x4 block is entirely inside or outside.
+    const bool active = x0 < W && y0 < H;
+
+    V l1[2][2];
+    V l2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if(active)
+    {
+#pragma unroll
+      for(int qy = 0; qy < 2; ++qy)
+      {
+        V                    a[4], b[4];
+        const unsigned char* r0 = p.lv[0].ptr + size_t(y0 + 2 * qy) * p.lv[0].pitch + size_t(x0) * F::kTexelBytes;
+        const unsigned char* r1 = r0 + p.lv[0].pitch;
+        if(kVec)
+        {
+          F::load4(sm.tables, r0, a);
+          F::load4(sm.tables, r1, b);
+        }
+        else
+        {
+#pragma unroll
+          for(int i = 0; i < 4; ++i)
+          {
+            a[i] = F::load(sm.tables, r0 + i * F::kTexelBytes);
+            b[i] = F::load(sm.tables, r1 + i * F::kTexelBytes);
+          }
+        }
+        // level +1: vertical pairing (k = 1)
+        l1[qy][0] = F::reduce4(a[0], b[0], a[1], b[1]);
+        l1[qy][1] = F::reduce4(a[2], b[2], a[3], b[3]);
+        unsigned char* d = p.lv[1].ptr + size_t((y0 >> 1) + qy) * p.lv[1].pitch + size_t(x0 >> 1) * F::kTexelBytes;
+        if(kVec)
+          F::template store2<false>(sm.tables, d, l1[qy][0], l1[qy][1]);
+        else
+        {
+          F::template store<false>(sm.tables, d, l1[qy][0]);
+          F::template store<false>(sm.tables, d + F::kTexelBytes, l1[qy][1]);
+        }
+      }
+      // level +2 from the thread's own 2x2 of level +1
+      l2 = reduce4Paired<F>(fastPairingIsHorizontal(2, M), l1[0][0], l1[0][1], l1[1][0], l1[1][1]);
+      F::template store<false>(sm.tables,
+                               p.lv[2].ptr + size_t(y0 >> 2) * p.lv[2].pitch + size_t(x0 >> 2) * F::kTexelBytes, l2);
+    }
+
+    if(M >= 3)
+    {
+      // level +3: 2x2 threads = lanes l, l^1 (x), l^16 (y), l^17.  All four compute the
+      // same bits (float add is commutative), the even/even one stores.
+      const V sx = shflXor(l2, 1), sy = shflXor(l2, 16), sxy = shflXor(l2, 17);
+      const V l3 = reduce4Paired<F>(fastPairingIsHorizontal(3, M), l2, sx, sy, sxy);
+      if(active && !(tx & 1u) && !(ty & 1u))
+      {
+        F::template store<false>(
+            sm.tables, p.lv[3].ptr + size_t(y0 >> 3) * p.lv[3].pitch + size_t(x0 >> 3) * F::kTexelBytes, l3);
+        if(M >= 4)
+          sm.l3[parity][ty >> 1][tx >> 1] = l3;
+      }
+    }
+
+    if(M >= 4)
+    {
+      __syncthreads();
+      if(tid < 32)
+      {
+        // 16 lanes <-> 4x4 texels of level +4; then +5 (2x2) and +6 (1) by shuffles.
+        const uint32_t i = tid & 3u, j = (tid >> 2) & 3u;
+        const uint32_t ox = tileX * 64u + i * 16u, oy = tileY * 64u + j * 16u;  // origin in level 0
+        const bool     valid = tid < 16 && ox < W && oy < H;
+        V              l4    = make_float4(0.f, 0.f, 0.f, 0.f);
+        if(valid)
+        {
+          const V ul = sm.l3[parity][2 * j][2 * i], ur = sm.l3[parity][2 * j][2 * i + 1];
+          const V ll = sm.l3[parity][2 * j + 1][2 * i], lr = sm.l3[parity][2 * j + 1][2 * i + 1];
+          l4         = reduce4Paired<F>(fastPairingIsHorizontal(4, M), ul, ur, ll, lr);
+          F::template store<false>(
+              sm.tables, p.lv[4].ptr + size_t(oy >> 4) * p.lv[4].pitch + size_t(ox >> 4) * F::kTexelBytes, l4);
+        }
+        if(M >= 5)
+        {
+          const V sx = shflXor(l4, 1), sy = shflXor(l4, 4), sxy = shflXor(l4, 5);
+          const V l5 = reduce4Paired<F>(fastPairingIsHorizontal(5, M), l4, sx, sy, sxy);
+          if(valid && !(i & 1u) && !(j & 1u))
+            F::template store<false>(
+                sm.tables, p.lv[5].ptr + size_t(oy >> 5) * p.lv[5].pitch + size_t(ox >> 5) * F::kTexelBytes, l5);
+          if(M >= 6)
+          {
+            const V tx2 = shflXor(l5, 2), ty2 = shflXor(l5, 8), txy2 = shflXor(l5, 10);
+            const V l6  = reduce4Paired<F>(fastPairingIsHorizontal(6, M), l5, tx2, ty2, txy2);
+            if(valid && tid == 0)
+              F::template store<false>(
+                  sm.tables, p.lv[6].ptr + size_t(oy >> 6) * p.lv[6].pitch + size_t(ox >> 6) * F::kTexelBytes, l6);
+          }
+        }
+      }
+      // sm.l3 is double buffered: the next iteration writes the other half, and the
+      // barrier of that iteration orders this read before the overwrite after it.
+    }
+  }
+}
+
+// M = 1: one thread per output texel (glsl:345-357 with levelCount_ == 1).
+template <class F>
+__global__ void __launch_bounds__(256) fastKernel1(const FastParams p)
+{
+  using V = typename F::Value;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  FastSmem<F>& sm = *reinterpret_cast<FastSmem<F>*>(smemRaw);
+  F::sharedInit(sm.tables, p.tables);
+  __syncthreads();
+  const uint32_t W1 = p.lv[1].w, H1 = p.lv[1].h;
+  const uint64_t n = uint64_t(W1) * H1;
+  for(uint64_t g = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < n; g += uint64_t(gridDim.x) * blockDim.x)
+  {
+    const uint32_t       x = uint32_t(g % W1), y = uint32_t(g / W1);
+    const unsigned char* s = p.lv[0].ptr + size_t(2 * y) * p.lv[0].pitch + size_t(2 * x) * F::kTexelBytes;
+    const V ul = F::load(sm.tables, s), ur = F::load(sm.tables, s + F::kTexelBytes);
+    const V ll = F::load(sm.tables, s + p.lv[0].pitch), lr = F::load(sm.tables, s + p.lv[0].pitch + F::kTexelBytes);
+    F::template store<false>(sm.tables, p.lv[1].ptr + size_t(y) * p.lv[1].pitch + size_t(x) * F::kTexelBytes,
+                             F::reduce4(ul, ll, ur, lr));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// General pipeline.
+
+struct GeneralParams
+{
+  LevelView           lv[3];  // input, +1, +2
+  uint32_t            levels; // 1 or 2
+  uint32_t            tilesX, tilesY;
+  const DeviceTables* tables;
+};
+
+constexpr int kGenTile2 = 16;                  // tile edge in level +2
+constexpr int kGenTile1 = 2 * kGenTile2 + 1;   // <= 33 texels of level +1 per axis
+constexpr int kGenPitch = kGenTile1 + 1;
+
+template <class F>
+struct GeneralSmem
+{
+  typename F::Shared tables;
+  float4             l1[kGenTile1][kGenPitch];  // [y][x] level +1 tile (float32 carry)
+};
+
+// kernelSizeFromInputSize_, glsl:557-561
+__device__ __forceinline__ int kernelTaps(uint32_t size)
+{
+  return size == 1u ? 1 : int(2u | (size & 1u));
+}
+
+// Weights of the 3-tap kernel for destination index i of n (glsl:582-586, :639-643):
+// (n - i, n, 1 + i) / (2n + 1) with w2 evaluated as 1 - w0 - w1.
+__device__ __forceinline__ void taps3(uint32_t n, uint32_t i, float& w0, float& w1, float& w2)
+{
+  const float fn  = float(n);
+  const float rcp = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(2.0f, fn), 1.0f));
+  w0              = __fmul_rn(rcp, __fsub_rn(fn, float(i)));
+  w1              = __fmul_rn(rcp, fn);
+  w2              = __fsub_rn(__fsub_rn(1.0f, w0), w1);
+}
+
+// reduceStoreSample_ without the store (glsl:575-651): vertical reduction of each
+// source column, then horizontal reduction.  `fetch(dx, dy)` returns the source
+// sample at (srcX + dx, srcY + dy).
+template <class F, class Fetch>
+__device__ __forceinline__ typename F::Value reduceSample(int kx, int ky, uint32_t dstW, uint32_t dstH,
+                                                          uint32_t dx, uint32_t dy, Fetch fetch)
+{
+  using V = typename F::Value;
+  V     hcol[3];
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+  if(ky == 3)
+    taps3(dstH, dy, w0, w1, w2);
+#pragma unroll
+  for(int c = 0; c < 3; ++c)
+  {
+    if(c < kx)
+    {
+      const V v0 = fetch(c, 0);
+      if(ky == 3)
+        hcol[c] = F::reduce(w0, v0, w1, fetch(c, 1), w2, fetch(c, 2));
+      else if(ky == 2)
+        hcol[c] = F::reduce2(v0, fetch(c, 1));
+      else
+        hcol[c] = v0;
+    }
+  }
+  if(kx == 3)
+  {
+    taps3(dstW, dx, w0, w1, w2);
+    return F::reduce(w0, hcol[0], w1, hcol[1], w2, hcol[2]);
+  }
+  if(kx == 2)
+    return F::reduce2(hcol[0], hcol[1]);
+  return hcol[0];
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) generalKernel(const GeneralParams p)
+{
+  using V = typename F::Value;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  GeneralSmem<F>& sm = *reinterpret_cast<GeneralSmem<F>*>(smemRaw);
+  F::sharedInit(sm.tables, p.tables);
+  __syncthreads();
+
+  const LevelView L0 = p.lv[0], L1 = p.lv[1], L2 = p.lv[2];
+  const int       k1x = kernelTaps(L0.w), k1y = kernelTaps(L0.h);
+  const uint32_t  numTiles = p.tilesX * p.tilesY;
+
+  for(uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x)
+  {
+    const uint32_t tileX = tile % p.tilesX, tileY = tile / p.tilesX;
+    if(p.levels == 1)
+    {
+      // 32x32 tile of level +1, no carry needed.
+      for(uint32_t t = threadIdx.x; t < 32u * 32u; t += blockDim.x)
+      {
+        const uint32_t x = tileX * 32u + (t & 31u), y = tileY * 32u + (t >> 5);
+        if(x >= L1.w || y >= L1.h)
+          continue;
+        const unsigned char* s   = L0.ptr + size_t(2 * y) * L0.pitch + size_t(2 * x) * F::kTexelBytes;
+        const V              out = reduceSample<F>(k1x, k1y, L1.w, L1.h, x, y, [&](int dx, int dy) {
+          return F::load(sm.tables, s + size_t(dy) * L0.pitch + size_t(dx) * F::kTexelBytes);
+        });
+        F::template store<true>(sm.tables, L1.ptr + size_t(y) * L1.pitch + size_t(x) * F::kTexelBytes, out);
+      }
+      continue;
+    }
+
+    // Two levels.  Tile of level +2: [x2a, x2b) x [y2a, y2b); the level +1 footprint it
+    // needs starts at (2*x2a, 2*y2a) and spans 2*n + taps - 2 texels per axis.
+    const int      k2x = kernelTaps(L1.w), k2y = kernelTaps(L1.h);
+    const uint32_t x2a = tileX * kGenTile2, y2a = tileY * kGenTile2;
+    const uint32_t x2b = min(x2a + kGenTile2, L2.w), y2b = min(y2a + kGenTile2, L2.h);
+    const uint32_t fw = min(2u * (x2b - x2a) + uint32_t(k2x) - 2u, L1.w - 2u * x2a);
+    const uint32_t fh = min(2u * (y2b - y2a) + uint32_t(k2y) - 2u, L1.h - 2u * y2a);
+
+    __syncthreads();  // previous tile's level +2 pass is done with sm.l1
+    for(uint32_t t = threadIdx.x; t < fw * fh; t += blockDim.x)
+    {
+      const uint32_t lx = t % fw, ly = t / fw;
+      const uint32_t x = 2u * x2a + lx, y = 2u * y2a + ly;
+      const unsigned char* s   = L0.ptr + size_t(2 * y) * L0.pitch + size_t(2 * x) * F::kTexelBytes;
+      const V              out = reduceSample<F>(k1x, k1y, L1.w, L1.h, x, y, [&](int dx, int dy) {
+        return F::load(sm.tables, s + size_t(dy) * L0.pitch + size_t(dx) * F::kTexelBytes);
+      });
+      // The halo column/row is also produced (with identical bits) by the neighbouring
+      // tile, exactly like the reference's overlapping work groups.
+      F::template store<true>(sm.tables, L1.ptr + size_t(y) * L1.pitch + size_t(x) * F::kTexelBytes, out);
+      sm.l1[ly][lx] = out;
+    }
+    __syncthreads();
+    const uint32_t tw = x2b - x2a, th = y2b - y2a;
+    for(uint32_t t = threadIdx.x; t < tw * th; t += blockDim.x)
+    {
+      const uint32_t lx = t % tw, ly = t / tw;
+      const V        out = reduceSample<F>(k2x, k2y, L2.w, L2.h, x2a + lx, y2a + ly,
+                                           [&](int dx, int dy) { return sm.l1[2 * ly + dy][2 * lx + dx]; });
+      F::template store<true>(sm.tables, L2.ptr + size_t(y2a + ly) * L2.pitch + size_t(x2a + lx) * F::kTexelBytes,
+                              out);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Premultiply-alpha pre-pass, include/scoped_image.hpp:233-255 (sRGBA8 only).
+__global__ void __launch_bounds__(256) premultiplyKernel(const uint32_t* in, uint32_t* out, uint64_t texels,
+                                                         const DeviceTables* tables)
+{
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  Srgba8::Shared& sm = *reinterpret_cast<Srgba8::Shared*>(smemRaw);
+  Srgba8::sharedInit(sm, tables);
+  __syncthreads();
+  for(uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < texels; i += uint64_t(gridDim.x) * blockDim.x)
+  {
+    const uint32_t w = in[i];
+    float4         v = Srgba8::decodeWord(sm, w);
+    const uint32_t r = Srgba8::encodeChannel<true>(sm, __fmul_rn(v.x, v.w));
+    const uint32_t g = Srgba8::encodeChannel<true>(sm, __fmul_rn(v.y, v.w));
+    const uint32_t b = Srgba8::encodeChannel<true>(sm, __fmul_rn(v.z, v.w));
+    out[i]           = ((r >> 16) & 0xFFu) | (((g >> 16) & 0xFFu) << 8) | (((b >> 16) & 0xFFu) << 16) | (w & 0xFF000000u);
+  }
+}
+
+}  // namespace nvpyr
