@@ -49,6 +49,7 @@ static uint32_t f2b(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
 
 int main()
 {
+  setvbuf(stdout, NULL, _IONBF, 0);
   // ---------- (1) decode table ----------
   const int w = 256, h = 4;
   uint8_t* himg = (uint8_t*)malloc(w * h * 4);
