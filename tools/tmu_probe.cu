@@ -116,7 +116,7 @@ int main()
   printf("(2) bilinear @ quad centre, %ld rgb samples: == f32 vertical-pair avg of HW LUT %.4f%%, == horizontal-pair %.4f%%, == exact-sum rounded %.4f%%, max |diff| vs exact avg of HW LUT %.3e\n",
          n, 100.0 * eqV / n, 100.0 * eqH / n, 100.0 * eqD / n, maxd);
   printf("    vs pinned-table software path: bit-equal %.4f%%, max |diff| %.3e\n", 100.0 * eqPinned / n, maxdPinned);
-  for(int i = 0; i < 4; ++i) { int x = 37 + i * 91, y = 600 + i * 13; float got = hq[(size_t)y * (W / 2) + x].x; const uint8_t* p00 = big + 4 * ((size_t)(2 * y) * W + 2 * x);
+  for(int i = 0; i < 4; ++i) { int x = 37 + i * 91, y = 300 + i * 13; float got = hq[(size_t)y * (W / 2) + x].x; const uint8_t* p00 = big + 4 * ((size_t)(2 * y) * W + 2 * x);
     double ex = 0.25 * ((double)hwlut[p00[0]] + hwlut[p00[4]] + hwlut[p00[4 * W]] + hwlut[p00[4 * W + 4]]); printf("    sample: got %.10g (%08x) exact-avg %.10g\n", got, f2b(got), ex); }
 
   // ---------- (3) throughput ----------

@@ -3,11 +3,15 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <atomic>
+#include <type_traits>
 #include <mutex>
 #include <vector>
 
 #include "../../include/nvpyr.h"
+#include "nvpyr_fast_srgba8.cuh"
 #include "nvpyr_kernels.cuh"
 #include "nvpyr_plan.hpp"
 #include "srgb_tables.inc"
@@ -16,6 +20,12 @@ namespace nvpyr {
 namespace {
 
 thread_local int      g_lastCudaError = 0;
+// NVPYR_GENERIC_FAST=1 routes sRGBA8 through the generic functor kernel (fastKernel<Srgba8, M>)
+// instead of the tuned one; both must produce the same bits (tests/test_gpu_parity.py).
+const bool g_forceGenericFast = [] {
+  const char* e = getenv("NVPYR_GENERIC_FAST");
+  return e != nullptr && e[0] == '1';
+}();
 std::atomic<uint64_t> g_launchCount{0};
 
 #define NVPYR_CUDA(call)                                                                                          \
@@ -117,12 +127,12 @@ nvpyrStatus getContext(DeviceContext** out)
 
 // ------------------------------------------------------------------ launches
 template <class K>
-nvpyrStatus persistentGrid(K kernel, size_t smem, int smCount, uint64_t workItems, int* grid)
+nvpyrStatus persistentGrid(K kernel, size_t smem, int smCount, uint64_t workItems, int* grid, int threads = 256)
 {
   // Opt in to > 48 KB of dynamic shared memory (idempotent, cheap).
   NVPYR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int perSm = 0;
-  NVPYR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, 256, smem));
+  NVPYR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, smem));
   if(perSm < 1)
     return NVPYR_ERROR_UNSUPPORTED;
   uint64_t g = uint64_t(perSm) * uint64_t(smCount);
@@ -141,6 +151,23 @@ nvpyrStatus launchFastT(const DeviceContext& ctx, const FastParams& p, cudaStrea
   if(st != NVPYR_SUCCESS)
     return st;
   fastKernel<F, M, kVec><<<grid, 256, smem, stream>>>(p);
+  NVPYR_CUDA(cudaGetLastError());
+  ++g_launchCount;
+  return NVPYR_SUCCESS;
+}
+
+// The tuned sRGBA8 kernel (nvpyr_fast_srgba8.cuh): 128x64 tiles, 512 threads.
+template <int M>
+nvpyrStatus launchFastSrgba8T(const DeviceContext& ctx, FastParams p, cudaStream_t stream)
+{
+  p.tilesX          = (p.lv[0].w + 127u) / 128u;
+  p.tilesY          = (p.lv[0].h + 63u) / 64u;
+  const size_t smem = sizeof(Srgba8FastSmem);
+  int          grid = 1;
+  nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M>, smem, ctx.smCount, uint64_t(p.tilesX) * p.tilesY, &grid, 512);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  fastSrgba8Kernel<M><<<grid, 512, smem, stream>>>(p);
   NVPYR_CUDA(cudaGetLastError());
   ++g_launchCount;
   return NVPYR_SUCCESS;
@@ -172,6 +199,8 @@ nvpyrStatus launchFast(const DeviceContext& ctx, FastParams p, uint32_t M, cudaS
                    && (reinterpret_cast<uintptr_t>(p.lv[1].ptr) % a1 == 0) && (p.lv[1].pitch % a1 == 0);
 #define NVPYR_FAST_CASE(m)                                                                                        \
   case m:                                                                                                         \
+    if(std::is_same<F, Srgba8>::value && vec && !g_forceGenericFast)                                              \
+      return launchFastSrgba8T<m>(ctx, p, stream);                                                                \
     return vec ? launchFastT<F, m, true>(ctx, p, stream) : launchFastT<F, m, false>(ctx, p, stream);
   switch(M)
   {
