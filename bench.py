@@ -173,6 +173,57 @@ def run_reference_arm(args):
     return 0
 
 
+# ----------------------------------------------------------------------------- synthetic inputs
+def fill_julia(level0, w, h):
+    """Julia-set texture of the reference demo (shaders/julia.comp:27-63 with demo_app/julia.cpp:65-81's
+    constants, maxIterations 64) written into level0 (uint8 [h, w, 4] CUDA view), tile by tile."""
+    import math
+    import torch
+    alpha = 2109710467 * 1.4629180792671596e-09
+    cr, ci = float(0.7885 * math.sin(alpha)), float(0.7885 * math.cos(alpha))
+    scale, off_r, off_i, max_it = 4.0 / w, -2.0, 2.0 * h / w, 64
+    dev = level0.device
+    rows = 1024
+    xs = torch.arange(w, device=dev, dtype=torch.float32) * scale + off_r
+    for y0 in range(0, h, rows):
+        ys = torch.arange(y0, min(h, y0 + rows), device=dev, dtype=torch.float32) * -scale + off_i
+        zr = xs[None, :].expand(ys.numel(), w).clone()
+        zi = ys[:, None].expand(ys.numel(), w).clone()
+        it = torch.zeros_like(zr, dtype=torch.int32)
+        alive = torch.ones_like(zr, dtype=torch.bool)
+        for _ in range(max_it):
+            alive &= (zr * zr + zi * zi) <= 4
+            tr = zr * zr - zi * zi + cr
+            ti = 2 * zr * zi + ci
+            zr = torch.where(alive, tr, zr)
+            zi = torch.where(alive, ti, zi)
+            it += alive.to(torch.int32)
+        itf = it.to(torch.float32)
+        low = it < 16
+        s = (4 + itf) * 0.05
+        n = torch.clamp(127.0 * (itf - 16) / torch.clamp(max_it - itf, min=1.0), 0, 255).floor()
+        out = level0[y0:y0 + ys.numel()]
+        out[..., 0] = torch.where(low, torch.zeros_like(s), n).to(torch.uint8)
+        out[..., 1] = torch.where(low, 128 * s, 128 + torch.floor(n / 4)).to(torch.uint8)
+        out[..., 2] = torch.where(low, 255 * s, 255 - n).to(torch.uint8)
+        out[..., 3] = torch.where(low, 255 * s, torch.full_like(s, 255)).to(torch.uint8)
+
+
+def fill_gradient(level0, w, h):
+    """Opaque smooth gradient with a little dither (low-entropy case)."""
+    import torch
+    dev = level0.device
+    x = torch.arange(w, device=dev, dtype=torch.float32)[None, :]
+    for y0 in range(0, h, 2048):
+        y = torch.arange(y0, min(h, y0 + 2048), device=dev, dtype=torch.float32)[:, None]
+        out = level0[y0:y0 + y.numel()]
+        d = ((x.to(torch.int32) * 7 + y.to(torch.int32) * 13) & 3).to(torch.float32)
+        out[..., 0] = (x * (255.0 / w) + d * 0.25).expand(y.numel(), w).to(torch.uint8)
+        out[..., 1] = (y * (255.0 / h) + d * 0.25).expand(y.numel(), w).to(torch.uint8)
+        out[..., 2] = (127.5 + 127.5 * torch.sin(x / 97.0) * torch.cos(y / 131.0)).to(torch.uint8)
+        out[..., 3] = 255
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_gpu_arm(args):
     import numpy as np
@@ -245,6 +296,26 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     assert nv.launch_count() - l0 == args.steps
     k_ms = kev0.elapsed_time(kev1) / args.steps
+
+    # ---- same chain on the other synthetic inputs of SURVEY 8d (bytes moved are identical) ----
+    other_inputs = {}
+    if rank == 0 and not args.no_other_inputs:
+        for name, fill in (("julia", fill_julia), ("gradient", fill_gradient)):
+            fill(bufs[0][:4 * W * H].view(H, W, 4), W, H)
+            bufs[1][:4 * W * H].copy_(bufs[0][:4 * W * H])
+            for i in range(3):
+                step(i)
+            torch.cuda.synchronize()
+            oev0, oev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_o = max(4, min(args.steps, 10))
+            oev0.record(stream)
+            for i in range(n_o):
+                step(i)
+            oev1.record(stream)
+            torch.cuda.synchronize()
+            o_ms = oev0.elapsed_time(oev1) / n_o
+            other_inputs[name] = {"us_per_chain": 1e3 * o_ms, "GBps": chain_bytes / (o_ms * 1e-3) / 1e9,
+                                  "frac_of_hbm_peak": None}
     t_wall2 = time.time()
 
     # ---- end to end through the host-buffer entry point (nvpyrGenerateHost): H2D level 0 + D2H chain ----
@@ -285,6 +356,8 @@ def run_gpu_arm(args):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
+    for v in other_inputs.values():
+        v["frac_of_hbm_peak"] = v["GBps"] / peak
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath):
@@ -300,7 +373,9 @@ def run_gpu_arm(args):
                                "(BASELINE configs[2])",
                    "algorithmic_bytes_per_step": chain_bytes, "us_per_chain": 1e3 * ms_per_step,
                    "l2_policy": "inputs larger than L2: two distinct 1.43 GB chains alternated",
-                   "per_rank": "one chain per step per rank, no collective", "launches_per_chain": launches / args.steps},
+                   "per_rank": "one chain per step per rank, no collective", "launches_per_chain": launches / args.steps,
+                   "input": "uniform random bytes, all four channels (worst case for the encode table's bank conflicts)",
+                   "other_inputs": other_inputs},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "fastKernel<Srgba8,6> (level 0 -> levels 1..6)",
                      "algorithmic_bytes_per_launch": k_bytes, "us_per_launch": 1e3 * k_ms, "peak_source": peak_src},
@@ -319,6 +394,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-inputs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -58,6 +58,53 @@ def test_srgba8_bit_exact_vs_shader_order_oracle(nv, cuda, oracle, size):
         assert_same(got, want, w, h, oracle, "srgba8")
 
 
+@pytest.mark.parametrize("size", [(256, 256), (4096, 64), (192, 320), (136, 512), (260, 260), (63, 63)],
+                         ids=lambda s: f"{s[0]}x{s[1]}")
+def test_dark_and_sparse_images_bit_exact(nv, cuda, oracle, size):
+    """Exact zeros, the smallest non-zero sums (isolated code-1 texels) and saturated texels: the
+    edge cases of the clamp-free encode table of the tuned kernel."""
+    w, h = size
+    rng = np.random.default_rng(w * 7 + h)
+    images = [np.zeros(4 * w * h, dtype=np.uint8), np.full(4 * w * h, 255, dtype=np.uint8)]
+    sparse = np.zeros(4 * w * h, dtype=np.uint8)
+    idx = rng.integers(0, sparse.size, sparse.size // 97)
+    sparse[idx] = 1
+    images.append(sparse)
+    low = rng.integers(0, 3, 4 * w * h, dtype=np.uint8)
+    images.append(low)
+    spikes = np.zeros(4 * w * h, dtype=np.uint8)
+    spikes[rng.integers(0, spikes.size, 40)] = 255
+    images.append(spikes)
+    for l0 in images:
+        want, _ = oracle.shader_chain(l0, w, h)
+        got = gpu_chain(nv, cuda, l0, w, h)
+        assert_same(got, want, w, h, oracle, "dark/sparse")
+
+
+def test_generic_functor_kernel_matches_tuned_kernel(nv, cuda, oracle):
+    """NVPYR_GENERIC_FAST=1 routes sRGBA8 through fastKernel<Srgba8, M> (the functor-template kernel a user
+    instance would get); it must give the same bits as the tuned kernel.  Runs in a subprocess because the
+    switch is read once at library load."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import vk_compute_mipmaps_b200 as nv, _oracle\n"
+        "o = _oracle.load_oracle()\n"
+        "for (w, h) in [(256, 256), (192, 64), (120, 72), (64, 4096)]:\n"
+        "    l0 = _oracle.random_level0(w, h, 3)\n"
+        "    buf = torch.zeros(nv.chain_bytes(w, h), dtype=torch.uint8, device='cuda')\n"
+        "    buf[:4 * w * h] = torch.from_numpy(l0).cuda()\n"
+        "    nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(), w, h, image=buf)\n"
+        "    torch.cuda.synchronize()\n"
+        "    assert (buf.cpu().numpy() == o.shader_chain(l0, w, h)[0]).all(), (w, h)\n"
+        "print('generic ok')\n") % (_oracle.ROOT, os.path.join(_oracle.ROOT, "tests"))
+    env = dict(os.environ, NVPYR_GENERIC_FAST="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "generic ok" in out.stdout, out.stderr[-2000:]
+
+
 @pytest.mark.parametrize("size", [(64, 64), (256, 256), (96, 160), (100, 37), (260, 260), (1, 9)],
                          ids=lambda s: f"{s[0]}x{s[1]}")
 def test_force_general_bit_exact(nv, cuda, oracle, size):

@@ -156,11 +156,11 @@ nvpyrStatus launchFastT(const DeviceContext& ctx, const FastParams& p, cudaStrea
   return NVPYR_SUCCESS;
 }
 
-// The tuned sRGBA8 kernel (nvpyr_fast_srgba8.cuh): 128x64 tiles, 512 threads.
+// The tuned sRGBA8 kernel (nvpyr_fast_srgba8.cuh): warp-autonomous 64x64 tiles, 16 warps per CTA.
 template <int M>
 nvpyrStatus launchFastSrgba8T(const DeviceContext& ctx, FastParams p, cudaStream_t stream)
 {
-  p.tilesX          = (p.lv[0].w + 127u) / 128u;
+  p.tilesX          = (p.lv[0].w + 63u) / 64u;  // one warp per 64x64 tile
   p.tilesY          = (p.lv[0].h + 63u) / 64u;
   const size_t smem = sizeof(Srgba8FastSmem);
   int          grid = 1;
