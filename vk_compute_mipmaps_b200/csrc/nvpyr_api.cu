@@ -6,7 +6,9 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <map>
 #include <type_traits>
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -24,6 +26,11 @@ thread_local int      g_lastCudaError = 0;
 // instead of the tuned one; both must produce the same bits (tests/test_gpu_parity.py).
 const bool g_forceGenericFast = [] {
   const char* e = getenv("NVPYR_GENERIC_FAST");
+  return e != nullptr && e[0] == '1';
+}();
+// NVPYR_NO_TAIL_FUSION=1: one launch per reference dispatch (no cooperative tail kernel).
+const bool g_noTailFusion = [] {
+  const char* e = getenv("NVPYR_NO_TAIL_FUSION");
   return e != nullptr && e[0] == '1';
 }();
 std::atomic<uint64_t> g_launchCount{0};
@@ -72,15 +79,22 @@ bool buildHostTables(DeviceTables& t)
     }
     t.encode[key - kEncMinKey] = entry - lo;  // pre-biased: kernel adds the full bit pattern
   }
+  for(uint32_t i = kEncEntries; i < kEncEntriesPadded; ++i)
+    t.encode[i] = 0;
   return true;
 }
 
 // ------------------------------------------------------------ device context
+// Tail launches in flight at the same time each need their own ticket counter.
+constexpr uint32_t kTicketPool = 4096;
+
 struct DeviceContext
 {
   int           device   = -1;
   int           smCount  = 0;
   DeviceTables* tables   = nullptr;
+  uint32_t*     tickets  = nullptr;  // kTicketPool zero-initialised counters for tailKernel
+  std::atomic<uint32_t> nextTicket{0};
   void*         scratch  = nullptr;  // nvpyrGenerateHost staging chain
   size_t        scratchBytes = 0;
   std::mutex    scratchMutex;
@@ -116,26 +130,60 @@ nvpyrStatus getContext(DeviceContext** out)
     g_lastCudaError = int(e);
     return NVPYR_ERROR_CUDA;
   }
+  uint32_t* tickets = nullptr;
+  e                 = cudaMalloc(&tickets, kTicketPool * sizeof(uint32_t));
+  if(e == cudaSuccess)
+    e = cudaMemset(tickets, 0, kTicketPool * sizeof(uint32_t));
+  if(e != cudaSuccess)
+  {
+    cudaFree(d);
+    cudaFree(tickets);
+    g_lastCudaError = int(e);
+    return NVPYR_ERROR_CUDA;
+  }
   DeviceContext* c = new DeviceContext;
   c->device        = dev;
   c->smCount       = prop.multiProcessorCount;
   c->tables        = d;
+  c->tickets       = tickets;
   g_ctx.push_back(c);
   *out = c;
   return NVPYR_SUCCESS;
 }
 
 // ------------------------------------------------------------------ launches
-template <class K>
-nvpyrStatus persistentGrid(K kernel, size_t smem, int smCount, uint64_t workItems, int* grid, int threads = 256)
+// Blocks per SM of a kernel (and the > 48 KB shared-memory opt-in), cached per (kernel, device):
+// the two runtime calls cost several microseconds, as much as a small launch.
+nvpyrStatus blocksPerSm(const void* kernel, size_t smem, int threads, int device, int* perSm)
 {
-  // Opt in to > 48 KB of dynamic shared memory (idempotent, cheap).
+  static std::mutex                                  m;
+  static std::map<std::pair<const void*, int>, int>  cache;
+  std::lock_guard<std::mutex>                        lock(m);
+  auto                                               it = cache.find({kernel, device});
+  if(it != cache.end())
+  {
+    *perSm = it->second;
+    return NVPYR_SUCCESS;
+  }
   NVPYR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  int perSm = 0;
-  NVPYR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, smem));
-  if(perSm < 1)
+  int n = 0;
+  NVPYR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem));
+  if(n < 1)
     return NVPYR_ERROR_UNSUPPORTED;
-  uint64_t g = uint64_t(perSm) * uint64_t(smCount);
+  cache[{kernel, device}] = n;
+  *perSm                  = n;
+  return NVPYR_SUCCESS;
+}
+
+template <class K>
+nvpyrStatus persistentGrid(K kernel, size_t smem, const DeviceContext& ctx, uint64_t workItems, int* grid,
+                           int threads = 256)
+{
+  int         perSm = 0;
+  nvpyrStatus st    = blocksPerSm(reinterpret_cast<const void*>(kernel), smem, threads, ctx.device, &perSm);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  uint64_t g = uint64_t(perSm) * uint64_t(ctx.smCount);
   if(g > workItems)
     g = workItems;
   *grid = int(g < 1 ? 1 : g);
@@ -147,7 +195,7 @@ nvpyrStatus launchFastT(const DeviceContext& ctx, const FastParams& p, cudaStrea
 {
   const size_t smem = sizeof(FastSmem<F>);
   int          grid = 1;
-  nvpyrStatus  st   = persistentGrid(fastKernel<F, M, kVec>, smem, ctx.smCount, uint64_t(p.tilesX) * p.tilesY, &grid);
+  nvpyrStatus  st   = persistentGrid(fastKernel<F, M, kVec>, smem, ctx, uint64_t(p.tilesX) * p.tilesY, &grid);
   if(st != NVPYR_SUCCESS)
     return st;
   fastKernel<F, M, kVec><<<grid, 256, smem, stream>>>(p);
@@ -156,15 +204,26 @@ nvpyrStatus launchFastT(const DeviceContext& ctx, const FastParams& p, cudaStrea
   return NVPYR_SUCCESS;
 }
 
+// Vector path of the fast kernels: 16-byte aligned input rows, output rows of level +1 aligned
+// for a two-texel store.
+template <class F>
+bool fastVectorOk(const LevelView* lv)
+{
+  const uint32_t a1 = 2u * F::kTexelBytes > 16u ? 16u : 2u * F::kTexelBytes;
+  return (reinterpret_cast<uintptr_t>(lv[0].ptr) % 16u == 0) && (lv[0].pitch % 16u == 0)
+         && (reinterpret_cast<uintptr_t>(lv[1].ptr) % a1 == 0) && (lv[1].pitch % a1 == 0);
+}
+
 // The tuned sRGBA8 kernel (nvpyr_fast_srgba8.cuh): warp-autonomous 64x64 tiles, 16 warps per CTA.
 template <int M>
 nvpyrStatus launchFastSrgba8T(const DeviceContext& ctx, FastParams p, cudaStream_t stream)
 {
-  p.tilesX          = (p.lv[0].w + 63u) / 64u;  // one warp per 64x64 tile
-  p.tilesY          = (p.lv[0].h + 63u) / 64u;
+  constexpr uint32_t tileH = M >= 3 ? (1u << M) : 8u;  // one warp per 64 x tileH tile
+  p.tilesX                 = (p.lv[0].w + 63u) / 64u;
+  p.tilesY                 = (p.lv[0].h + tileH - 1u) / tileH;
   const size_t smem = sizeof(Srgba8FastSmem);
   int          grid = 1;
-  nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M>, smem, ctx.smCount, uint64_t(p.tilesX) * p.tilesY, &grid, 512);
+  nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M>, smem, ctx, uint64_t(p.tilesX) * p.tilesY, &grid, 512);
   if(st != NVPYR_SUCCESS)
     return st;
   fastSrgba8Kernel<M><<<grid, 512, smem, stream>>>(p);
@@ -182,7 +241,7 @@ nvpyrStatus launchFast(const DeviceContext& ctx, FastParams p, uint32_t M, cudaS
     const size_t   smem  = sizeof(FastSmem<F>);
     const uint64_t items = (uint64_t(p.lv[1].w) * p.lv[1].h + 255u) / 256u;
     int            grid  = 1;
-    nvpyrStatus    st    = persistentGrid(fastKernel1<F>, smem, ctx.smCount, items, &grid);
+    nvpyrStatus    st    = persistentGrid(fastKernel1<F>, smem, ctx, items, &grid);
     if(st != NVPYR_SUCCESS)
       return st;
     fastKernel1<F><<<grid, 256, smem, stream>>>(p);
@@ -192,11 +251,7 @@ nvpyrStatus launchFast(const DeviceContext& ctx, FastParams p, uint32_t M, cudaS
   }
   p.tilesX = (p.lv[0].w + 63u) / 64u;
   p.tilesY = (p.lv[0].h + 63u) / 64u;
-  // Vector path: 16-byte aligned input rows, output rows of level +1 aligned for a
-  // two-texel store.
-  const uint32_t a1 = 2u * F::kTexelBytes > 16u ? 16u : 2u * F::kTexelBytes;
-  const bool vec = (reinterpret_cast<uintptr_t>(p.lv[0].ptr) % 16u == 0) && (p.lv[0].pitch % 16u == 0)
-                   && (reinterpret_cast<uintptr_t>(p.lv[1].ptr) % a1 == 0) && (p.lv[1].pitch % a1 == 0);
+  const bool vec = fastVectorOk<F>(p.lv);
 #define NVPYR_FAST_CASE(m)                                                                                        \
   case m:                                                                                                         \
     if(std::is_same<F, Srgba8>::value && vec && !g_forceGenericFast)                                              \
@@ -214,23 +269,22 @@ nvpyrStatus launchFast(const DeviceContext& ctx, FastParams p, uint32_t M, cudaS
 #undef NVPYR_FAST_CASE
 }
 
+inline void generalTiles(const LevelView* lv, uint32_t levels, uint32_t tile2, uint32_t* tx, uint32_t* ty)
+{
+  const LevelView& out = levels == 1 ? lv[1] : lv[2];
+  const uint32_t   t   = levels == 1 ? 2u * tile2 : tile2;
+  *tx                  = (out.w + t - 1u) / t;
+  *ty                  = (out.h + t - 1u) / t;
+}
+
 template <class F>
 nvpyrStatus launchGeneral(const DeviceContext& ctx, GeneralParams p, cudaStream_t stream)
 {
   p.tables = ctx.tables;
-  if(p.levels == 1)
-  {
-    p.tilesX = (p.lv[1].w + 31u) / 32u;
-    p.tilesY = (p.lv[1].h + 31u) / 32u;
-  }
-  else
-  {
-    p.tilesX = (p.lv[2].w + kGenTile2 - 1) / kGenTile2;
-    p.tilesY = (p.lv[2].h + kGenTile2 - 1) / kGenTile2;
-  }
+  generalTiles(p.lv, p.levels, kGenTile2, &p.tilesX, &p.tilesY);
   const size_t smem = sizeof(GeneralSmem<F>);
   int          grid = 1;
-  nvpyrStatus  st   = persistentGrid(generalKernel<F>, smem, ctx.smCount, uint64_t(p.tilesX) * p.tilesY, &grid);
+  nvpyrStatus  st   = persistentGrid(generalKernel<F>, smem, ctx, uint64_t(p.tilesX) * p.tilesY, &grid);
   if(st != NVPYR_SUCCESS)
     return st;
   generalKernel<F><<<grid, 256, smem, stream>>>(p);
@@ -244,7 +298,7 @@ nvpyrStatus launchPremultiply(const DeviceContext& ctx, const void* in, void* ou
 {
   const size_t smem = sizeof(Srgba8::Shared);
   int          grid = 1;
-  nvpyrStatus  st   = persistentGrid(premultiplyKernel, smem, ctx.smCount, (texels + 255u) / 256u, &grid);
+  nvpyrStatus  st   = persistentGrid(premultiplyKernel, smem, ctx, (texels + 255u) / 256u, &grid);
   if(st != NVPYR_SUCCESS)
     return st;
   premultiplyKernel<<<grid, 256, smem, stream>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out),
@@ -322,31 +376,102 @@ nvpyrStatus resolve(const nvpyrDispatchDesc* d, ResolvedDesc& r)
   return NVPYR_SUCCESS;
 }
 
+// Steps whose input level has at most kTailMaxTexels texels are candidates for tailKernel: a
+// "grid step" spread over all CTAs followed by "solo" steps (input <= kSoloMaxTexels) that the
+// last CTA runs alone.
+constexpr uint64_t kTailMaxTexels = 512ull * 512ull;
+constexpr uint64_t kSoloMaxTexels = 64ull * 64ull;
+
 template <class F>
-nvpyrStatus runPlan(const DeviceContext& ctx, const ResolvedDesc& r)
+struct TailFunctors
+{
+  using type = F;
+};
+template <>
+struct TailFunctors<Srgba8>
+{
+  using type = Srgba8Lite;  // small levels: 1 KB decode table, cheap to set up
+};
+
+// One tail launch: steps[0] on the whole grid, steps[1..count) solo.
+template <class F>
+nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPlanStep* steps, int count)
+{
+  using TF = typename TailFunctors<F>::type;
+  TailParams tp{};
+  tp.numSteps = uint32_t(count);
+  tp.tables   = ctx.tables;
+  tp.ticket   = ctx.tickets + (ctx.nextTicket.fetch_add(1) % kTicketPool);
+  for(int i = 0; i < count; ++i)
+  {
+    const nvpyrPlanStep& s  = steps[i];
+    TailStep&            ts = tp.steps[i];
+    ts.pipeline             = s.pipeline;
+    ts.levels               = s.levelCount;
+    for(uint32_t k = 0; k <= s.levelCount; ++k)
+      ts.lv[k] = r.lv[s.inputLevel + k];
+    if(s.pipeline == 1)
+    {
+      ts.vec    = fastVectorOk<F>(ts.lv) ? 1u : 0u;
+      ts.tilesX = (ts.lv[0].w + 63u) / 64u;
+      ts.tilesY = (ts.lv[0].h + 63u) / 64u;
+    }
+    else
+      generalTiles(ts.lv, s.levelCount, kGenTile2Small, &ts.tilesX, &ts.tilesY);
+  }
+  uint64_t work = uint64_t(tp.steps[0].tilesX) * tp.steps[0].tilesY;
+  if(tp.steps[0].pipeline == 1 && tp.steps[0].levels == 1)  // fastLoop1 is thread-strided, not tiled
+    work = (uint64_t(tp.steps[0].lv[1].w) * tp.steps[0].lv[1].h + 255u) / 256u;
+  const size_t smem = sizeof(TailSmem<TF>);
+  int          grid = 1;
+  nvpyrStatus  st   = persistentGrid(tailKernel<TF>, smem, ctx, work, &grid);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  tailKernel<TF><<<grid, 256, smem, r.stream>>>(tp);
+  NVPYR_CUDA(cudaGetLastError());
+  ++g_launchCount;
+  return NVPYR_SUCCESS;
+}
+
+template <class F>
+nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r)
 {
   nvpyrPlanStep steps[NVPYR_MAX_STEPS];
   const int     n = buildPlan(r.w, r.h, r.levels, defaultGeneralDispatcher, r.fast, steps, NVPYR_MAX_STEPS);
   if(n < 0)
     return NVPYR_ERROR_INVALID_VALUE;
-  for(int i = 0; i < n; ++i)
+  auto texels = [&](int i) { return uint64_t(steps[i].srcWidth) * steps[i].srcHeight; };
+  for(int i = 0; i < n;)
   {
     const nvpyrPlanStep& s = steps[i];
     nvpyrStatus          st;
-    if(s.pipeline == 1)
+    if(!g_noTailFusion && texels(i) <= kTailMaxTexels)
     {
-      FastParams p{};
-      for(uint32_t k = 0; k <= s.levelCount; ++k)
-        p.lv[k] = r.lv[s.inputLevel + k];
-      st = launchFast<F>(ctx, p, s.levelCount, r.stream);
+      // grid step i, then as many solo steps as follow (level sizes only shrink)
+      int count = 1;
+      while(i + count < n && texels(i + count) <= kSoloMaxTexels && count < int(kMaxTailSteps))
+        ++count;
+      st = launchTail<F>(ctx, r, steps + i, count);
+      i += count;
     }
     else
     {
-      GeneralParams p{};
-      for(uint32_t k = 0; k <= s.levelCount; ++k)
-        p.lv[k] = r.lv[s.inputLevel + k];
-      p.levels = s.levelCount;
-      st       = launchGeneral<F>(ctx, p, r.stream);
+      if(s.pipeline == 1)
+      {
+        FastParams p{};
+        for(uint32_t k = 0; k <= s.levelCount; ++k)
+          p.lv[k] = r.lv[s.inputLevel + k];
+        st = launchFast<F>(ctx, p, s.levelCount, r.stream);
+      }
+      else
+      {
+        GeneralParams p{};
+        for(uint32_t k = 0; k <= s.levelCount; ++k)
+          p.lv[k] = r.lv[s.inputLevel + k];
+        p.levels = s.levelCount;
+        st       = launchGeneral<F>(ctx, p, r.stream);
+      }
+      ++i;
     }
     if(st != NVPYR_SUCCESS)
       return st;
@@ -631,6 +756,7 @@ nvpyrStatus nvpyrShutdown(void)
   {
     cudaSetDevice(c->device);
     cudaFree(c->tables);
+    cudaFree(c->tickets);
     if(c->scratch)
       cudaFree(c->scratch);
     delete c;

@@ -20,19 +20,23 @@
 //  * level +3 is a "transpose-reduce": in two shuffle steps the four threads of a 2x2 block
 //    end up holding ONE channel each of the common result (3 SHFL + 3 FADD per thread
 //    instead of 12 + 12), encode it in parallel and gather the four bytes with two PRMTs.
-//  * warp-autonomous tiles: one WARP owns a 64x64 input tile and walks it as eight 64x8
-//    slabs (lane = 4x4 texels), keeping the level +3 sums in a 1 KB warp-private shared
-//    tile; levels +4..+6 are finished by the same warp.  No CTA-wide barrier exists after
-//    the table set-up (the v2 kernel lost 13 % of its warp time at one).
+//  * warp-autonomous tiles: one WARP owns a 64 x max(8, 2^M) input tile and walks it as
+//    64x8 slabs (lane = 4x4 texels), keeping the level +3 sums in a 1 KB warp-private shared
+//    tile; levels +4..+M are finished by the same warp.  No CTA-wide barrier exists after
+//    the table set-up (the v2 kernel lost 13 % of its warp time at one).  Tiles are only as
+//    tall as the step needs, so steps with M < 6 expose 2-8x more independent warp tasks.
 //  * the next slab's four 16-byte rows are prefetched into registers before the current
 //    slab is processed.
 //
 // CTA = 512 threads = 16 warps sharing the tables; two CTAs per SM.
 #pragma once
+#include <stddef.h>
+
 #include "nvpyr_kernels.cuh"
 
 namespace nvpyr {
 
+constexpr int      kFastWarps     = 16;
 constexpr int      kDecScaleExp   = 100;  // decode table holds 2^-100 * linearFromSrgb(code)
 constexpr uint32_t kEncLowOctaves = 11;   // bucket table extended below 2^-13 down to d(1) / 4^6
 constexpr uint32_t kEncMinKeyExt  = kEncMinKey - kEncLowOctaves * (1u << (23 - kEncShift));
@@ -42,9 +46,11 @@ struct Srgba8FastSmem
 {
   float    decode[256 * 64];        // [code][64]: floats 0..31 = per-lane copies, 32..63 spare (zero words live there)
   float    pad[32];                 // keeps the zero words in the spare halves (see encScaled)
-  uint32_t encode[kEncEntriesExt];  // bucket table (nvpyr_functors.cuh), extended downwards
+  alignas(16) uint32_t encode[kEncEntriesExt + 3];  // bucket table (nvpyr_functors.cuh), extended downwards
   alignas(16) float l3[16][8][8][4];  // per warp: level +3 sums of its 64x64 tile, [slab][x][channel]
 };
+
+static_assert(offsetof(Srgba8FastSmem, encode) == 65536 + 128, "encScaled's zero words assume this layout");
 
 // Per-level constants of the scaled encode.  The carried value is S' = 2^-E * 4^K * x, so
 // bits(x) = bits(S') + ((E - 2K) << 23) and key(x) = key(S') + (E - 2K) * 256.
@@ -76,9 +82,11 @@ __device__ __forceinline__ void srgba8FastInit(Srgba8FastSmem& sm, const DeviceT
     d[0] = v4, d[1] = v4, d[2] = v4, d[3] = v4;
   }
   constexpr uint32_t kLow = kEncEntriesExt - kEncEntries;
-  for(uint32_t i = threadIdx.x; i < kEncEntriesExt; i += blockDim.x)
-    sm.encode[i] = i < kLow ? 0u - ((kEncMinKeyExt + i) << kEncShift)  // code 0, no threshold, pre-biased
-                            : __ldg(&t->encode[i - kLow]);
+  static_assert(kLow % 4 == 0, "upper part of the table must stay 16-byte aligned");
+  for(uint32_t i = threadIdx.x; i < kLow; i += blockDim.x)
+    sm.encode[i] = 0u - ((kEncMinKeyExt + i) << kEncShift);  // code 0, no threshold, pre-biased
+  copyTableWide<kFastWarps * 32>(reinterpret_cast<uint4*>(&sm.encode[kLow]),
+                                 reinterpret_cast<const uint4*>(t->encode), kEncEntriesPadded / 4);
   if(threadIdx.x == 0)
   {
     putZeroWord<1>(sm), putZeroWord<2>(sm), putZeroWord<3>(sm);
@@ -147,8 +155,6 @@ __device__ __forceinline__ float4 sum4Paired(bool horizontal, float4 ul, float4 
   return f4add(p, q);
 }
 
-constexpr int kFastWarps = 16;
-
 template <int M>
 __global__ void __launch_bounds__(kFastWarps * 32, 2) fastSrgba8Kernel(const FastParams p)
 {
@@ -187,8 +193,9 @@ __global__ void __launch_bounds__(kFastWarps * 32, 2) fastSrgba8Kernel(const Fas
     const unsigned char* src;
     bool                 active;
   };
+  constexpr uint32_t kTileH = M >= 3 ? (1u << M) : 8u, kSlabs = kTileH / 8u;
   auto tileCursor = [&](uint32_t t) {
-    const uint32_t x0 = (t % p.tilesX) * 64u + tx * 4u, y0 = (t / p.tilesX) * 64u + ty * 4u;
+    const uint32_t x0 = (t % p.tilesX) * 64u + tx * 4u, y0 = (t / p.tilesX) * kTileH + ty * 4u;
     Cursor         c;
     c.src    = p.lv[0].ptr + size_t(y0) * pitch0 + size_t(x0) * 4u;
     c.active = t < numTiles && x0 < W && y0 < H;
@@ -210,20 +217,20 @@ __global__ void __launch_bounds__(kFastWarps * 32, 2) fastSrgba8Kernel(const Fas
   {
     const uint32_t tileX = tile % p.tilesX, tileY = tile / p.tilesX;
     const uint32_t x0 = tileX * 64u + tx * 4u;
-    uint32_t       y0 = tileY * 64u + ty * 4u;
+    uint32_t       y0 = tileY * kTileH + ty * 4u;
     // Output cursors of this lane (advance by one slab = 8 input rows per iteration).
     unsigned char* d1 = p.lv[1].ptr + size_t(y0 >> 1) * pitch1 + size_t(x0 >> 1) * 4u;
     unsigned char* d2 = p.lv[2].ptr + size_t(y0 >> 2) * pitch2 + size_t(x0 >> 2) * 4u;
     unsigned char* d3 = M >= 3 ? p.lv[3].ptr + size_t(y0 >> 3) * p.lv[3].pitch + size_t(x0 >> 3) * 4u : nullptr;
     const Cursor   nextTile = tileCursor(tile + tileStep);
 #pragma unroll 1
-    for(uint32_t slab = 0; slab < 8u; ++slab, y0 += 8u, d1 += 4u * pitch1, d2 += 2u * pitch2)
+    for(uint32_t slab = 0; slab < kSlabs; ++slab, y0 += 8u, d1 += 4u * pitch1, d2 += 2u * pitch2)
     {
       // Edges are multiples of 2^M >= 4: a 4x4 block is entirely inside or outside.
       const bool  active = nxt.active;
       const uint4 c0 = row[0], c1 = row[1], c2 = row[2], c3 = row[3];
       // prefetch the next slab (of this tile, or the first one of this warp's next tile)
-      if(slab < 7u)
+      if(slab + 1u < kSlabs)
       {
         nxt.src += 8u * pitch0;
         nxt.active = x0 < W && y0 + 8u < H;
@@ -277,8 +284,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 2) fastSrgba8Kernel(const Fas
       __syncwarp();
       // 16 lanes <-> 4 x 4 texels of level +4; +5 and +6 with butterflies.
       const uint32_t i = lane & 3u, j = (lane >> 2) & 3u;
-      const uint32_t ox = tileX * 64u + i * 16u, oy = tileY * 64u + j * 16u;  // origin in the input level
-      const bool     valid = lane < 16u && ox < W && oy < H;
+      const uint32_t ox = tileX * 64u + i * 16u, oy = tileY * kTileH + j * 16u;  // origin in the input level
+      const bool     valid = lane < 16u && j * 16u < kTileH && ox < W && oy < H;
       float4         s4    = make_float4(0.f, 0.f, 0.f, 0.f);
       if(valid)
       {

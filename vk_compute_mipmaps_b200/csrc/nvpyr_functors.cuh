@@ -49,11 +49,36 @@ constexpr uint32_t kEncMinKey  = kEncMinBits >> kEncShift;
 constexpr uint32_t kEncMaxKey  = kEncMaxBits >> kEncShift;
 constexpr uint32_t kEncEntries = kEncMaxKey - kEncMinKey + 1;  // 3329
 
-struct DeviceTables
+constexpr uint32_t kEncEntriesPadded = (kEncEntries + 3u) & ~3u;  // whole uint4s for the copy into shared memory
+
+struct alignas(16) DeviceTables
 {
-  float    decode[256];          // linearFromSrgb(c), shaders/srgb.h:18-28 (pinned bits)
-  uint32_t encode[kEncEntries];  // bucket table described above
+  float    decode[256];                // linearFromSrgb(c), shaders/srgb.h:18-28 (pinned bits)
+  uint32_t encode[kEncEntriesPadded];  // bucket table described above
 };
+
+// Copies n4 uint4s global -> shared with every load of a thread in flight before its first
+// store: the per-CTA table set-up is pure latency, and it is paid by every launch.
+template <int kThreads>
+__device__ __forceinline__ void copyTableWide(uint4* dst, const uint4* src, uint32_t n4)
+{
+  constexpr int kMaxPerThread = 4;
+  uint4         v[kMaxPerThread];
+#pragma unroll
+  for(int k = 0; k < kMaxPerThread; ++k)
+  {
+    const uint32_t i = threadIdx.x + uint32_t(k) * kThreads;
+    if(i < n4)
+      v[k] = __ldg(src + i);
+  }
+#pragma unroll
+  for(int k = 0; k < kMaxPerThread; ++k)
+  {
+    const uint32_t i = threadIdx.x + uint32_t(k) * kThreads;
+    if(i < n4)
+      dst[i] = v[k];
+  }
+}
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b)
 {
@@ -83,36 +108,51 @@ struct LinearReduce
 };
 
 // ---------------------------------------------------------------------------
-// sRGBA8: srgba8_mipmap_preamble.glsl
-struct Srgba8 : LinearReduce
+// sRGBA8: srgba8_mipmap_preamble.glsl.  kRep = 32: the decode table is replicated per lane
+// (entry (code, lane) at [code * 32 + lane]) so a warp-wide lookup with arbitrary codes never
+// has a bank conflict -- for kernels that stream large levels.  kRep = 1: a single 1 KB copy,
+// cheap to set up -- for the small tail levels.
+template <int kRep>
+struct Srgba8T : LinearReduce
 {
+  static_assert(kRep == 1 || kRep == 32, "decode table replication");
   static constexpr int kTexelBytes = 4;
 
-  struct Shared
+  struct alignas(16) Shared
   {
-    // decode table replicated per lane: entry (code, lane) at [code * 32 + lane], so a
-    // warp-wide lookup with arbitrary codes never has a bank conflict.
-    float    decode[256 * 32];
-    uint32_t encode[kEncEntries];
+    float                decode[256 * kRep];
+    alignas(16) uint32_t encode[kEncEntriesPadded];
   };
 
+  // Called by all 256 threads of a CTA.
   __device__ static void sharedInit(Shared& s, const DeviceTables* t)
   {
-    for(uint32_t i = threadIdx.x; i < 256u * 32u; i += blockDim.x)
-      s.decode[i] = __ldg(&t->decode[i >> 5]);
-    for(uint32_t i = threadIdx.x; i < kEncEntries; i += blockDim.x)
-      s.encode[i] = __ldg(&t->encode[i]);
+    static_assert(kEncEntriesPadded / 4 <= 4 * 256, "copyTableWide capacity");
+    if(kRep == 1)
+      s.decode[threadIdx.x & 255u] = __ldg(&t->decode[threadIdx.x & 255u]);
+    else
+    {
+      // thread -> one code, its 32 lane copies as 8 x float4
+      const float  v  = __ldg(&t->decode[threadIdx.x & 255u]);
+      const float4 v4 = make_float4(v, v, v, v);
+      float4*      d  = reinterpret_cast<float4*>(&s.decode[(threadIdx.x & 255u) * kRep]);
+#pragma unroll
+      for(int k = 0; k < kRep / 4; ++k)
+        d[k] = v4;
+    }
+    copyTableWide<256>(reinterpret_cast<uint4*>(s.encode), reinterpret_cast<const uint4*>(t->encode),
+                       kEncEntriesPadded / 4);
   }
 
   // texelFetch on the sRGB view: RGB through the decode table, alpha = a * (1/255)
   // (shaders/srgb.h:60, mipmap_storage.hpp:400).
   __device__ __forceinline__ static Value decodeWord(const Shared& s, uint32_t w)
   {
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = kRep == 32 ? (threadIdx.x & 31u) : 0u;
     Value          v;
-    v.x = s.decode[((w & 0xFFu) << 5) | lane];
-    v.y = s.decode[(((w >> 8) & 0xFFu) << 5) | lane];
-    v.z = s.decode[(((w >> 16) & 0xFFu) << 5) | lane];
+    v.x = s.decode[((w & 0xFFu) * kRep) | lane];
+    v.y = s.decode[(((w >> 8) & 0xFFu) * kRep) | lane];
+    v.z = s.decode[(((w >> 16) & 0xFFu) * kRep) | lane];
     v.w = __fmul_rn(float(w >> 24), 1.0f / 255.0f);
     return v;
   }
@@ -167,6 +207,9 @@ struct Srgba8 : LinearReduce
     *reinterpret_cast<uint2*>(p) = make_uint2(encodeWord<kClampHigh>(s, v0), encodeWord<kClampHigh>(s, v1));
   }
 };
+
+using Srgba8     = Srgba8T<32>;
+using Srgba8Lite = Srgba8T<1>;
 
 // ---------------------------------------------------------------------------
 // RGBA32F: the template of nvpro_pyramid.glsl:27-49 instantiated with identity

@@ -70,24 +70,24 @@ struct FastSmem
   float4             l3[2][8][8];  // level +3 of the current tile, double buffered
 };
 
-// kVec: all row starts of lv[0] are 16-byte aligned and those of lv[1] are
-// aligned for a 2-texel store.
+// Tile loop of an M-level fast step, executed by a whole 256-thread CTA: tiles firstTile,
+// firstTile + tileStride, ...  `tables` is the functor set's shared-memory state, `l3` a
+// [2][8][8] float4 scratch.  Contains CTA barriers: every thread of the CTA must call it with
+// the same arguments.
+// kVec: all row starts of lv[0] are 16-byte aligned and those of lv[1] are aligned for a
+// 2-texel store.
 template <class F, int M, bool kVec>
-__global__ void __launch_bounds__(256) fastKernel(const FastParams p)
+__device__ __forceinline__ void fastTileLoop(const FastParams& p, const typename F::Shared& tables,
+                                             float4 (*l3buf)[8][8], uint32_t firstTile, uint32_t tileStride)
 {
-  static_assert(M >= 2 && M <= 6, "fastKernel handles 2..6 levels");
+  static_assert(M >= 2 && M <= 6, "fastTileLoop handles 2..6 levels");
   using V = typename F::Value;
-  extern __shared__ __align__(16) unsigned char smemRaw[];
-  FastSmem<F>& sm = *reinterpret_cast<FastSmem<F>*>(smemRaw);
-  F::sharedInit(sm.tables, p.tables);
-  __syncthreads();
-
   const uint32_t tid = threadIdx.x, tx = tid & 15u, ty = tid >> 4;
   const uint32_t W = p.lv[0].w, H = p.lv[0].h;
   const uint32_t numTiles = p.tilesX * p.tilesY;
   uint32_t       parity   = 0;
 
-  for(uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, parity ^= 1u)
+  for(uint32_t tile = firstTile; tile < numTiles; tile += tileStride, parity ^= 1u)
   {
     const uint32_t tileX = tile % p.tilesX, tileY = tile / p.tilesX;
     const uint32_t x0 = tileX * 64u + tx * 4u, y0 = tileY * 64u + ty * 4u;
@@ -106,16 +106,16 @@ __global__ void __launch_bounds__(256) fastKernel(const FastParams p)
         const unsigned char* r1 = r0 + p.lv[0].pitch;
         if(kVec)
         {
-          F::load4(sm.tables, r0, a);
-          F::load4(sm.tables, r1, b);
+          F::load4(tables, r0, a);
+          F::load4(tables, r1, b);
         }
         else
         {
 #pragma unroll
           for(int i = 0; i < 4; ++i)
           {
-            a[i] = F::load(sm.tables, r0 + i * F::kTexelBytes);
-            b[i] = F::load(sm.tables, r1 + i * F::kTexelBytes);
+            a[i] = F::load(tables, r0 + i * F::kTexelBytes);
+            b[i] = F::load(tables, r1 + i * F::kTexelBytes);
           }
         }
         // level +1: vertical pairing (k = 1)
@@ -123,16 +123,16 @@ __global__ void __launch_bounds__(256) fastKernel(const FastParams p)
         l1[qy][1] = F::reduce4(a[2], b[2], a[3], b[3]);
         unsigned char* d = p.lv[1].ptr + size_t((y0 >> 1) + qy) * p.lv[1].pitch + size_t(x0 >> 1) * F::kTexelBytes;
         if(kVec)
-          F::template store2<false>(sm.tables, d, l1[qy][0], l1[qy][1]);
+          F::template store2<false>(tables, d, l1[qy][0], l1[qy][1]);
         else
         {
-          F::template store<false>(sm.tables, d, l1[qy][0]);
-          F::template store<false>(sm.tables, d + F::kTexelBytes, l1[qy][1]);
+          F::template store<false>(tables, d, l1[qy][0]);
+          F::template store<false>(tables, d + F::kTexelBytes, l1[qy][1]);
         }
       }
       // level +2 from the thread's own 2x2 of level +1
       l2 = reduce4Paired<F>(fastPairingIsHorizontal(2, M), l1[0][0], l1[0][1], l1[1][0], l1[1][1]);
-      F::template store<false>(sm.tables,
+      F::template store<false>(tables,
                                p.lv[2].ptr + size_t(y0 >> 2) * p.lv[2].pitch + size_t(x0 >> 2) * F::kTexelBytes, l2);
     }
 
@@ -145,9 +145,9 @@ __global__ void __launch_bounds__(256) fastKernel(const FastParams p)
       if(active && !(tx & 1u) && !(ty & 1u))
       {
         F::template store<false>(
-            sm.tables, p.lv[3].ptr + size_t(y0 >> 3) * p.lv[3].pitch + size_t(x0 >> 3) * F::kTexelBytes, l3);
+            tables, p.lv[3].ptr + size_t(y0 >> 3) * p.lv[3].pitch + size_t(x0 >> 3) * F::kTexelBytes, l3);
         if(M >= 4)
-          sm.l3[parity][ty >> 1][tx >> 1] = l3;
+          l3buf[parity][ty >> 1][tx >> 1] = l3;
       }
     }
 
@@ -163,11 +163,11 @@ __global__ void __launch_bounds__(256) fastKernel(const FastParams p)
         V              l4    = make_float4(0.f, 0.f, 0.f, 0.f);
         if(valid)
         {
-          const V ul = sm.l3[parity][2 * j][2 * i], ur = sm.l3[parity][2 * j][2 * i + 1];
-          const V ll = sm.l3[parity][2 * j + 1][2 * i], lr = sm.l3[parity][2 * j + 1][2 * i + 1];
+          const V ul = l3buf[parity][2 * j][2 * i], ur = l3buf[parity][2 * j][2 * i + 1];
+          const V ll = l3buf[parity][2 * j + 1][2 * i], lr = l3buf[parity][2 * j + 1][2 * i + 1];
           l4         = reduce4Paired<F>(fastPairingIsHorizontal(4, M), ul, ur, ll, lr);
           F::template store<false>(
-              sm.tables, p.lv[4].ptr + size_t(oy >> 4) * p.lv[4].pitch + size_t(ox >> 4) * F::kTexelBytes, l4);
+              tables, p.lv[4].ptr + size_t(oy >> 4) * p.lv[4].pitch + size_t(ox >> 4) * F::kTexelBytes, l4);
         }
         if(M >= 5)
         {
@@ -175,43 +175,61 @@ __global__ void __launch_bounds__(256) fastKernel(const FastParams p)
           const V l5 = reduce4Paired<F>(fastPairingIsHorizontal(5, M), l4, sx, sy, sxy);
           if(valid && !(i & 1u) && !(j & 1u))
             F::template store<false>(
-                sm.tables, p.lv[5].ptr + size_t(oy >> 5) * p.lv[5].pitch + size_t(ox >> 5) * F::kTexelBytes, l5);
+                tables, p.lv[5].ptr + size_t(oy >> 5) * p.lv[5].pitch + size_t(ox >> 5) * F::kTexelBytes, l5);
           if(M >= 6)
           {
             const V tx2 = shflXor(l5, 2), ty2 = shflXor(l5, 8), txy2 = shflXor(l5, 10);
             const V l6  = reduce4Paired<F>(fastPairingIsHorizontal(6, M), l5, tx2, ty2, txy2);
             if(valid && tid == 0)
               F::template store<false>(
-                  sm.tables, p.lv[6].ptr + size_t(oy >> 6) * p.lv[6].pitch + size_t(ox >> 6) * F::kTexelBytes, l6);
+                  tables, p.lv[6].ptr + size_t(oy >> 6) * p.lv[6].pitch + size_t(ox >> 6) * F::kTexelBytes, l6);
           }
         }
       }
-      // sm.l3 is double buffered: the next iteration writes the other half, and the
+      // l3buf is double buffered: the next iteration writes the other half, and the
       // barrier of that iteration orders this read before the overwrite after it.
     }
   }
 }
 
-// M = 1: one thread per output texel (glsl:345-357 with levelCount_ == 1).
-template <class F>
-__global__ void __launch_bounds__(256) fastKernel1(const FastParams p)
+template <class F, int M, bool kVec>
+__global__ void __launch_bounds__(256) fastKernel(const FastParams p)
 {
-  using V = typename F::Value;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   FastSmem<F>& sm = *reinterpret_cast<FastSmem<F>*>(smemRaw);
   F::sharedInit(sm.tables, p.tables);
   __syncthreads();
+  fastTileLoop<F, M, kVec>(p, sm.tables, sm.l3, blockIdx.x, gridDim.x);
+}
+
+// M = 1 (glsl:345-357 with levelCount_ == 1): one thread per output texel, grid-strided from
+// `first` with stride `stride` (in threads).
+template <class F>
+__device__ __forceinline__ void fastLoop1(const FastParams& p, const typename F::Shared& tables, uint64_t first,
+                                          uint64_t stride)
+{
+  using V = typename F::Value;
   const uint32_t W1 = p.lv[1].w, H1 = p.lv[1].h;
   const uint64_t n = uint64_t(W1) * H1;
-  for(uint64_t g = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < n; g += uint64_t(gridDim.x) * blockDim.x)
+  for(uint64_t g = first; g < n; g += stride)
   {
     const uint32_t       x = uint32_t(g % W1), y = uint32_t(g / W1);
     const unsigned char* s = p.lv[0].ptr + size_t(2 * y) * p.lv[0].pitch + size_t(2 * x) * F::kTexelBytes;
-    const V ul = F::load(sm.tables, s), ur = F::load(sm.tables, s + F::kTexelBytes);
-    const V ll = F::load(sm.tables, s + p.lv[0].pitch), lr = F::load(sm.tables, s + p.lv[0].pitch + F::kTexelBytes);
-    F::template store<false>(sm.tables, p.lv[1].ptr + size_t(y) * p.lv[1].pitch + size_t(x) * F::kTexelBytes,
+    const V ul = F::load(tables, s), ur = F::load(tables, s + F::kTexelBytes);
+    const V ll = F::load(tables, s + p.lv[0].pitch), lr = F::load(tables, s + p.lv[0].pitch + F::kTexelBytes);
+    F::template store<false>(tables, p.lv[1].ptr + size_t(y) * p.lv[1].pitch + size_t(x) * F::kTexelBytes,
                              F::reduce4(ul, ll, ur, lr));
   }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) fastKernel1(const FastParams p)
+{
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  FastSmem<F>& sm = *reinterpret_cast<FastSmem<F>*>(smemRaw);
+  F::sharedInit(sm.tables, p.tables);
+  __syncthreads();
+  fastLoop1<F>(p, sm.tables, uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, uint64_t(gridDim.x) * blockDim.x);
 }
 
 // ---------------------------------------------------------------------------
@@ -225,15 +243,23 @@ struct GeneralParams
   const DeviceTables* tables;
 };
 
-constexpr int kGenTile2 = 16;                  // tile edge in level +2
-constexpr int kGenTile1 = 2 * kGenTile2 + 1;   // <= 33 texels of level +1 per axis
-constexpr int kGenPitch = kGenTile1 + 1;
+constexpr int kGenTile2 = 16;  // tile edge in level +2 of the stand-alone general kernel
+constexpr int kGenTile2Small = 8;  // ... of the tail kernel (more, smaller tiles: the levels are tiny)
+
+// Shared scratch of a T2 x T2 tile of level +2: (2 T2 + 1)^2 texels of level +1 (float32 carry).
+template <int T2>
+struct GenTile
+{
+  static constexpr int kTile1 = 2 * T2 + 1;
+  static constexpr int kPitch = kTile1 + 1;
+  float4               l1[kTile1][kPitch];  // [y][x]
+};
 
 template <class F>
 struct GeneralSmem
 {
   typename F::Shared tables;
-  float4             l1[kGenTile1][kGenPitch];  // [y][x] level +1 tile (float32 carry)
+  GenTile<kGenTile2> tile;
 };
 
 // kernelSizeFromInputSize_, glsl:557-561
@@ -289,35 +315,34 @@ __device__ __forceinline__ typename F::Value reduceSample(int kx, int ky, uint32
   return hcol[0];
 }
 
-template <class F>
-__global__ void __launch_bounds__(256) generalKernel(const GeneralParams p)
+// Tile loop of a 1- or 2-level general step, executed by a whole CTA (contains CTA barriers).
+// p.tilesX/Y must have been computed for T2 (generalTiles()).
+template <class F, int T2>
+__device__ __forceinline__ void generalTileLoop(const GeneralParams& p, const typename F::Shared& tables,
+                                                GenTile<T2>& scratch, uint32_t firstTile, uint32_t tileStride)
 {
+  float4(*l1buf)[GenTile<T2>::kPitch] = scratch.l1;
   using V = typename F::Value;
-  extern __shared__ __align__(16) unsigned char smemRaw[];
-  GeneralSmem<F>& sm = *reinterpret_cast<GeneralSmem<F>*>(smemRaw);
-  F::sharedInit(sm.tables, p.tables);
-  __syncthreads();
-
   const LevelView L0 = p.lv[0], L1 = p.lv[1], L2 = p.lv[2];
   const int       k1x = kernelTaps(L0.w), k1y = kernelTaps(L0.h);
   const uint32_t  numTiles = p.tilesX * p.tilesY;
 
-  for(uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x)
+  for(uint32_t tile = firstTile; tile < numTiles; tile += tileStride)
   {
     const uint32_t tileX = tile % p.tilesX, tileY = tile / p.tilesX;
     if(p.levels == 1)
     {
-      // 32x32 tile of level +1, no carry needed.
-      for(uint32_t t = threadIdx.x; t < 32u * 32u; t += blockDim.x)
+      // (2 T2) x (2 T2) tile of level +1, no carry needed.
+      for(uint32_t t = threadIdx.x; t < 4u * T2 * T2; t += blockDim.x)
       {
-        const uint32_t x = tileX * 32u + (t & 31u), y = tileY * 32u + (t >> 5);
+        const uint32_t x = tileX * (2u * T2) + (t % (2u * T2)), y = tileY * (2u * T2) + (t / (2u * T2));
         if(x >= L1.w || y >= L1.h)
           continue;
         const unsigned char* s   = L0.ptr + size_t(2 * y) * L0.pitch + size_t(2 * x) * F::kTexelBytes;
         const V              out = reduceSample<F>(k1x, k1y, L1.w, L1.h, x, y, [&](int dx, int dy) {
-          return F::load(sm.tables, s + size_t(dy) * L0.pitch + size_t(dx) * F::kTexelBytes);
+          return F::load(tables, s + size_t(dy) * L0.pitch + size_t(dx) * F::kTexelBytes);
         });
-        F::template store<true>(sm.tables, L1.ptr + size_t(y) * L1.pitch + size_t(x) * F::kTexelBytes, out);
+        F::template store<true>(tables, L1.ptr + size_t(y) * L1.pitch + size_t(x) * F::kTexelBytes, out);
       }
       continue;
     }
@@ -325,8 +350,8 @@ __global__ void __launch_bounds__(256) generalKernel(const GeneralParams p)
     // Two levels.  Tile of level +2: [x2a, x2b) x [y2a, y2b); the level +1 footprint it
     // needs starts at (2*x2a, 2*y2a) and spans 2*n + taps - 2 texels per axis.
     const int      k2x = kernelTaps(L1.w), k2y = kernelTaps(L1.h);
-    const uint32_t x2a = tileX * kGenTile2, y2a = tileY * kGenTile2;
-    const uint32_t x2b = min(x2a + kGenTile2, L2.w), y2b = min(y2a + kGenTile2, L2.h);
+    const uint32_t x2a = tileX * T2, y2a = tileY * T2;
+    const uint32_t x2b = min(x2a + T2, L2.w), y2b = min(y2a + T2, L2.h);
     const uint32_t fw = min(2u * (x2b - x2a) + uint32_t(k2x) - 2u, L1.w - 2u * x2a);
     const uint32_t fh = min(2u * (y2b - y2a) + uint32_t(k2y) - 2u, L1.h - 2u * y2a);
 
@@ -337,12 +362,12 @@ __global__ void __launch_bounds__(256) generalKernel(const GeneralParams p)
       const uint32_t x = 2u * x2a + lx, y = 2u * y2a + ly;
       const unsigned char* s   = L0.ptr + size_t(2 * y) * L0.pitch + size_t(2 * x) * F::kTexelBytes;
       const V              out = reduceSample<F>(k1x, k1y, L1.w, L1.h, x, y, [&](int dx, int dy) {
-        return F::load(sm.tables, s + size_t(dy) * L0.pitch + size_t(dx) * F::kTexelBytes);
+        return F::load(tables, s + size_t(dy) * L0.pitch + size_t(dx) * F::kTexelBytes);
       });
       // The halo column/row is also produced (with identical bits) by the neighbouring
       // tile, exactly like the reference's overlapping work groups.
-      F::template store<true>(sm.tables, L1.ptr + size_t(y) * L1.pitch + size_t(x) * F::kTexelBytes, out);
-      sm.l1[ly][lx] = out;
+      F::template store<true>(tables, L1.ptr + size_t(y) * L1.pitch + size_t(x) * F::kTexelBytes, out);
+      l1buf[ly][lx] = out;
     }
     __syncthreads();
     const uint32_t tw = x2b - x2a, th = y2b - y2a;
@@ -350,10 +375,141 @@ __global__ void __launch_bounds__(256) generalKernel(const GeneralParams p)
     {
       const uint32_t lx = t % tw, ly = t / tw;
       const V        out = reduceSample<F>(k2x, k2y, L2.w, L2.h, x2a + lx, y2a + ly,
-                                           [&](int dx, int dy) { return sm.l1[2 * ly + dy][2 * lx + dx]; });
-      F::template store<true>(sm.tables, L2.ptr + size_t(y2a + ly) * L2.pitch + size_t(x2a + lx) * F::kTexelBytes,
+                                           [&](int dx, int dy) { return l1buf[2 * ly + dy][2 * lx + dx]; });
+      F::template store<true>(tables, L2.ptr + size_t(y2a + ly) * L2.pitch + size_t(x2a + lx) * F::kTexelBytes,
                               out);
     }
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) generalKernel(const GeneralParams p)
+{
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  GeneralSmem<F>& sm = *reinterpret_cast<GeneralSmem<F>*>(smemRaw);
+  F::sharedInit(sm.tables, p.tables);
+  __syncthreads();
+  generalTileLoop<F, kGenTile2>(p, sm.tables, sm.tile, blockIdx.x, gridDim.x);
+}
+
+// ---------------------------------------------------------------------------
+// Tail kernel: several consecutive small steps of a plan in ONE launch.
+//
+// The reference records one dispatch + pipeline barrier per step
+// (nvpro_pyramid_dispatch.hpp:142-187); on B200 a launch costs more than the work of a small
+// level.  Step 0 ("grid step") is spread over all CTAs; the CTA that finishes it LAST (atomic
+// ticket) then runs the remaining ("solo") steps alone, with CTA barriers where the reference
+// has pipeline barriers.  No CTA ever waits for another one, so no cooperative launch is
+// needed.  Carry groups (and therefore bits) are unchanged: each step still re-reads the
+// 8-bit level written by the previous step.
+constexpr uint32_t kMaxTailSteps = 12;
+
+struct TailStep
+{
+  uint32_t  pipeline;  // 1 fast, 0 general
+  uint32_t  levels;
+  uint32_t  vec;       // fast: vector loads/stores allowed
+  uint32_t  tilesX, tilesY;
+  LevelView lv[7];
+};
+
+struct TailParams
+{
+  uint32_t            numSteps;
+  uint32_t*           ticket;  // zero on entry, reset to zero by the last CTA
+  const DeviceTables* tables;
+  TailStep            steps[kMaxTailSteps];
+};
+
+template <class F>
+struct TailSmem
+{
+  typename F::Shared tables;
+  union
+  {
+    float4                  l3[2][8][8];
+    GenTile<kGenTile2Small> tile;
+  };
+  uint32_t isLast;
+};
+
+template <class F>
+__device__ __forceinline__ void tailRunStep(const TailStep& st, TailSmem<F>& sm, const DeviceTables* tables,
+                                            uint32_t first, uint32_t stride)
+{
+  if(st.pipeline == 1u)
+  {
+    FastParams p;
+#pragma unroll
+    for(int k = 0; k < 7; ++k)
+      p.lv[k] = st.lv[k];
+    p.tilesX = st.tilesX;
+    p.tilesY = st.tilesY;
+    p.tables = tables;
+#define NVPYR_TAIL_FAST(m)                                                                                        \
+  case m:                                                                                                         \
+    if(st.vec)                                                                                                    \
+      fastTileLoop<F, m, true>(p, sm.tables, sm.l3, first, stride);                                               \
+    else                                                                                                          \
+      fastTileLoop<F, m, false>(p, sm.tables, sm.l3, first, stride);                                              \
+    break;
+    switch(st.levels)
+    {
+      case 1:
+        fastLoop1<F>(p, sm.tables, uint64_t(first) * blockDim.x + threadIdx.x, uint64_t(stride) * blockDim.x);
+        break;
+        NVPYR_TAIL_FAST(2)
+        NVPYR_TAIL_FAST(3)
+        NVPYR_TAIL_FAST(4)
+        NVPYR_TAIL_FAST(5)
+        NVPYR_TAIL_FAST(6)
+    }
+#undef NVPYR_TAIL_FAST
+  }
+  else
+  {
+    GeneralParams p;
+    p.lv[0] = st.lv[0], p.lv[1] = st.lv[1], p.lv[2] = st.lv[2];
+    p.levels = st.levels;
+    p.tilesX = st.tilesX;
+    p.tilesY = st.tilesY;
+    p.tables = tables;
+    generalTileLoop<F, kGenTile2Small>(p, sm.tables, sm.tile, first, stride);
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) tailKernel(const __grid_constant__ TailParams tp)
+{
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  TailSmem<F>& sm = *reinterpret_cast<TailSmem<F>*>(smemRaw);
+  F::sharedInit(sm.tables, tp.tables);
+  __syncthreads();
+
+  tailRunStep<F>(tp.steps[0], sm, tp.tables, blockIdx.x, gridDim.x);
+  if(tp.numSteps == 1u)
+    return;
+
+  // Publish this CTA's part of step 0, then find out whether it was the last one.
+  __threadfence();
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    const uint32_t t = atomicAdd(tp.ticket, 1u);
+    sm.isLast        = t == gridDim.x - 1u;
+    if(sm.isLast)
+      *tp.ticket = 0u;  // every CTA has taken its ticket: safe to recycle the counter
+  }
+  __syncthreads();
+  if(!sm.isLast)
+    return;
+  __threadfence();  // acquire side of the ticket
+
+  for(uint32_t s = 1; s < tp.numSteps; ++s)
+  {
+    tailRunStep<F>(tp.steps[s], sm, tp.tables, 0u, 1u);
+    __threadfence_block();
+    __syncthreads();  // the reference's inter-dispatch pipeline barrier (one CTA: a CTA barrier suffices)
   }
 }
 
