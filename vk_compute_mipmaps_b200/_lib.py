@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnvpyr.so")
+# NVPYR_LIB_PATH: load another build of the same ABI (A/B timing of kernel variants).
+LIB_PATH = os.environ.get("NVPYR_LIB_PATH") or os.path.join(_HERE, "libnvpyr.so")
 
 NVPYR_MAX_LEVELS = 32
 NVPYR_MAX_STEPS = 40

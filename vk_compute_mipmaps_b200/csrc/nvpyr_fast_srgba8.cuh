@@ -25,6 +25,8 @@
 //    tile; levels +4..+M are finished by the same warp.  No CTA-wide barrier exists after
 //    the table set-up (the v2 kernel lost 13 % of its warp time at one).  Tiles are only as
 //    tall as the step needs, so steps with M < 6 expose 2-8x more independent warp tasks.
+//  * packed adds: FADD2 (add.rn.f32x2) performs two IEEE float32 additions per issue slot;
+//    the sums run on (R, G) and (B, A) pairs.
 //  * the next slab's four 16-byte rows are prefetched into registers before the current
 //    slab is processed.
 //
@@ -107,19 +109,72 @@ __device__ __forceinline__ float decAlpha(uint32_t w)
   return __fmul_rn(float(w >> 24), 1.0f / 255.0f);
 }
 
-// Un-normalised sum of one 2x2 quad, vertical pairing: (UL + LL) + (UR + LR)  (glsl:180-188).
-__device__ __forceinline__ float4 quadSumV(const unsigned char* dec, uint32_t laneOff, uint32_t ul, uint32_t ur,
-                                           uint32_t ll, uint32_t lr)
+// Packed float32 pairs: Blackwell's FADD2 performs two IEEE round-to-nearest float32 additions
+// in ONE issue slot (add.rn.f32x2).  The kernel is issue-bound, so the pairwise sums of
+// (R, G) and (B, A) are done two channels at a time; each lane of the pair is rounded exactly
+// like a scalar __fadd_rn.
+struct F2
 {
-  float4 s;
-  s.x = __fadd_rn(__fadd_rn(dec8<0>(dec, ul, laneOff), dec8<0>(dec, ll, laneOff)),
-                  __fadd_rn(dec8<0>(dec, ur, laneOff), dec8<0>(dec, lr, laneOff)));
-  s.y = __fadd_rn(__fadd_rn(dec8<1>(dec, ul, laneOff), dec8<1>(dec, ll, laneOff)),
-                  __fadd_rn(dec8<1>(dec, ur, laneOff), dec8<1>(dec, lr, laneOff)));
-  s.z = __fadd_rn(__fadd_rn(dec8<2>(dec, ul, laneOff), dec8<2>(dec, ll, laneOff)),
-                  __fadd_rn(dec8<2>(dec, ur, laneOff), dec8<2>(dec, lr, laneOff)));
-  s.w = __fadd_rn(__fadd_rn(decAlpha(ul), decAlpha(ll)), __fadd_rn(decAlpha(ur), decAlpha(lr)));
-  return s;
+  unsigned long long v;
+};
+__device__ __forceinline__ F2 pack2(float lo, float hi)
+{
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(F2 a, float& lo, float& hi)
+{
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b)
+{
+  F2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+// A texel value as two packed pairs: rg = (R, G), ba = (B, A).
+struct V4
+{
+  F2 rg, ba;
+};
+__device__ __forceinline__ V4 add4(V4 a, V4 b)
+{
+  V4 r;
+  r.rg = add2(a.rg, b.rg);
+  r.ba = add2(a.ba, b.ba);
+  return r;
+}
+__device__ __forceinline__ float4 toFloat4(V4 a)
+{
+  float4 f;
+  unpack2(a.rg, f.x, f.y);
+  unpack2(a.ba, f.z, f.w);
+  return f;
+}
+__device__ __forceinline__ V4 toV4(float4 f)
+{
+  V4 r;
+  r.rg = pack2(f.x, f.y);
+  r.ba = pack2(f.z, f.w);
+  return r;
+}
+
+// Decoded texel (rgb pre-scaled by 2^-100, alpha = a * (1/255)) as packed pairs.
+__device__ __forceinline__ V4 decodeTexel(const unsigned char* dec, uint32_t laneOff, uint32_t w)
+{
+  V4 r;
+  r.rg = pack2(dec8<0>(dec, w, laneOff), dec8<1>(dec, w, laneOff));
+  r.ba = pack2(dec8<2>(dec, w, laneOff), decAlpha(w));
+  return r;
+}
+
+// Un-normalised sum of one 2x2 quad, vertical pairing: (UL + LL) + (UR + LR)  (glsl:180-188).
+__device__ __forceinline__ V4 quadSumV(const unsigned char* dec, uint32_t laneOff, uint32_t ul, uint32_t ur,
+                                       uint32_t ll, uint32_t lr)
+{
+  return add4(add4(decodeTexel(dec, laneOff, ul), decodeTexel(dec, laneOff, ll)),
+              add4(decodeTexel(dec, laneOff, ur), decodeTexel(dec, laneOff, lr)));
 }
 
 // Encode of one RGB channel carried as S' = 2^-100 * 4^K * x; the code lands in bits 16..23.
@@ -148,11 +203,24 @@ __device__ __forceinline__ uint32_t encWordScaled(const unsigned char* encBytes,
   return __byte_perm(__byte_perm(r, g, 0x0062), __byte_perm(b, a, 0x0042), 0x5410);
 }
 
-__device__ __forceinline__ float4 sum4Paired(bool horizontal, float4 ul, float4 ur, float4 ll, float4 lr)
+template <int K>
+__device__ __forceinline__ uint32_t encWordScaled(const unsigned char* encBytes, V4 s)
 {
-  const float4 p = horizontal ? f4add(ul, ur) : f4add(ul, ll);
-  const float4 q = horizontal ? f4add(ll, lr) : f4add(ur, lr);
-  return f4add(p, q);
+  return encWordScaled<K>(encBytes, toFloat4(s));
+}
+
+__device__ __forceinline__ V4 sum4Paired(bool horizontal, V4 ul, V4 ur, V4 ll, V4 lr)
+{
+  const V4 p = horizontal ? add4(ul, ur) : add4(ul, ll);
+  const V4 q = horizontal ? add4(ll, lr) : add4(ur, lr);
+  return add4(p, q);
+}
+__device__ __forceinline__ V4 shflXor(V4 a, int mask)
+{
+  V4 r;
+  r.rg.v = __shfl_xor_sync(0xffffffffu, a.rg.v, mask);
+  r.ba.v = __shfl_xor_sync(0xffffffffu, a.ba.v, mask);
+  return r;
 }
 
 template <int M>
@@ -239,29 +307,49 @@ __global__ void __launch_bounds__(kFastWarps * 32, 2) fastSrgba8Kernel(const Fas
         nxt = nextTile;
       loadRows(nxt);
 
-      float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+      V4 s2 = toV4(make_float4(0.f, 0.f, 0.f, 0.f));
       if(active)
       {
-        // level +1 (K = 1): four quads, vertical pairing
-        const float4 s00 = quadSumV(dec, laneOff, c0.x, c0.y, c1.x, c1.y);
-        const float4 s01 = quadSumV(dec, laneOff, c0.z, c0.w, c1.z, c1.w);
-        *reinterpret_cast<uint2*>(d1) = make_uint2(encWordScaled<1>(enc, s00), encWordScaled<1>(enc, s01));
-        const float4 s10 = quadSumV(dec, laneOff, c2.x, c2.y, c3.x, c3.y);
-        const float4 s11 = quadSumV(dec, laneOff, c2.z, c2.w, c3.z, c3.w);
-        *reinterpret_cast<uint2*>(d1 + pitch1) = make_uint2(encWordScaled<1>(enc, s10), encWordScaled<1>(enc, s11));
-        // level +2 (K = 2) from the thread's own 2x2
-        s2 = sum4Paired(fastPairingIsHorizontal(2, M), s00, s01, s10, s11);
+        // level +1 (K = 1): four quads, vertical pairing inside each; level +2 (K = 2) from the
+        // thread's own 2x2.  The quads are visited in the order of the level +2 pairing so that
+        // only one partial sum stays live (register pressure).
+        if(fastPairingIsHorizontal(2, M))
+        {
+          const V4 s00 = quadSumV(dec, laneOff, c0.x, c0.y, c1.x, c1.y);
+          const V4 s01 = quadSumV(dec, laneOff, c0.z, c0.w, c1.z, c1.w);
+          *reinterpret_cast<uint2*>(d1) = make_uint2(encWordScaled<1>(enc, s00), encWordScaled<1>(enc, s01));
+          const V4 top = add4(s00, s01);
+          const V4 s10 = quadSumV(dec, laneOff, c2.x, c2.y, c3.x, c3.y);
+          const V4 s11 = quadSumV(dec, laneOff, c2.z, c2.w, c3.z, c3.w);
+          *reinterpret_cast<uint2*>(d1 + pitch1) = make_uint2(encWordScaled<1>(enc, s10), encWordScaled<1>(enc, s11));
+          s2 = add4(top, add4(s10, s11));  // (UL + UR) + (LL + LR)
+        }
+        else
+        {
+          const V4       s00 = quadSumV(dec, laneOff, c0.x, c0.y, c1.x, c1.y);
+          const uint32_t e00 = encWordScaled<1>(enc, s00);
+          const V4       s10 = quadSumV(dec, laneOff, c2.x, c2.y, c3.x, c3.y);
+          const uint32_t e10 = encWordScaled<1>(enc, s10);
+          const V4       left = add4(s00, s10);
+          const V4       s01 = quadSumV(dec, laneOff, c0.z, c0.w, c1.z, c1.w);
+          *reinterpret_cast<uint2*>(d1) = make_uint2(e00, encWordScaled<1>(enc, s01));
+          const V4 s11 = quadSumV(dec, laneOff, c2.z, c2.w, c3.z, c3.w);
+          *reinterpret_cast<uint2*>(d1 + pitch1) = make_uint2(e10, encWordScaled<1>(enc, s11));
+          s2 = add4(left, add4(s01, s11));  // (UL + LL) + (UR + LR)
+        }
         *reinterpret_cast<uint32_t*>(d2) = encWordScaled<2>(enc, s2);
       }
 
       if(M >= 3)
       {
         // level +3 (K = 3), horizontal pairing for every M: (self + x) + (y + xy).
-        // Step x: even lanes keep (R, G), odd lanes keep (B, A).
-        const float keep0 = xOdd ? s2.z : s2.x, keep1 = xOdd ? s2.w : s2.y;
-        const float send0 = xOdd ? s2.x : s2.z, send1 = xOdd ? s2.y : s2.w;
-        const float t0    = __fadd_rn(keep0, __shfl_xor_sync(0xffffffffu, send0, 1));
-        const float t1    = __fadd_rn(keep1, __shfl_xor_sync(0xffffffffu, send1, 1));
+        // Step x: even lanes keep (R, G) and send (B, A); odd lanes the other way round.
+        const F2 keep = xOdd ? s2.ba : s2.rg, send = xOdd ? s2.rg : s2.ba;
+        F2       got;
+        got.v      = __shfl_xor_sync(0xffffffffu, send.v, 1);
+        const F2 t = add2(keep, got);
+        float    t0, t1;
+        unpack2(t, t0, t1);
         // Step y: y-even lanes keep the first of their two channels, y-odd lanes the second.
         const float u = __fadd_rn(yOdd ? t1 : t0, __shfl_xor_sync(0xffffffffu, yOdd ? t0 : t1, 16));
         // encode this lane's channel, gather the four bytes
@@ -286,12 +374,12 @@ __global__ void __launch_bounds__(kFastWarps * 32, 2) fastSrgba8Kernel(const Fas
       const uint32_t i = lane & 3u, j = (lane >> 2) & 3u;
       const uint32_t ox = tileX * 64u + i * 16u, oy = tileY * kTileH + j * 16u;  // origin in the input level
       const bool     valid = lane < 16u && j * 16u < kTileH && ox < W && oy < H;
-      float4         s4    = make_float4(0.f, 0.f, 0.f, 0.f);
+      V4             s4    = toV4(make_float4(0.f, 0.f, 0.f, 0.f));
       if(valid)
       {
         const float4* l3 = reinterpret_cast<const float4*>(myL3);
-        const float4  ul = l3[(2 * j) * 8 + 2 * i], ur = l3[(2 * j) * 8 + 2 * i + 1];
-        const float4  ll = l3[(2 * j + 1) * 8 + 2 * i], lr = l3[(2 * j + 1) * 8 + 2 * i + 1];
+        const V4      ul = toV4(l3[(2 * j) * 8 + 2 * i]), ur = toV4(l3[(2 * j) * 8 + 2 * i + 1]);
+        const V4      ll = toV4(l3[(2 * j + 1) * 8 + 2 * i]), lr = toV4(l3[(2 * j + 1) * 8 + 2 * i + 1]);
         s4               = sum4Paired(fastPairingIsHorizontal(4, M), ul, ur, ll, lr);
         *reinterpret_cast<uint32_t*>(p.lv[4].ptr + size_t(oy >> 4) * p.lv[4].pitch + size_t(ox >> 4) * 4u) =
             encWordScaled<4>(enc, s4);
@@ -299,15 +387,15 @@ __global__ void __launch_bounds__(kFastWarps * 32, 2) fastSrgba8Kernel(const Fas
       if(M >= 5)
       {
         // vertical pairing (shared-memory tail of the reference): (self + y) + (x + xy)
-        const float4 a  = f4add(s4, shflXor(s4, 4));
-        const float4 s5 = f4add(a, shflXor(a, 1));
+        const V4 a  = add4(s4, shflXor(s4, 4));
+        const V4 s5 = add4(a, shflXor(a, 1));
         if(valid && !(i & 1u) && !(j & 1u))
           *reinterpret_cast<uint32_t*>(p.lv[5].ptr + size_t(oy >> 5) * p.lv[5].pitch + size_t(ox >> 5) * 4u) =
               encWordScaled<5>(enc, s5);
         if(M >= 6)
         {
-          const float4 c  = f4add(s5, shflXor(s5, 8));
-          const float4 s6 = f4add(c, shflXor(c, 2));
+          const V4 c  = add4(s5, shflXor(s5, 8));
+          const V4 s6 = add4(c, shflXor(c, 2));
           if(valid && lane == 0u)
             *reinterpret_cast<uint32_t*>(p.lv[6].ptr + size_t(oy >> 6) * p.lv[6].pitch + size_t(ox >> 6) * 4u) =
                 encWordScaled<6>(enc, s6);
