@@ -255,6 +255,9 @@ def run_gpu_arm(args):
         b = torch.empty(chain_bytes, dtype=torch.uint8, device=dev)
         b[:4 * W * H] = torch.randint(0, 256, (4 * W * H,), dtype=torch.uint8, device=dev, generator=gen)
         bufs.append(b)
+    if args.input != "random":
+        {"julia": fill_julia, "gradient": fill_gradient}[args.input](bufs[0][:4 * W * H].view(H, W, 4), W, H)
+        bufs[1][:4 * W * H].copy_(bufs[0][:4 * W * H])
     stream = torch.cuda.current_stream()
 
     def step(i):
@@ -374,7 +377,9 @@ def run_gpu_arm(args):
                    "algorithmic_bytes_per_step": chain_bytes, "us_per_chain": 1e3 * ms_per_step,
                    "l2_policy": "inputs larger than L2: two distinct 1.43 GB chains alternated",
                    "per_rank": "one chain per step per rank, no collective", "launches_per_chain": launches / args.steps,
-                   "input": "uniform random bytes, all four channels (worst case for the encode table's bank conflicts)",
+                   "input": {"random": "uniform random bytes, all four channels (worst case for the encode table's bank "
+                                       "conflicts)", "julia": "Julia set of the reference demo", "gradient":
+                             "opaque smooth gradient"}[args.input],
                    "other_inputs": other_inputs},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "fastKernel<Srgba8,6> (level 0 -> levels 1..6)",
@@ -395,6 +400,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-inputs", action="store_true")
+    ap.add_argument("--input", default="random", choices=["random", "julia", "gradient"],
+                    help="level-0 content of the headline loop (default: uniform random bytes, the worst case)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
