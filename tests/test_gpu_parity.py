@@ -105,6 +105,36 @@ def test_generic_functor_kernel_matches_tuned_kernel(nv, cuda, oracle):
     assert out.returncode == 0 and "generic ok" in out.stdout, out.stderr[-2000:]
 
 
+def test_standalone_kernels_on_small_levels(nv, cuda, oracle):
+    """NVPYR_TAIL_MAX_TEXELS=0 disables the fused tail launch, so the tuned stand-alone kernels (strip-walking
+    general kernel, warp-tile fast kernel) also run the tiny and ragged levels: every strip/segment edge case at
+    sizes the oracle checks in milliseconds."""
+    import subprocess
+    import sys
+    sizes = [(63, 63), (100, 37), (255, 255), (511, 300), (254, 254), (17, 513), (129, 129), (6, 10), (31, 31),
+             (32, 32), (61, 61), (62, 62), (33, 2), (2, 33), (3, 3), (5, 5), (2, 2), (301, 7), (7, 301), (91, 181),
+             (260, 260), (136, 512), (120, 72), (1023, 57), (64, 64), (192, 320)]
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import vk_compute_mipmaps_b200 as nv, _oracle\n"
+        "o = _oracle.load_oracle()\n"
+        "for (w, h) in %r:\n"
+        "  for fg in (False, True):\n"
+        "    l0 = _oracle.random_level0(w, h, w * 31 + h)\n"
+        "    buf = torch.zeros(nv.chain_bytes(w, h), dtype=torch.uint8, device='cuda')\n"
+        "    buf[:4 * w * h] = torch.from_numpy(l0).cuda()\n"
+        "    nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(fast_pipeline=not fg), w, h, image=buf)\n"
+        "    torch.cuda.synchronize()\n"
+        "    want = o.shader_chain(l0, w, h, force_general=fg)[0]\n"
+        "    got = buf.cpu().numpy()\n"
+        "    assert (got == want).all(), (w, h, fg, int((got != want).sum()))\n"
+        "print('standalone ok')\n") % (_oracle.ROOT, os.path.join(_oracle.ROOT, "tests"), sizes)
+    env = dict(os.environ, NVPYR_TAIL_MAX_TEXELS="0")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "standalone ok" in out.stdout, (out.stdout[-500:], out.stderr[-2000:])
+
+
 @pytest.mark.parametrize("size", [(64, 64), (256, 256), (96, 160), (100, 37), (260, 260), (1, 9)],
                          ids=lambda s: f"{s[0]}x{s[1]}")
 def test_force_general_bit_exact(nv, cuda, oracle, size):

@@ -14,6 +14,7 @@
 
 #include "../../include/nvpyr.h"
 #include "nvpyr_fast_srgba8.cuh"
+#include "nvpyr_general_srgba8.cuh"
 #include "nvpyr_kernels.cuh"
 #include "nvpyr_plan.hpp"
 #include "srgb_tables.inc"
@@ -277,10 +278,53 @@ inline void generalTiles(const LevelView* lv, uint32_t levels, uint32_t tile2, u
   *ty                  = (out.h + t - 1u) / t;
 }
 
+// The tuned sRGBA8 general kernel (nvpyr_general_srgba8.cuh): warp strips, streaming rows.
+template <int kLevels, bool kX3, bool kY3>
+nvpyrStatus launchGeneralSrgba8T(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
+{
+  GenStripParams p{};
+  p.lv[0] = gp.lv[0], p.lv[1] = gp.lv[1], p.lv[2] = gp.lv[2];
+  p.tables            = ctx.tables;
+  p.stripsX           = std::max(1u, (gp.lv[1].w - 1u + 29u) / 30u);
+  const size_t smem   = sizeof(GenSrgba8Smem);
+  int          perSm  = 0;
+  nvpyrStatus  st     = blocksPerSm(reinterpret_cast<const void*>(generalSrgba8Kernel<kLevels, kX3, kY3>), smem,
+                                    kGenWarps * 32, ctx.device, &perSm);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  // Rows per warp task: aim at ~4 tasks per resident warp, at least 4 rows (halo/prologue overhead).
+  const uint32_t rows    = kLevels == 2 ? gp.lv[2].h : gp.lv[1].h;
+  const uint64_t warps   = uint64_t(perSm) * ctx.smCount * kGenWarps;
+  const uint32_t wantSeg = uint32_t(std::max<uint64_t>(1, (4 * warps + p.stripsX - 1) / p.stripsX));
+  p.segRows              = std::min(64u, std::max(kLevels == 2 ? 4u : 8u, (rows + wantSeg - 1) / wantSeg));
+  p.segsY                = (rows + p.segRows - 1) / p.segRows;
+  const uint64_t tasks   = uint64_t(p.stripsX) * p.segsY;
+  const uint64_t ctas    = std::min<uint64_t>(uint64_t(perSm) * ctx.smCount, (tasks + kGenWarps - 1) / kGenWarps);
+  generalSrgba8Kernel<kLevels, kX3, kY3><<<int(std::max<uint64_t>(1, ctas)), kGenWarps * 32, smem, stream>>>(p);
+  NVPYR_CUDA(cudaGetLastError());
+  ++g_launchCount;
+  return NVPYR_SUCCESS;
+}
+
+template <int kLevels>
+nvpyrStatus launchGeneralSrgba8(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
+{
+  const bool x3 = gp.lv[0].w & 1u, y3 = gp.lv[0].h & 1u;
+  if(x3)
+    return y3 ? launchGeneralSrgba8T<kLevels, true, true>(ctx, gp, stream)
+              : launchGeneralSrgba8T<kLevels, true, false>(ctx, gp, stream);
+  return y3 ? launchGeneralSrgba8T<kLevels, false, true>(ctx, gp, stream)
+            : launchGeneralSrgba8T<kLevels, false, false>(ctx, gp, stream);
+}
+
 template <class F>
 nvpyrStatus launchGeneral(const DeviceContext& ctx, GeneralParams p, cudaStream_t stream)
 {
   p.tables = ctx.tables;
+  // Tuned path: sRGBA8, no 1-texel-wide/high level involved (those use kernel size 1).
+  if(std::is_same<F, Srgba8>::value && !g_forceGenericFast && p.lv[0].w >= 2 && p.lv[0].h >= 2
+     && (p.levels == 1 || (p.lv[1].w >= 2 && p.lv[1].h >= 2)))
+    return p.levels == 1 ? launchGeneralSrgba8<1>(ctx, p, stream) : launchGeneralSrgba8<2>(ctx, p, stream);
   generalTiles(p.lv, p.levels, kGenTile2, &p.tilesX, &p.tilesY);
   const size_t smem = sizeof(GeneralSmem<F>);
   int          grid = 1;
@@ -379,7 +423,12 @@ nvpyrStatus resolve(const nvpyrDispatchDesc* d, ResolvedDesc& r)
 // Steps whose input level has at most kTailMaxTexels texels are candidates for tailKernel: a
 // "grid step" spread over all CTAs followed by "solo" steps (input <= kSoloMaxTexels) that the
 // last CTA runs alone.
-constexpr uint64_t kTailMaxTexels = 512ull * 512ull;
+const uint64_t kTailMaxTexels = [] {
+  // NVPYR_TAIL_MAX_TEXELS overrides the threshold (tests use 0 to force the stand-alone kernels
+  // onto tiny levels).
+  const char* e = getenv("NVPYR_TAIL_MAX_TEXELS");
+  return e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : 512ull * 512ull;
+}();
 constexpr uint64_t kSoloMaxTexels = 64ull * 64ull;
 
 template <class F>

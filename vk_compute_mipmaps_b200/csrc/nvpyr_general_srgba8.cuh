@@ -1,0 +1,272 @@
+// nvpyr_general_srgba8.cuh -- tuned general (NPOT) pipeline for sRGBA8: 1 or 2 levels from an
+// input level of any size >= 2x2, the reference's energy-conserving separable 1/2/3-tap kernel
+// (nvpro_pyramid/nvpro_pyramid.glsl:575-656) with its float32 carry from level +1 to level +2.
+//
+// Same float32 expression tree per output texel as generalKernel<Srgba8> (nvpyr_kernels.cuh) --
+// vertical reduction of each source column, then horizontal reduction, weights
+// (n - i, n, 1 - w0 - w1) / (2n + 1) -- hence the same bits, but organised as a stream:
+//
+//   * one WARP owns a strip of 31 columns of level +1 (lane l <-> column c0 + l, strips advance by
+//     30: the last column is the halo the next strip recomputes, like the reference's overlapping
+//     work groups) and walks DOWN a segment of rows.  Each lane loads its own two source columns
+//     (a warp reads 256 contiguous bytes per source row), decodes them once (PRMT + conflict-free
+//     LDS, as in the fast kernel), keeps source row 2y+2 in registers as row 2(y+1) of the next
+//     output row, reduces its two columns vertically and fetches the third column's vertical sum
+//     from lane l+1 with shuffles.  The reference fetches and decodes up to 9 texels per output
+//     texel; here it is 2 (+ 2 shuffled floats4).
+//   * level +2 is accumulated on the fly: each lane keeps the last two level +1 values of its
+//     column (float32, never re-quantised), reduces vertically every second row, and even lanes
+//     finish horizontally with two shuffles.  No shared-memory tile, no barrier.
+//
+// 1/(2n+1) is one IEEE division per kernel; per-row weights cost a subtract and two multiplies.
+#pragma once
+#include "nvpyr_fast_srgba8.cuh"
+
+namespace nvpyr {
+
+struct GenSrgba8Smem
+{
+  float                decode[256 * 64];  // [code][64]: floats 0..31 = linearFromSrgb(code) per lane
+  alignas(16) uint32_t encode[kEncEntriesPadded];
+};
+
+struct GenStripParams
+{
+  LevelView           lv[3];
+  uint32_t            stripsX;   // strips of 30 (+1 halo) level +1 columns
+  uint32_t            segsY;     // row segments
+  uint32_t            segRows;   // rows per segment: of level +2 (two levels) or of level +1 (one level)
+  const DeviceTables* tables;
+};
+
+constexpr int kGenWarps = 8;
+
+__device__ __forceinline__ void genSrgba8Init(GenSrgba8Smem& sm, const DeviceTables* t)
+{
+  for(uint32_t i = threadIdx.x; i < 512u; i += kGenWarps * 32)
+  {
+    const uint32_t code = i >> 1, half = i & 1u;
+    const float    v    = __ldg(&t->decode[code]);
+    float4*        d    = reinterpret_cast<float4*>(&sm.decode[code * 64u + half * 16u]);
+    const float4   v4   = make_float4(v, v, v, v);
+    d[0] = v4, d[1] = v4, d[2] = v4, d[3] = v4;
+  }
+  copyTableWide<kGenWarps * 32>(reinterpret_cast<uint4*>(sm.encode), reinterpret_cast<const uint4*>(t->encode),
+                                kEncEntriesPadded / 4);
+}
+
+__device__ __forceinline__ float4 genDecode(const unsigned char* dec, uint32_t laneOff, uint32_t w)
+{
+  return make_float4(dec8<0>(dec, w, laneOff), dec8<1>(dec, w, laneOff), dec8<2>(dec, w, laneOff), decAlpha(w));
+}
+
+// srgbFromLinear with both clamps (weighted sums may exceed 1 by an ulp); code in bits 16..23.
+__device__ __forceinline__ uint32_t genEncChannel(const unsigned char* enc, float x)
+{
+  uint32_t b         = min(max(__float_as_uint(x), kEncMinBits), kEncMaxBits);
+  const uint32_t off = (b >> (kEncShift - 2)) & 0x3FFFCu;
+  return *reinterpret_cast<const uint32_t*>(enc + off - kEncMinKey * 4u) + b;
+}
+__device__ __forceinline__ uint32_t genEncWord(const unsigned char* enc, float4 v)
+{
+  const uint32_t r = genEncChannel(enc, v.x), g = genEncChannel(enc, v.y), b = genEncChannel(enc, v.z);
+  // uint(a * 255 + 0.5): a <= 1 + 2 ulp, so the truncation never exceeds 255
+  const uint32_t a = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(v.w, 255.0f), 0.5f), 8388608.0f));
+  return __byte_perm(__byte_perm(r, g, 0x0062), __byte_perm(b, a, 0x0042), 0x5410);
+}
+
+// Weights of destination index i of n (glsl:582-586): w0 = rcp*(n-i), w1 = rcp*n, w2 = 1-w0-w1.
+struct Taps
+{
+  float w0, w1, w2;
+};
+__device__ __forceinline__ Taps genTaps(float rcp, float fn, uint32_t i)
+{
+  Taps t;
+  t.w0 = __fmul_rn(rcp, __fsub_rn(fn, float(i)));
+  t.w1 = __fmul_rn(rcp, fn);
+  t.w2 = __fsub_rn(__fsub_rn(1.0f, t.w0), t.w1);
+  return t;
+}
+__device__ __forceinline__ float genRcp(uint32_t n)
+{
+  const float fn = float(n);
+  return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(2.0f, fn), 1.0f));
+}
+__device__ __forceinline__ float4 shflDown(float4 v, int d)
+{
+  return make_float4(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d),
+                     __shfl_down_sync(0xffffffffu, v.z, d), __shfl_down_sync(0xffffffffu, v.w, d));
+}
+
+// kLevels: 1 or 2.  kX3 / kY3: the first level uses 3 taps (odd source size) along x / y; otherwise 2.
+template <int kLevels, bool kX3, bool kY3>
+__global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const GenStripParams p)
+{
+  using R = LinearReduce;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  GenSrgba8Smem& sm = *reinterpret_cast<GenSrgba8Smem*>(smemRaw);
+  genSrgba8Init(sm, p.tables);
+  __syncthreads();
+  const unsigned char* dec = reinterpret_cast<const unsigned char*>(sm.decode);
+  const unsigned char* enc = reinterpret_cast<const unsigned char*>(sm.encode);
+
+  const uint32_t  lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, laneOff = lane * 4u;
+  const LevelView L0 = p.lv[0], L1 = p.lv[1], L2 = p.lv[2];
+  const float     fH1 = float(L1.h), fW1 = float(L1.w);
+  const float     rcpY1 = kY3 ? genRcp(L1.h) : 0.f, rcpX1 = kX3 ? genRcp(L1.w) : 0.f;
+  // second level (uniform run-time branches)
+  const bool  x3b = kLevels == 2 && (L1.w & 1u), y3b = kLevels == 2 && (L1.h & 1u);
+  const float fH2 = kLevels == 2 ? float(L2.h) : 0.f, fW2 = kLevels == 2 ? float(L2.w) : 0.f;
+  const float rcpY2 = y3b ? genRcp(L2.h) : 0.f, rcpX2 = x3b ? genRcp(L2.w) : 0.f;
+
+  const uint32_t numTasks = p.stripsX * p.segsY;
+  for(uint32_t task = blockIdx.x + gridDim.x * warp; task < numTasks; task += gridDim.x * kGenWarps)
+  {
+    const uint32_t sx = task % p.stripsX, sy = task / p.stripsX;
+    const uint32_t x1 = sx * 30u + lane;  // this lane's column of level +1
+    const uint32_t c0 = 2u * x1;          // its first source column
+    const bool     srcA = c0 < L0.w, srcB = c0 + 1u < L0.w;
+    const bool     out1 = x1 < L1.w && lane < 31u;
+    Taps           tx1{0.f, 0.f, 0.f};
+    if(kX3)
+      tx1 = genTaps(rcpX1, fW1, x1);
+    // level +2: even lanes own column x2 = 15 sx + lane / 2
+    const uint32_t x2   = sx * 15u + (lane >> 1);
+    const bool     out2 = kLevels == 2 && !(lane & 1u) && lane < 30u && x2 < L2.w;
+    Taps           tx2{0.f, 0.f, 0.f};
+    if(kLevels == 2 && x3b)
+      tx2 = genTaps(rcpX2, fW2, x2);
+
+    // rows of level +1 handled by this task: [ya, yb]
+    uint32_t ya, yb, r2a = 0;
+    if(kLevels == 2)
+    {
+      r2a                = sy * p.segRows;
+      const uint32_t r2b = min(r2a + p.segRows, L2.h);
+      ya                 = 2u * r2a;
+      yb                 = min(y3b ? 2u * r2b : 2u * r2b - 1u, L1.h - 1u);
+    }
+    else
+    {
+      ya = sy * p.segRows;
+      yb = min(ya + p.segRows, L1.h) - 1u;
+    }
+
+    const unsigned char* src = L0.ptr + size_t(2u * ya) * L0.pitch + size_t(c0) * 4u;  // source row 2*ya
+    unsigned char*       d1  = L1.ptr + size_t(ya) * L1.pitch + size_t(x1) * 4u;
+    auto                 load2 = [&](const unsigned char* row, uint32_t& a, uint32_t& b) {
+      a = srcA ? __ldg(reinterpret_cast<const uint32_t*>(row)) : 0u;
+      b = srcB ? __ldg(reinterpret_cast<const uint32_t*>(row + 4)) : 0u;
+    };
+
+    float4 carryA = make_float4(0.f, 0.f, 0.f, 0.f), carryB = carryA;  // decoded source row 2y (3-tap only)
+    if(kY3)
+    {
+      uint32_t a, b;
+      load2(src, a, b);
+      carryA = genDecode(dec, laneOff, a);
+      carryB = genDecode(dec, laneOff, b);
+    }
+    // raw words of the next output row's new source rows (prefetched)
+    uint32_t n0a, n0b, n1a, n1b;
+    {
+      const unsigned char* r = kY3 ? src + L0.pitch : src;
+      load2(r, n0a, n0b);
+      load2(r + L0.pitch, n1a, n1b);
+    }
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;  // last level +1 values of this column
+
+    for(uint32_t y = ya; y <= yb; ++y, src += 2u * L0.pitch, d1 += L1.pitch)
+    {
+      const uint32_t m0a = n0a, m0b = n0b, m1a = n1a, m1b = n1b;
+      if(y < yb)
+      {
+        const unsigned char* r = (kY3 ? src + L0.pitch : src) + 2u * L0.pitch;
+        load2(r, n0a, n0b);
+        load2(r + L0.pitch, n1a, n1b);
+      }
+      // ---- vertical reduction of this lane's two source columns ----
+      const float4 vA0 = genDecode(dec, laneOff, m0a), vB0 = genDecode(dec, laneOff, m0b);
+      const float4 vA1 = genDecode(dec, laneOff, m1a), vB1 = genDecode(dec, laneOff, m1b);
+      float4       hA, hB;
+      if(kY3)
+      {
+        const Taps ty = genTaps(rcpY1, fH1, y);
+        hA            = R::reduce(ty.w0, carryA, ty.w1, vA0, ty.w2, vA1);
+        hB            = R::reduce(ty.w0, carryB, ty.w1, vB0, ty.w2, vB1);
+        carryA        = vA1;
+        carryB        = vB1;
+      }
+      else
+      {
+        hA = R::reduce2(vA0, vA1);
+        hB = R::reduce2(vB0, vB1);
+      }
+      // ---- horizontal reduction ----
+      float4 o;
+      if(kX3)
+      {
+        const float4 hC = shflDown(hA, 1);  // column 2 x1 + 2 = first column of lane + 1
+        o               = R::reduce(tx1.w0, hA, tx1.w1, hB, tx1.w2, hC);
+      }
+      else
+        o = R::reduce2(hA, hB);
+      if(out1)
+        *reinterpret_cast<uint32_t*>(d1) = genEncWord(enc, o);
+
+      // ---- level +2, float32 carry ----
+      if(kLevels == 2)
+      {
+        const uint32_t j = y - ya;  // row index inside the segment
+        float4         g;
+        bool           emit = false;
+        uint32_t       y2   = 0;
+        if(y3b)
+        {
+          // rows 2 y2, 2 y2 + 1, 2 y2 + 2: emit when the third arrives (even j >= 2)
+          if(!(j & 1u))
+          {
+            if(j >= 2u)
+            {
+              y2            = r2a + (j >> 1) - 1u;
+              const Taps ty = genTaps(rcpY2, fH2, y2);
+              g             = R::reduce(ty.w0, q0, ty.w1, q1, ty.w2, o);
+              emit          = true;
+            }
+            q0 = o;
+          }
+          else
+            q1 = o;
+        }
+        else
+        {
+          if(j & 1u)
+          {
+            y2   = r2a + (j >> 1);
+            g    = R::reduce2(q0, o);
+            emit = true;
+          }
+          else
+            q0 = o;
+        }
+        if(emit)  // warp-uniform
+        {
+          const float4 g1 = shflDown(g, 1);
+          float4       o2;
+          if(x3b)
+          {
+            const float4 g2 = shflDown(g, 2);
+            o2              = R::reduce(tx2.w0, g, tx2.w1, g1, tx2.w2, g2);
+          }
+          else
+            o2 = R::reduce2(g, g1);
+          if(out2)
+            *reinterpret_cast<uint32_t*>(L2.ptr + size_t(y2) * L2.pitch + size_t(x2) * 4u) = genEncWord(enc, o2);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace nvpyr
