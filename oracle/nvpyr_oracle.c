@@ -31,8 +31,9 @@
  *             truncates alpha).
  *
  * Numerics pinned for Oracle A (implementation-defined in GLSL):
- *   - float32 everywhere, round-to-nearest-even, no FMA contraction
- *     (compile with -ffp-contract=off)
+ *   - float32 everywhere, round-to-nearest-even; the compiler may contract nothing
+ *     (compile with -ffp-contract=off); the ONE contraction of the contract is explicit:
+ *     the 3-tap REDUCE a0*v0 + a1*v1 + a2*v2 is mul, fma, fma (see a_reduce)
  *   - sRGB decode = 256-entry table, sRGB encode = 255 thresholds, both
  *     committed as bit patterns in vk_compute_mipmaps_b200/csrc/srgb_tables.inc
  *     and verified against the srgb.h formulas (nvo_*_formula below)
@@ -377,10 +378,19 @@ static inline void a_store(actx* c, ivec2 p, int level, vec4 v)
   }
 }
 
-/* srgba8_mipmap_preamble.glsl:24-25; contraction pinned OFF. */
+/* srgba8_mipmap_preamble.glsl:24-25: out_ = a0 * v0 + a1 * v1 + a2 * v2.  GLSL lets the
+ * implementation contract this (no `precise`), and a GPU compiler does: one multiply and two
+ * fused multiply-adds, left to right.  Pinned to exactly that form (fmaf is correctly rounded):
+ *   fma(a2, v2, fma(a1, v1, a0 * v0)) */
+static inline float a_reduce1(float a0, float v0, float a1, float v1, float a2, float v2)
+{
+  return fmaf(a2, v2, fmaf(a1, v1, a0 * v0));
+}
 static inline vec4 a_reduce(float a0, vec4 v0, float a1, vec4 v1, float a2, vec4 v2)
 {
-  return v_add(v_add(v_scale(a0, v0), v_scale(a1, v1)), v_scale(a2, v2));
+  vec4 r = {a_reduce1(a0, v0.x, a1, v1.x, a2, v2.x), a_reduce1(a0, v0.y, a1, v1.y, a2, v2.y),
+            a_reduce1(a0, v0.z, a1, v1.z, a2, v2.z), a_reduce1(a0, v0.w, a1, v1.w, a2, v2.w)};
+  return r;
 }
 /* :35 */
 static inline vec4 a_reduce2(vec4 v0, vec4 v1)

@@ -429,7 +429,8 @@ const uint64_t kTailMaxTexels = [] {
   const char* e = getenv("NVPYR_TAIL_MAX_TEXELS");
   return e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : 512ull * 512ull;
 }();
-constexpr uint64_t kSoloMaxTexels = 64ull * 64ull;
+constexpr uint64_t kSoloMaxTexelsFast    = 64ull * 64ull;  // one 64x64 tile
+constexpr uint64_t kSoloMaxTexelsGeneral = 32ull * 32ull;  // one 8x8 tile of level +2
 
 template <class F>
 struct TailFunctors
@@ -498,7 +499,8 @@ nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r)
     {
       // grid step i, then as many solo steps as follow (level sizes only shrink)
       int count = 1;
-      while(i + count < n && texels(i + count) <= kSoloMaxTexels && count < int(kMaxTailSteps))
+      while(i + count < n && count < int(kMaxTailSteps)
+            && texels(i + count) <= (steps[i + count].pipeline == 1 ? kSoloMaxTexelsFast : kSoloMaxTexelsGeneral))
         ++count;
       st = launchTail<F>(ctx, r, steps + i, count);
       i += count;

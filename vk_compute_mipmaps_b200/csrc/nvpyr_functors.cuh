@@ -22,9 +22,9 @@
 //
 // Shipped instances: Srgba8 (nvpro_pyramid/srgba8_mipmap_preamble.glsl) and
 // Rgba32f (identity load/store).  All float arithmetic uses the *_rn intrinsics
-// so that nvcc can never contract a*b+c into an FMA: the numerics contract
-//  is float32, round-to-nearest, no contraction, in the pairing order
-// of the reference shader.
+// so that nvcc never decides about contraction: the numerics contract
+// is float32, round-to-nearest, the pairing order of the reference shader, and
+// exactly one explicit contraction (the 3-tap REDUCE = mul, fma, fma).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -93,10 +93,17 @@ __device__ __forceinline__ float4 f4scale(float s, float4 a)
 struct LinearReduce
 {
   using Value = float4;
-  // a0*v0 + a1*v1 + a2*v2, left-associated, not contracted.
+  // a0*v0 + a1*v1 + a2*v2 contracted the way a GPU compiler contracts the GLSL expression
+  // (srgba8_mipmap_preamble.glsl:24-25 has no `precise`): mul, fma, fma, left to right.
+  // This is the only contraction of the numerics contract, and it is explicit.
+  __device__ __forceinline__ static float reduce1(float a0, float v0, float a1, float v1, float a2, float v2)
+  {
+    return __fmaf_rn(a2, v2, __fmaf_rn(a1, v1, __fmul_rn(a0, v0)));
+  }
   __device__ __forceinline__ static Value reduce(float a0, Value v0, float a1, Value v1, float a2, Value v2)
   {
-    return f4add(f4add(f4scale(a0, v0), f4scale(a1, v1)), f4scale(a2, v2));
+    return make_float4(reduce1(a0, v0.x, a1, v1.x, a2, v2.x), reduce1(a0, v0.y, a1, v1.y, a2, v2.y),
+                       reduce1(a0, v0.z, a1, v1.z, a2, v2.z), reduce1(a0, v0.w, a1, v1.w, a2, v2.w));
   }
   __device__ __forceinline__ static Value reduce2(Value v0, Value v1) { return f4scale(0.5f, f4add(v0, v1)); }
   // 0.25 * ((v00 + v01) + (v10 + v11)): the caller chooses which neighbours share a

@@ -55,9 +55,36 @@ __device__ __forceinline__ void genSrgba8Init(GenSrgba8Smem& sm, const DeviceTab
                                 kEncEntriesPadded / 4);
 }
 
-__device__ __forceinline__ float4 genDecode(const unsigned char* dec, uint32_t laneOff, uint32_t w)
+// Packed float32 pairs (FMUL2 / FADD2, two IEEE roundings per issue slot): see nvpyr_fast_srgba8.cuh.
+__device__ __forceinline__ F2 mul2(F2 a, F2 b)
 {
-  return make_float4(dec8<0>(dec, w, laneOff), dec8<1>(dec, w, laneOff), dec8<2>(dec, w, laneOff), decAlpha(w));
+  F2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c)
+{
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+// a0*v0 + a1*v1 + a2*v2 as mul, fma, fma (the contract's one explicit contraction, see
+// LinearReduce::reduce); weights come as (w, w) pairs.  FMUL2/FFMA2: two lanes per issue slot.
+__device__ __forceinline__ V4 genReduce3(F2 a0, V4 v0, F2 a1, V4 v1, F2 a2, V4 v2)
+{
+  V4 r;
+  r.rg = fma2(a2, v2.rg, fma2(a1, v1.rg, mul2(a0, v0.rg)));
+  r.ba = fma2(a2, v2.ba, fma2(a1, v1.ba, mul2(a0, v0.ba)));
+  return r;
+}
+// 0.5 * (v0 + v1) (srgba8_mipmap_preamble.glsl:35)
+__device__ __forceinline__ V4 genReduce2(V4 v0, V4 v1)
+{
+  const F2 half = pack2(0.5f, 0.5f);
+  V4       r;
+  r.rg = mul2(add2(v0.rg, v1.rg), half);
+  r.ba = mul2(add2(v0.ba, v1.ba), half);
+  return r;
 }
 
 // srgbFromLinear with both clamps (weighted sums may exceed 1 by an ulp); code in bits 16..23.
@@ -78,14 +105,15 @@ __device__ __forceinline__ uint32_t genEncWord(const unsigned char* enc, float4 
 // Weights of destination index i of n (glsl:582-586): w0 = rcp*(n-i), w1 = rcp*n, w2 = 1-w0-w1.
 struct Taps
 {
-  float w0, w1, w2;
+  F2 w0, w1, w2;  // each weight duplicated into both halves of a pair
 };
 __device__ __forceinline__ Taps genTaps(float rcp, float fn, uint32_t i)
 {
-  Taps t;
-  t.w0 = __fmul_rn(rcp, __fsub_rn(fn, float(i)));
-  t.w1 = __fmul_rn(rcp, fn);
-  t.w2 = __fsub_rn(__fsub_rn(1.0f, t.w0), t.w1);
+  const float w0 = __fmul_rn(rcp, __fsub_rn(fn, float(i)));
+  const float w1 = __fmul_rn(rcp, fn);
+  const float w2 = __fsub_rn(__fsub_rn(1.0f, w0), w1);
+  Taps        t;
+  t.w0 = pack2(w0, w0), t.w1 = pack2(w1, w1), t.w2 = pack2(w2, w2);
   return t;
 }
 __device__ __forceinline__ float genRcp(uint32_t n)
@@ -93,17 +121,18 @@ __device__ __forceinline__ float genRcp(uint32_t n)
   const float fn = float(n);
   return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(2.0f, fn), 1.0f));
 }
-__device__ __forceinline__ float4 shflDown(float4 v, int d)
+__device__ __forceinline__ V4 shflDown(V4 v, int d)
 {
-  return make_float4(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d),
-                     __shfl_down_sync(0xffffffffu, v.z, d), __shfl_down_sync(0xffffffffu, v.w, d));
+  V4 r;
+  r.rg.v = __shfl_down_sync(0xffffffffu, v.rg.v, d);
+  r.ba.v = __shfl_down_sync(0xffffffffu, v.ba.v, d);
+  return r;
 }
 
 // kLevels: 1 or 2.  kX3 / kY3: the first level uses 3 taps (odd source size) along x / y; otherwise 2.
 template <int kLevels, bool kX3, bool kY3>
 __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const GenStripParams p)
 {
-  using R = LinearReduce;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   GenSrgba8Smem& sm = *reinterpret_cast<GenSrgba8Smem*>(smemRaw);
   genSrgba8Init(sm, p.tables);
@@ -128,13 +157,14 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
     const uint32_t c0 = 2u * x1;          // its first source column
     const bool     srcA = c0 < L0.w, srcB = c0 + 1u < L0.w;
     const bool     out1 = x1 < L1.w && lane < 31u;
-    Taps           tx1{0.f, 0.f, 0.f};
+    const V4       zero = toV4(make_float4(0.f, 0.f, 0.f, 0.f));
+    Taps           tx1{zero.rg, zero.rg, zero.rg};
     if(kX3)
       tx1 = genTaps(rcpX1, fW1, x1);
     // level +2: even lanes own column x2 = 15 sx + lane / 2
     const uint32_t x2   = sx * 15u + (lane >> 1);
     const bool     out2 = kLevels == 2 && !(lane & 1u) && lane < 30u && x2 < L2.w;
-    Taps           tx2{0.f, 0.f, 0.f};
+    Taps           tx2{zero.rg, zero.rg, zero.rg};
     if(kLevels == 2 && x3b)
       tx2 = genTaps(rcpX2, fW2, x2);
 
@@ -160,13 +190,13 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
       b = srcB ? __ldg(reinterpret_cast<const uint32_t*>(row + 4)) : 0u;
     };
 
-    float4 carryA = make_float4(0.f, 0.f, 0.f, 0.f), carryB = carryA;  // decoded source row 2y (3-tap only)
+    V4 carryA = zero, carryB = zero;  // decoded source row 2y (3-tap only)
     if(kY3)
     {
       uint32_t a, b;
       load2(src, a, b);
-      carryA = genDecode(dec, laneOff, a);
-      carryB = genDecode(dec, laneOff, b);
+      carryA = decodeTexel(dec, laneOff, a);
+      carryB = decodeTexel(dec, laneOff, b);
     }
     // raw words of the next output row's new source rows (prefetched)
     uint32_t n0a, n0b, n1a, n1b;
@@ -175,7 +205,7 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
       load2(r, n0a, n0b);
       load2(r + L0.pitch, n1a, n1b);
     }
-    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;  // last level +1 values of this column
+    V4 q0 = zero, q1 = zero;  // last level +1 values of this column
 
     for(uint32_t y = ya; y <= yb; ++y, src += 2u * L0.pitch, d1 += L1.pitch)
     {
@@ -187,39 +217,39 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
         load2(r + L0.pitch, n1a, n1b);
       }
       // ---- vertical reduction of this lane's two source columns ----
-      const float4 vA0 = genDecode(dec, laneOff, m0a), vB0 = genDecode(dec, laneOff, m0b);
-      const float4 vA1 = genDecode(dec, laneOff, m1a), vB1 = genDecode(dec, laneOff, m1b);
-      float4       hA, hB;
+      const V4 vA0 = decodeTexel(dec, laneOff, m0a), vB0 = decodeTexel(dec, laneOff, m0b);
+      const V4 vA1 = decodeTexel(dec, laneOff, m1a), vB1 = decodeTexel(dec, laneOff, m1b);
+      V4       hA, hB;
       if(kY3)
       {
         const Taps ty = genTaps(rcpY1, fH1, y);
-        hA            = R::reduce(ty.w0, carryA, ty.w1, vA0, ty.w2, vA1);
-        hB            = R::reduce(ty.w0, carryB, ty.w1, vB0, ty.w2, vB1);
+        hA            = genReduce3(ty.w0, carryA, ty.w1, vA0, ty.w2, vA1);
+        hB            = genReduce3(ty.w0, carryB, ty.w1, vB0, ty.w2, vB1);
         carryA        = vA1;
         carryB        = vB1;
       }
       else
       {
-        hA = R::reduce2(vA0, vA1);
-        hB = R::reduce2(vB0, vB1);
+        hA = genReduce2(vA0, vA1);
+        hB = genReduce2(vB0, vB1);
       }
       // ---- horizontal reduction ----
-      float4 o;
+      V4 o;
       if(kX3)
       {
-        const float4 hC = shflDown(hA, 1);  // column 2 x1 + 2 = first column of lane + 1
-        o               = R::reduce(tx1.w0, hA, tx1.w1, hB, tx1.w2, hC);
+        const V4 hC = shflDown(hA, 1);  // column 2 x1 + 2 = first column of lane + 1
+        o           = genReduce3(tx1.w0, hA, tx1.w1, hB, tx1.w2, hC);
       }
       else
-        o = R::reduce2(hA, hB);
+        o = genReduce2(hA, hB);
       if(out1)
-        *reinterpret_cast<uint32_t*>(d1) = genEncWord(enc, o);
+        *reinterpret_cast<uint32_t*>(d1) = genEncWord(enc, toFloat4(o));
 
       // ---- level +2, float32 carry ----
       if(kLevels == 2)
       {
         const uint32_t j = y - ya;  // row index inside the segment
-        float4         g;
+        V4             g    = zero;
         bool           emit = false;
         uint32_t       y2   = 0;
         if(y3b)
@@ -231,7 +261,7 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
             {
               y2            = r2a + (j >> 1) - 1u;
               const Taps ty = genTaps(rcpY2, fH2, y2);
-              g             = R::reduce(ty.w0, q0, ty.w1, q1, ty.w2, o);
+              g             = genReduce3(ty.w0, q0, ty.w1, q1, ty.w2, o);
               emit          = true;
             }
             q0 = o;
@@ -244,7 +274,7 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
           if(j & 1u)
           {
             y2   = r2a + (j >> 1);
-            g    = R::reduce2(q0, o);
+            g    = genReduce2(q0, o);
             emit = true;
           }
           else
@@ -252,17 +282,18 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
         }
         if(emit)  // warp-uniform
         {
-          const float4 g1 = shflDown(g, 1);
-          float4       o2;
+          const V4 g1 = shflDown(g, 1);
+          V4       o2;
           if(x3b)
           {
-            const float4 g2 = shflDown(g, 2);
-            o2              = R::reduce(tx2.w0, g, tx2.w1, g1, tx2.w2, g2);
+            const V4 g2 = shflDown(g, 2);
+            o2          = genReduce3(tx2.w0, g, tx2.w1, g1, tx2.w2, g2);
           }
           else
-            o2 = R::reduce2(g, g1);
+            o2 = genReduce2(g, g1);
           if(out2)
-            *reinterpret_cast<uint32_t*>(L2.ptr + size_t(y2) * L2.pitch + size_t(x2) * 4u) = genEncWord(enc, o2);
+            *reinterpret_cast<uint32_t*>(L2.ptr + size_t(y2) * L2.pitch + size_t(x2) * 4u) =
+                genEncWord(enc, toFloat4(o2));
         }
       }
     }
