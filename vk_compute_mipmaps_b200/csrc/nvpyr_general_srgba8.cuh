@@ -39,7 +39,7 @@ struct GenStripParams
   const DeviceTables* tables;
 };
 
-constexpr int kGenWarps = 8;
+constexpr int kGenWarps = 12;  // 12 warps x 2 CTAs per SM: measured best (8: latency-bound, 16: spills)
 
 __device__ __forceinline__ void genSrgba8Init(GenSrgba8Smem& sm, const DeviceTables* t)
 {
