@@ -1,0 +1,23 @@
+// The reference's FAST pipeline shader, compiled as C++ (see glsl_shim.hpp).  Mirrors
+// nvpro_pyramid/srgba8_mipmap_fast_pipeline.comp: same define, same two includes, same main().
+// The preamble's resource declarations (sampler2D srgbTex; uimage2D imageMipLevels[16];) become
+// namespace-scope objects of this translation unit; the driver fills them through emuFastSetImage.
+#include "glsl_shim.hpp"
+namespace emu_fast {
+#define float Float
+#define NVPRO_PYRAMID_IS_FAST_PIPELINE 1
+#include "nvpro_pyramid/srgba8_mipmap_preamble.glsl"
+#include "nvpro_pyramid/nvpro_pyramid.glsl"
+#undef float
+void mainEntry() { nvproPyramidMain(); }
+uint encode(Float x) { return srgbFromLinear(x); }
+void setImage(const uimage2D* levels)
+{
+  for(int i = 0; i < 16; ++i)
+    imageMipLevels[i] = levels[i];
+  srgbTex.levels = imageMipLevels;
+}
+}  // namespace emu_fast
+void emuFastMain() { emu_fast::mainEntry(); }
+void emuFastSetImage(const uimage2D* levels) { emu_fast::setImage(levels); }
+uint emuGlslSrgbFromLinear(float x) { return emu_fast::encode(Float(x)); }

@@ -9,6 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "libnvpyr_oracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libnvpyr_ref.so")
+EMU_SO = os.path.join(ORACLE_DIR, "_ref", "libnvpyr_glsl_emu.so")
 P = C.c_void_p
 
 
@@ -32,7 +33,7 @@ def build_oracle():
     src = os.path.join(ORACLE_DIR, "nvpyr_oracle.c")
     if (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
         subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
-    if os.path.isdir("/root/reference/nvpro_pyramid") and not os.path.exists(REF_SO):
+    if os.path.isdir("/root/reference/nvpro_pyramid") and not (os.path.exists(REF_SO) and os.path.exists(EMU_SO)):
         subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"])
 
 
@@ -155,6 +156,29 @@ class Ref:
         hs = (C.c_uint32 * 40)()
         n = self.lib.ref_layout(w, h, off, ws, hs, 40)
         return [(off[i], ws[i], hs[i]) for i in range(n)]
+
+
+class GlslEmu:
+    """The reference's GLSL shaders + dispatch header executed on the CPU (oracle/glsl_emu)."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        lib.emu_run_chain.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+        lib.emu_glsl_srgb_from_linear.argtypes = [C.c_float]
+
+    def run_chain(self, chain, w, h, levels=0, have_fast=1):
+        buf = np.array(chain, dtype=np.uint8, copy=True)
+        st = C.c_uint64()
+        n = self.lib.emu_run_chain(buf.ctypes.data, w, h, levels, have_fast, C.byref(st))
+        assert n >= 0, n
+        return buf, n, st.value
+
+
+def load_emu():
+    build_oracle()
+    if not os.path.exists(EMU_SO):
+        return None
+    return GlslEmu(C.CDLL(EMU_SO))
 
 
 def load_oracle():

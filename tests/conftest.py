@@ -29,6 +29,15 @@ def ref():
 
 
 @pytest.fixture(scope="session")
+def emu():
+    import _oracle
+    e = _oracle.load_emu()
+    if e is None:
+        pytest.skip("oracle/_ref/libnvpyr_glsl_emu.so not built (reference tree absent)")
+    return e
+
+
+@pytest.fixture(scope="session")
 def nv():
     import vk_compute_mipmaps_b200 as m
     return m

@@ -156,3 +156,58 @@ def test_oracle_a_rgba32f_close_to_float64(oracle):
         got = a[4 * off:4 * (off + cw * ch)].reshape(ch, cw, 4)
         np.testing.assert_allclose(got, cur, rtol=1e-6, atol=0)
         off += cw * ch
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Oracle A against the reference's OWN shader sources, executed (oracle/glsl_emu): nvproCmdPyramidDispatch from
+# nvpro_pyramid_dispatch.hpp drives nvpro_pyramid.glsl + srgba8_mipmap_preamble.glsl compiled as C++, one fiber
+# per invocation, shuffles and barriers as scheduling points.
+
+EMU_SIZES = [(64, 64), (256, 256), (128, 64), (64, 128), (16, 48), (32, 32), (96, 160), (8, 8), (4, 4), (192, 320),
+             (63, 63), (100, 37), (260, 260), (136, 512), (120, 72), (160, 96), (240, 144), (1, 9), (9, 1), (5, 5),
+             (2, 2), (33, 2), (255, 255), (254, 254), (17, 129), (1, 1 << 5), (3, 3), (6, 10), (129, 129), (448, 64),
+             (512, 512), (511, 300)]
+
+
+@pytest.mark.parametrize("size", EMU_SIZES, ids=lambda s: f"{s[0]}x{s[1]}")
+def test_oracle_a_equals_executed_reference_shaders(oracle, emu, size):
+    w, h = size
+    for seed, make in ((1, _oracle.random_level0), (2, lambda w, h, s: _oracle.smooth_level0(w, h, s))):
+        l0 = make(w, h, seed)
+        for have_fast in (1, 0):
+            want, stores = oracle.shader_chain(l0, w, h, force_general=not have_fast)
+            got, dispatches, emu_stores = emu.run_chain(oracle.new_chain(l0, w, h), w, h, 0, have_fast)
+            assert (got == want).all(), (size, have_fast)
+            assert emu_stores == stores  # same number of imageStore calls, duplicates included
+            assert dispatches == len(oracle.plan(w, h, 0, have_fast))
+
+
+def test_oracle_a_equals_executed_reference_shaders_partial_levels(oracle, emu):
+    w, h = 256, 128
+    l0 = _oracle.random_level0(w, h, 3)
+    for levels in (2, 3, 5, 8):
+        want, _ = oracle.shader_chain(l0, w, h, levels=levels)
+        got, _, _ = emu.run_chain(oracle.new_chain(l0, w, h, levels=levels), w, h, levels, 1)
+        assert (got == want).all(), levels
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_fixtures_through_executed_shaders(oracle, emu, path):
+    g = np.load(path)
+    w, h = int(g["width"]), int(g["height"])
+    l0 = g["level0"].reshape(-1)
+    got, _, _ = emu.run_chain(oracle.new_chain(l0, w, h), w, h)
+    assert hashlib.sha256(got.tobytes()).hexdigest() == str(g["oracle_a_sha256"])
+
+
+def test_glsl_encode_equals_pinned_thresholds(emu):
+    """srgbFromLinear of srgba8_mipmap_preamble.glsl:110-121, as compiled by the shim, has exactly the pinned
+    thresholds (so the GLSL twin and the C++ twin in shaders/srgb.h agree on every float)."""
+    import re
+    src = open(os.path.join(_oracle.ROOT, "vk_compute_mipmaps_b200", "csrc", "srgb_tables.inc")).read()
+    thr = [int(t, 16) for t in re.findall(r"0x([0-9a-f]{8})u", src.split("NVPYR_SRGB_ENCODE_THRESHOLD_BITS[255]")[1])]
+    f = emu.lib.emu_glsl_srgb_from_linear
+    for c, bits in enumerate(thr, start=1):
+        at = np.array([bits], dtype=np.uint32).view(np.float32)[0]
+        below = np.array([bits - 1], dtype=np.uint32).view(np.float32)[0]
+        assert f(float(at)) == c and f(float(below)) == c - 1
