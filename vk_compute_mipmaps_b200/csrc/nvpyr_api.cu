@@ -224,10 +224,10 @@ nvpyrStatus launchFastSrgba8T(const DeviceContext& ctx, FastParams p, cudaStream
   p.tilesY                 = (p.lv[0].h + tileH - 1u) / tileH;
   const size_t smem = sizeof(Srgba8FastSmem);
   int          grid = 1;
-  nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M>, smem, ctx, uint64_t(p.tilesX) * p.tilesY, &grid, 512);
+  nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M>, smem, ctx, uint64_t(p.tilesX) * p.tilesY, &grid, kFastWarps * 32);
   if(st != NVPYR_SUCCESS)
     return st;
-  fastSrgba8Kernel<M><<<grid, 512, smem, stream>>>(p);
+  fastSrgba8Kernel<M><<<grid, kFastWarps * 32, smem, stream>>>(p);
   NVPYR_CUDA(cudaGetLastError());
   ++g_launchCount;
   return NVPYR_SUCCESS;
