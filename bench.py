@@ -5,7 +5,9 @@
 
 Workload (BASELINE.json configs[2], the configuration the metric is quoted on): full mip chain of a synthetic
 16384x16384 sRGBA8 image, 15 levels, 1 431 655 764 algorithmic bytes (level 0 read once + every other level
-written once).  A "step" is one full-chain generation.  Two distinct 1.43 GB chains are alternated, each far
+written once).  Level 0 is the Julia-set texture the reference demo mip-maps every frame at this very size
+(--input julia, default); uniform random bytes (the worst case for shared-memory bank conflicts) and a smooth
+gradient are timed in the same run and reported under config.other_inputs.  A "step" is one full-chain generation.  Two distinct 1.43 GB chains are alternated, each far
 larger than the 126 MB L2, so level 0 is never cache resident.  At N > 1 every rank runs the same step on its own
 image (independent units, no data-path collective): weak scaling, value = N * bytes / max-over-ranks time.
 
@@ -255,9 +257,15 @@ def run_gpu_arm(args):
         b = torch.empty(chain_bytes, dtype=torch.uint8, device=dev)
         b[:4 * W * H] = torch.randint(0, 256, (4 * W * H,), dtype=torch.uint8, device=dev, generator=gen)
         bufs.append(b)
+    def fill_input(name):
+        if name == "random":
+            for b in bufs:
+                b[:4 * W * H] = torch.randint(0, 256, (4 * W * H,), dtype=torch.uint8, device=dev, generator=gen)
+        else:
+            {"julia": fill_julia, "gradient": fill_gradient}[name](bufs[0][:4 * W * H].view(H, W, 4), W, H)
+            bufs[1][:4 * W * H].copy_(bufs[0][:4 * W * H])
     if args.input != "random":
-        {"julia": fill_julia, "gradient": fill_gradient}[args.input](bufs[0][:4 * W * H].view(H, W, 4), W, H)
-        bufs[1][:4 * W * H].copy_(bufs[0][:4 * W * H])
+        fill_input(args.input)
     stream = torch.cuda.current_stream()
 
     def step(i):
@@ -303,9 +311,8 @@ def run_gpu_arm(args):
     # ---- same chain on the other synthetic inputs of SURVEY 8d (bytes moved are identical) ----
     other_inputs = {}
     if rank == 0 and not args.no_other_inputs:
-        for name, fill in (("julia", fill_julia), ("gradient", fill_gradient)):
-            fill(bufs[0][:4 * W * H].view(H, W, 4), W, H)
-            bufs[1][:4 * W * H].copy_(bufs[0][:4 * W * H])
+        for name in [n for n in ("julia", "random", "gradient") if n != args.input]:
+            fill_input(name)
             for i in range(3):
                 step(i)
             torch.cuda.synchronize()
@@ -372,8 +379,9 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "synthetic 16384x16384 sRGBA8 full mip chain, 15 levels, uniform random bytes "
-                               "(BASELINE configs[2])",
+        "config": {"workload": "synthetic 16384x16384 sRGBA8 full mip chain, 15 levels (BASELINE configs[2]); level 0 = "
+                               + {"julia": "the reference demo's Julia-set texture", "random": "uniform random bytes",
+                                  "gradient": "smooth opaque gradient"}[args.input],
                    "algorithmic_bytes_per_step": chain_bytes, "us_per_chain": 1e3 * ms_per_step,
                    "l2_policy": "inputs larger than L2: two distinct 1.43 GB chains alternated",
                    "per_rank": "one chain per step per rank, no collective", "launches_per_chain": launches / args.steps,
@@ -400,8 +408,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-inputs", action="store_true")
-    ap.add_argument("--input", default="random", choices=["random", "julia", "gradient"],
-                    help="level-0 content of the headline loop (default: uniform random bytes, the worst case)")
+    ap.add_argument("--input", default="julia", choices=["random", "julia", "gradient"],
+                    help="level-0 content of the headline loop. Default: the Julia-set texture the reference demo "
+                         "regenerates and mip-maps every frame at its default size 16384x16384 "
+                         "(demo_app/app_args.hpp:25, demo_app/julia.cpp:65-81). 'random' = uniform random bytes, the "
+                         "worst case for the encode table's bank conflicts; every input is timed and reported.")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -1,0 +1,27 @@
+#!/bin/bash
+# compute-sanitizer over a small but representative set of dispatches (all kernels, all schedule classes).
+# usage (GPU box): tools/sanitize.sh [memcheck|racecheck|initcheck|synccheck]
+TOOL=${1:-memcheck}
+cat > /tmp/san_driver.py <<'PY'
+import sys, numpy as np, torch
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import vk_compute_mipmaps_b200 as nv, _oracle
+o = _oracle.load_oracle()
+cases = [(256, 256, 0, False), (1024, 512, 0, False), (255, 255, 0, False), (260, 260, 0, False), (136, 512, 0, False),
+         (777, 1031, 0, False), (1200, 900, 0, False), (64, 64, 1, False), (100, 37, 1, False), (96, 160, 0, True)]
+for (w, h, fmt, fg) in cases:
+    l0 = _oracle.random_level0(w, h, 5, fmt=fmt)
+    dt = torch.uint8 if fmt == 0 else torch.float32
+    buf = torch.zeros(nv.chain_bytes(w, h, 0, fmt) // (1 if fmt == 0 else 4), dtype=dt, device='cuda')
+    buf[:4 * w * h] = torch.from_numpy(l0).cuda()
+    nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(format=fmt, fast_pipeline=not fg), w, h, image=buf)
+    torch.cuda.synchronize()
+    want = o.shader_chain(l0, w, h, fmt=fmt, force_general=fg)[0]
+    got = buf.cpu().numpy()
+    assert (got.view(np.uint8) == want.view(np.uint8)).all(), (w, h, fmt, fg)
+print('sanitize driver ok')
+PY
+for tail in 262144 0; do
+  echo "== $TOOL NVPYR_TAIL_MAX_TEXELS=$tail"
+  NVPYR_TAIL_MAX_TEXELS=$tail compute-sanitizer --tool $TOOL --kernel-regex kns=nvpyr --print-limit 20 python /tmp/san_driver.py 2>&1 | tail -6
+done
