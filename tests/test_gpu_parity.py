@@ -299,6 +299,54 @@ def test_generate_host_round_trip(nv, cuda, oracle):
     assert (gotf.view(np.uint32) == wantf.view(np.uint32)).all()
 
 
+def test_generate_host_banded_pipeline(nv, cuda, oracle):
+    """nvpyrGenerateHost cuts level 0 into bands and overlaps upload / kernels / download on three streams
+    when the chain starts with a fast step.  NVPYR_HOST_BAND_BYTES (read at library load, hence the
+    subprocess) shrinks the bands so that sizes the oracle handles exercise many bands, ragged last bands,
+    the in-place (staging buffer) mode, the premultiply pre-pass per band and rgba32f."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import _oracle, vk_compute_mipmaps_b200 as nv
+o = _oracle.load_oracle()
+# (w, h): 6-level first step with 9 bands + ragged last; M = 2 (260 = 4 * 65); M = 3; wide
+for (w, h) in [(512, 1088), (260, 780), (1000, 1016), (2048, 256)]:
+    l0 = _oracle.random_level0(w, h, w + h)
+    want, _ = o.shader_chain(l0, w, h)
+    got = nv.generate_host(l0, w, h)
+    assert (got == want).all(), ("separate", w, h)
+    chain = np.zeros(nv.chain_bytes(w, h), np.uint8)
+    chain[:4 * w * h] = l0.ravel()
+    nv.generate_host(chain[:4 * w * h], w, h, out=chain)
+    assert (chain == want).all(), ("in place", w, h)
+    got = nv.generate_host(l0, w, h, mip_levels=3)
+    assert (got == o.shader_chain(l0, w, h, levels=3)[0]).all(), ("3 levels", w, h)
+# premultiply: level 0 changes, so it must come back even in place
+w, h = 256, 1024
+l0 = _oracle.random_level0(w, h, 5)
+pm = o.premultiply(l0)
+want, _ = o.shader_chain(pm, w, h)
+chain = np.zeros(nv.chain_bytes(w, h), np.uint8)
+chain[:4 * w * h] = l0.ravel()
+nv.generate_host(chain[:4 * w * h], w, h, flags=nv.FLAG_PREMULTIPLY_ALPHA, out=chain)
+assert (chain == want).all(), "premultiply in place"
+# rgba32f
+w, h = 128, 512
+l0f = _oracle.random_level0(w, h, 2, fmt=1)
+wantf, _ = o.shader_chain(l0f, w, h, fmt=1)
+gotf = nv.generate_host(l0f, w, h, fmt=nv.FORMAT_RGBA32F)
+assert (gotf.view(np.uint32) == wantf.view(np.uint32)).all(), "rgba32f"
+print("banded ok", nv.launch_count())
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NVPYR_HOST_BAND_BYTES=str(128 * 1024))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    # 512x1088 in 128 KB bands = 64-row bands -> 17 launches for step 0 alone: banding really happened
+    assert int(out.stdout.split()[-1]) > 60, out.stdout
+
+
 def test_other_stream(nv, cuda, oracle):
     w, h = 320, 192
     l0 = _oracle.random_level0(w, h, 13)

@@ -89,6 +89,8 @@ bool buildHostTables(DeviceTables& t)
 // Tail launches in flight at the same time each need their own ticket counter.
 constexpr uint32_t kTicketPool = 4096;
 
+constexpr uint32_t kMaxHostBands = 64;
+
 struct DeviceContext
 {
   int           device   = -1;
@@ -99,6 +101,10 @@ struct DeviceContext
   void*         scratch  = nullptr;  // nvpyrGenerateHost staging chain
   size_t        scratchBytes = 0;
   std::mutex    scratchMutex;
+  // nvpyrGenerateHost pipeline: upload, compute and download run on three streams so that the two
+  // PCIe directions and the kernels overlap band by band (created on first use, under scratchMutex).
+  cudaStream_t  hostUp = nullptr, hostRun = nullptr, hostDown = nullptr;
+  cudaEvent_t   hostEvUp[kMaxHostBands] = {}, hostEvRun[kMaxHostBands + 1] = {};
 };
 
 std::mutex                  g_ctxMutex;
@@ -483,15 +489,17 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
   return NVPYR_SUCCESS;
 }
 
+// firstStep > 0: the steps before it have been enqueued by the caller (nvpyrGenerateHost runs step 0
+// band by band).
 template <class F>
-nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r)
+nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0)
 {
   nvpyrPlanStep steps[NVPYR_MAX_STEPS];
   const int     n = buildPlan(r.w, r.h, r.levels, defaultGeneralDispatcher, r.fast, steps, NVPYR_MAX_STEPS);
   if(n < 0)
     return NVPYR_ERROR_INVALID_VALUE;
   auto texels = [&](int i) { return uint64_t(steps[i].srcWidth) * steps[i].srcHeight; };
-  for(int i = 0; i < n;)
+  for(int i = firstStep; i < n;)
   {
     const nvpyrPlanStep& s = steps[i];
     nvpyrStatus          st;
@@ -551,6 +559,127 @@ nvpyrStatus dispatchResolved(const ResolvedDesc& r)
   if(r.levels <= 1)
     return NVPYR_SUCCESS;
   return r.format == NVPYR_FORMAT_SRGBA8 ? runPlan<Srgba8>(*ctx, r) : runPlan<Rgba32f>(*ctx, r);
+}
+
+// ------------------------------------------------- host round trip, pipelined
+nvpyrStatus hostPipelineInit(DeviceContext& ctx)
+{
+  if(ctx.hostUp != nullptr)
+    return NVPYR_SUCCESS;
+  cudaStream_t s[3] = {};
+  for(int i = 0; i < 3; ++i)
+    NVPYR_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+  for(uint32_t i = 0; i < kMaxHostBands; ++i)
+    NVPYR_CUDA(cudaEventCreateWithFlags(&ctx.hostEvUp[i], cudaEventDisableTiming));
+  for(uint32_t i = 0; i <= kMaxHostBands; ++i)
+    NVPYR_CUDA(cudaEventCreateWithFlags(&ctx.hostEvRun[i], cudaEventDisableTiming));
+  ctx.hostRun = s[1], ctx.hostDown = s[2];
+  ctx.hostUp  = s[0];  // last: marks the pipeline as complete
+  return NVPYR_SUCCESS;
+}
+
+// Band height (rows of level 0) of the pipelined round trip; 0 = do not band.  NVPYR_HOST_BAND_BYTES
+// overrides the target band size (0 disables banding).
+const uint64_t kHostBandBytes = [] {
+  const char* e = getenv("NVPYR_HOST_BAND_BYTES");
+  return e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : 32ull << 20;
+}();
+
+// Upload, generate, download -- the shape of minimal_app (minimal_mipmaps.cpp:134-217) -- with the three
+// stages overlapped.  When the chain starts with a fast-pipeline step of M >= 2 levels, level 0 is cut
+// into bands of whole tile rows (a multiple of 2^M rows: no texel of levels 1..M depends on two bands,
+// and the float32 expression trees are untouched).  Band b is uploaded on stream `hostUp`; the step runs on it on
+// `hostRun` as soon as it has arrived; its rows of levels 1 and 2 (and 0, unless the caller's chain
+// already holds it) go back on `hostDown` while band b+1 is still arriving: both PCIe directions and the
+// SMs are busy at once.  The rest of the plan and the small levels follow in one piece.
+// In place (hostChain == hostLevel0, the reference's single staging buffer, scoped_image.hpp:436-453)
+// level 0 is not downloaded again unless the premultiply pre-pass changed it.
+template <class F>
+nvpyrStatus generateHostPipelined(DeviceContext& ctx, const ResolvedDesc& r, const void* hostLevel0, void* hostChain,
+                                  uint64_t chainBytes)
+{
+  const unsigned char* hin      = static_cast<const unsigned char*>(hostLevel0);
+  unsigned char*       hout     = static_cast<unsigned char*>(hostChain);
+  unsigned char*       dev      = r.lv[0].ptr;
+  const uint64_t       rowBytes = uint64_t(r.w) * r.texelBytes, level0Bytes = rowBytes * r.h;
+  const bool           premul   = r.flags & NVPYR_FLAG_PREMULTIPLY_ALPHA;
+  const bool           level0Back = premul || hostChain != hostLevel0;
+
+  nvpyrPlanStep steps[NVPYR_MAX_STEPS];
+  const int     n = r.levels > 1 ? buildPlan(r.w, r.h, r.levels, defaultGeneralDispatcher, r.fast, steps, NVPYR_MAX_STEPS) : 0;
+  if(n < 0)
+    return NVPYR_ERROR_INVALID_VALUE;
+
+  uint32_t bandRows = 0, M = 0;
+  if(n > 0 && steps[0].pipeline == 1 && steps[0].levelCount >= 2 && kHostBandBytes != 0 && level0Bytes >= 2 * kHostBandBytes)
+  {
+    M                   = steps[0].levelCount;
+    const uint32_t unit = std::max(8u, 1u << M);  // tile height of the fast kernels
+    uint64_t       rows = std::max<uint64_t>(1, kHostBandBytes / rowBytes);
+    rows                = (rows + unit - 1) / unit * unit;
+    const uint64_t minRows = (uint64_t(r.h) + kMaxHostBands - 1) / kMaxHostBands;
+    if(rows < minRows)
+      rows = (minRows + unit - 1) / unit * unit;
+    bandRows = uint32_t(std::min<uint64_t>(rows, r.h));
+  }
+
+  if(bandRows == 0 || bandRows >= r.h)
+  {
+    // One piece: upload, whole plan, download.
+    NVPYR_CUDA(cudaMemcpyAsync(dev, hin, level0Bytes, cudaMemcpyHostToDevice, ctx.hostRun));
+    nvpyrStatus st = dispatchResolved(r);
+    if(st != NVPYR_SUCCESS)
+      return st;
+    const uint64_t from = level0Back ? 0 : level0Bytes;
+    if(chainBytes > from)
+      NVPYR_CUDA(cudaMemcpyAsync(hout + from, dev + from, chainBytes - from, cudaMemcpyDeviceToHost, ctx.hostRun));
+    return NVPYR_SUCCESS;
+  }
+
+  const uint32_t bandLevels = 2;  // levels 1..2 travel back band by band, the small rest at the end
+  uint32_t       band       = 0;
+  for(uint32_t row0 = 0; row0 < r.h; row0 += bandRows, ++band)
+  {
+    const uint32_t rows = std::min(bandRows, r.h - row0);
+    NVPYR_CUDA(cudaMemcpyAsync(dev + row0 * rowBytes, hin + row0 * rowBytes, rows * rowBytes, cudaMemcpyHostToDevice, ctx.hostUp));
+    NVPYR_CUDA(cudaEventRecord(ctx.hostEvUp[band], ctx.hostUp));
+    NVPYR_CUDA(cudaStreamWaitEvent(ctx.hostRun, ctx.hostEvUp[band], 0));
+    if(premul)
+    {
+      nvpyrStatus st = launchPremultiply(ctx, dev + row0 * rowBytes, dev + row0 * rowBytes, uint64_t(rows) * r.w, ctx.hostRun);
+      if(st != NVPYR_SUCCESS)
+        return st;
+    }
+    FastParams p{};
+    for(uint32_t k = 0; k <= M; ++k)
+    {
+      p.lv[k]     = r.lv[k];
+      p.lv[k].ptr = r.lv[k].ptr + size_t(row0 >> k) * r.lv[k].pitch;
+      p.lv[k].h   = rows >> k;  // rows and row0 are multiples of 2^M (H is, too)
+    }
+    nvpyrStatus st = launchFast<F>(ctx, p, M, ctx.hostRun);
+    if(st != NVPYR_SUCCESS)
+      return st;
+    NVPYR_CUDA(cudaEventRecord(ctx.hostEvRun[band], ctx.hostRun));
+    NVPYR_CUDA(cudaStreamWaitEvent(ctx.hostDown, ctx.hostEvRun[band], 0));
+    for(uint32_t k = level0Back ? 0u : 1u; k <= bandLevels; ++k)
+    {
+      const size_t off = size_t(p.lv[k].ptr - dev), sz = size_t(p.lv[k].h) * p.lv[k].pitch;
+      NVPYR_CUDA(cudaMemcpyAsync(hout + off, dev + off, sz, cudaMemcpyDeviceToHost, ctx.hostDown));
+    }
+  }
+  // the rest of the plan, then levels 3.. in one piece
+  nvpyrStatus st = runPlan<F>(ctx, r, 1);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  NVPYR_CUDA(cudaEventRecord(ctx.hostEvRun[kMaxHostBands], ctx.hostRun));
+  NVPYR_CUDA(cudaStreamWaitEvent(ctx.hostDown, ctx.hostEvRun[kMaxHostBands], 0));
+  if(r.levels > bandLevels + 1)
+  {
+    const size_t off = size_t(r.lv[bandLevels + 1].ptr - dev);
+    NVPYR_CUDA(cudaMemcpyAsync(hout + off, dev + off, chainBytes - off, cudaMemcpyDeviceToHost, ctx.hostDown));
+  }
+  return NVPYR_SUCCESS;
 }
 
 }  // namespace
@@ -704,9 +833,9 @@ nvpyrStatus nvpyrGenerateHost(const void* hostLevel0, void* hostChain, nvpyrExte
     NVPYR_CUDA(cudaMalloc(&ctx->scratch, bytes));
     ctx->scratchBytes = bytes;
   }
-  const uint64_t level0Bytes = uint64_t(extent.width) * extent.height * (format == NVPYR_FORMAT_SRGBA8 ? 4u : 16u);
-  cudaStream_t   stream      = cudaStreamPerThread;
-  NVPYR_CUDA(cudaMemcpyAsync(ctx->scratch, hostLevel0, level0Bytes, cudaMemcpyHostToDevice, stream));
+  st = hostPipelineInit(*ctx);
+  if(st != NVPYR_SUCCESS)
+    return st;
   nvpyrDispatchDesc d;
   memset(&d, 0, sizeof d);
   d.structSize = sizeof d;
@@ -715,12 +844,21 @@ nvpyrStatus nvpyrGenerateHost(const void* hostLevel0, void* hostChain, nvpyrExte
   d.extent     = extent;
   d.levelCount = levelCount;
   d.base       = ctx->scratch;
-  d.stream     = reinterpret_cast<nvpyrStream>(stream);
-  st           = nvpyrDispatchEx(&d);
+  d.stream     = reinterpret_cast<nvpyrStream>(ctx->hostRun);
+  ResolvedDesc r;
+  st = resolve(&d, r);
   if(st != NVPYR_SUCCESS)
     return st;
-  NVPYR_CUDA(cudaMemcpyAsync(hostChain, ctx->scratch, bytes, cudaMemcpyDeviceToHost, stream));
-  NVPYR_CUDA(cudaStreamSynchronize(stream));
+  st = r.format == NVPYR_FORMAT_SRGBA8 ? generateHostPipelined<Srgba8>(*ctx, r, hostLevel0, hostChain, bytes)
+                                       : generateHostPipelined<Rgba32f>(*ctx, r, hostLevel0, hostChain, bytes);
+  // Never leave work in flight on the shared scratch chain, success or not.
+  const cudaError_t e0 = cudaStreamSynchronize(ctx->hostUp), e1 = cudaStreamSynchronize(ctx->hostRun),
+                    e2 = cudaStreamSynchronize(ctx->hostDown);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  NVPYR_CUDA(e0);
+  NVPYR_CUDA(e1);
+  NVPYR_CUDA(e2);
   return NVPYR_SUCCESS;
 }
 
@@ -810,6 +948,14 @@ nvpyrStatus nvpyrShutdown(void)
     cudaFree(c->tickets);
     if(c->scratch)
       cudaFree(c->scratch);
+    if(c->hostUp != nullptr)
+    {
+      cudaStreamDestroy(c->hostUp), cudaStreamDestroy(c->hostRun), cudaStreamDestroy(c->hostDown);
+      for(cudaEvent_t e : c->hostEvUp)
+        cudaEventDestroy(e);
+      for(cudaEvent_t e : c->hostEvRun)
+        cudaEventDestroy(e);
+    }
     delete c;
   }
   g_ctx.clear();
