@@ -39,7 +39,16 @@ struct GenStripParams
   const DeviceTables* tables;
 };
 
-constexpr int kGenWarps = 12;  // 12 warps x 2 CTAs per SM: measured best (8: latency-bound, 16: spills)
+#ifndef NVPYR_GEN_WARPS
+#define NVPYR_GEN_WARPS 12
+#endif
+#ifndef NVPYR_GEN_DEPTH
+#define NVPYR_GEN_DEPTH 1
+#endif
+constexpr int kGenWarps = NVPYR_GEN_WARPS;  // 12 warps x 2 CTAs per SM: measured best (8: latency-bound, 16: spills)
+// Output rows whose source words are in flight ahead of the row being computed.  A lane fetches only
+// 16 bytes per output row, so the bytes in flight per SM (Little's law: ~35 KB at HBM speed) come from depth.
+constexpr int kGenDepth = NVPYR_GEN_DEPTH;
 
 __device__ __forceinline__ void genSrgba8Init(GenSrgba8Smem& sm, const DeviceTables* t)
 {
@@ -184,7 +193,6 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
     }
 
     const unsigned char* src = L0.ptr + size_t(2u * ya) * L0.pitch + size_t(c0) * 4u;  // source row 2*ya
-    unsigned char*       d1  = L1.ptr + size_t(ya) * L1.pitch + size_t(x1) * 4u;
     auto                 load2 = [&](const unsigned char* row, uint32_t& a, uint32_t& b) {
       a = srcA ? __ldg(reinterpret_cast<const uint32_t*>(row)) : 0u;
       b = srcB ? __ldg(reinterpret_cast<const uint32_t*>(row + 4)) : 0u;
@@ -198,24 +206,42 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
       carryA = decodeTexel(dec, laneOff, a);
       carryB = decodeTexel(dec, laneOff, b);
     }
-    // raw words of the next output row's new source rows (prefetched)
-    uint32_t n0a, n0b, n1a, n1b;
+    // raw words of the new source rows of the next kGenDepth output rows (prefetched ring; the row loop
+    // is unrolled kGenDepth times so that ring slots are compile-time registers)
+    struct Raw
     {
-      const unsigned char* r = kY3 ? src + L0.pitch : src;
-      load2(r, n0a, n0b);
-      load2(r + L0.pitch, n1a, n1b);
+      uint32_t a0, b0, a1, b1;
+    };
+    Raw  ring[kGenDepth];
+    auto loadRow = [&](uint32_t y, Raw& r) {  // source rows of output row y (beyond yb: untouched)
+      if(y <= yb)
+      {
+        const unsigned char* q = src + size_t(2u * (y - ya) + (kY3 ? 1u : 0u)) * L0.pitch;
+        load2(q, r.a0, r.b0);
+        load2(q + L0.pitch, r.a1, r.b1);
+      }
+    };
+#pragma unroll
+    for(int d = 0; d < kGenDepth; ++d)
+    {
+      ring[d] = Raw{0u, 0u, 0u, 0u};
+      loadRow(ya + d, ring[d]);
     }
     V4 q0 = zero, q1 = zero;  // last level +1 values of this column
 
-    for(uint32_t y = ya; y <= yb; ++y, src += 2u * L0.pitch, d1 += L1.pitch)
+    unsigned char* d1row = L1.ptr + size_t(ya) * L1.pitch + size_t(x1) * 4u;
+    for(uint32_t yBase = ya; yBase <= yb; yBase += kGenDepth)
     {
-      const uint32_t m0a = n0a, m0b = n0b, m1a = n1a, m1b = n1b;
-      if(y < yb)
-      {
-        const unsigned char* r = (kY3 ? src + L0.pitch : src) + 2u * L0.pitch;
-        load2(r, n0a, n0b);
-        load2(r + L0.pitch, n1a, n1b);
-      }
+#pragma unroll
+     for(int slot = 0; slot < kGenDepth; ++slot)
+     {
+      const uint32_t y = yBase + slot;
+      if(y > yb)
+        break;
+      unsigned char* d1 = d1row;
+      d1row += L1.pitch;
+      const uint32_t m0a = ring[slot].a0, m0b = ring[slot].b0, m1a = ring[slot].a1, m1b = ring[slot].b1;
+      loadRow(y + kGenDepth, ring[slot]);
       // ---- vertical reduction of this lane's two source columns ----
       const V4 vA0 = decodeTexel(dec, laneOff, m0a), vB0 = decodeTexel(dec, laneOff, m0b);
       const V4 vA1 = decodeTexel(dec, laneOff, m1a), vB1 = decodeTexel(dec, laneOff, m1b);
@@ -296,6 +322,7 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
                 genEncWord(enc, toFloat4(o2));
         }
       }
+     }
     }
   }
 }
