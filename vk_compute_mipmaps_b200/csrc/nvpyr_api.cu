@@ -8,6 +8,7 @@
 #include <atomic>
 #include <map>
 #include <type_traits>
+#include <utility>
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -34,7 +35,31 @@ const bool g_noTailFusion = [] {
   const char* e = getenv("NVPYR_NO_TAIL_FUSION");
   return e != nullptr && e[0] == '1';
 }();
+// NVPYR_NO_PDL=1: plain stream-ordered launches (no programmatic dependent launch), for A/B timing.
+const bool g_noPdl = [] {
+  const char* e = getenv("NVPYR_NO_PDL");
+  return e != nullptr && e[0] == '1';
+}();
 std::atomic<uint64_t> g_launchCount{0};
+
+// Every kernel goes out with the programmatic-stream-serialization attribute: its CTAs may be scheduled
+// (and set up their shared-memory tables) while the previous kernel of the stream is still finishing;
+// the kernels call griddepcontrol.wait before touching any level (nvpyr_functors.cuh).
+template <class... KArgs, class... Args>
+cudaError_t launchKernel(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args)
+{
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim          = dim3(unsigned(grid));
+  cfg.blockDim         = dim3(unsigned(block));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream           = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs                                          = attr;
+  cfg.numAttrs                                       = g_noPdl ? 0u : 1u;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 #define NVPYR_CUDA(call)                                                                                          \
   do                                                                                                              \
@@ -205,8 +230,7 @@ nvpyrStatus launchFastT(const DeviceContext& ctx, const FastParams& p, cudaStrea
   nvpyrStatus  st   = persistentGrid(fastKernel<F, M, kVec>, smem, ctx, uint64_t(p.tilesX) * p.tilesY, &grid);
   if(st != NVPYR_SUCCESS)
     return st;
-  fastKernel<F, M, kVec><<<grid, 256, smem, stream>>>(p);
-  NVPYR_CUDA(cudaGetLastError());
+  NVPYR_CUDA(launchKernel(fastKernel<F, M, kVec>, grid, 256, smem, stream, p));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
@@ -233,8 +257,7 @@ nvpyrStatus launchFastSrgba8T(const DeviceContext& ctx, FastParams p, cudaStream
   nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M>, smem, ctx, uint64_t(p.tilesX) * p.tilesY, &grid, kFastWarps * 32);
   if(st != NVPYR_SUCCESS)
     return st;
-  fastSrgba8Kernel<M><<<grid, kFastWarps * 32, smem, stream>>>(p);
-  NVPYR_CUDA(cudaGetLastError());
+  NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M>, grid, kFastWarps * 32, smem, stream, p));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
@@ -251,8 +274,7 @@ nvpyrStatus launchFast(const DeviceContext& ctx, FastParams p, uint32_t M, cudaS
     nvpyrStatus    st    = persistentGrid(fastKernel1<F>, smem, ctx, items, &grid);
     if(st != NVPYR_SUCCESS)
       return st;
-    fastKernel1<F><<<grid, 256, smem, stream>>>(p);
-    NVPYR_CUDA(cudaGetLastError());
+    NVPYR_CUDA(launchKernel(fastKernel1<F>, grid, 256, smem, stream, p));
     ++g_launchCount;
     return NVPYR_SUCCESS;
   }
@@ -306,8 +328,8 @@ nvpyrStatus launchGeneralSrgba8T(const DeviceContext& ctx, const GeneralParams& 
   p.segsY                = (rows + p.segRows - 1) / p.segRows;
   const uint64_t tasks   = uint64_t(p.stripsX) * p.segsY;
   const uint64_t ctas    = std::min<uint64_t>(uint64_t(perSm) * ctx.smCount, (tasks + kGenWarps - 1) / kGenWarps);
-  generalSrgba8Kernel<kLevels, kX3, kY3><<<int(std::max<uint64_t>(1, ctas)), kGenWarps * 32, smem, stream>>>(p);
-  NVPYR_CUDA(cudaGetLastError());
+  NVPYR_CUDA(launchKernel(generalSrgba8Kernel<kLevels, kX3, kY3>, int(std::max<uint64_t>(1, ctas)), kGenWarps * 32, smem,
+                          stream, p));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
@@ -337,8 +359,7 @@ nvpyrStatus launchGeneral(const DeviceContext& ctx, GeneralParams p, cudaStream_
   nvpyrStatus  st   = persistentGrid(generalKernel<F>, smem, ctx, uint64_t(p.tilesX) * p.tilesY, &grid);
   if(st != NVPYR_SUCCESS)
     return st;
-  generalKernel<F><<<grid, 256, smem, stream>>>(p);
-  NVPYR_CUDA(cudaGetLastError());
+  NVPYR_CUDA(launchKernel(generalKernel<F>, grid, 256, smem, stream, p));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
@@ -351,9 +372,8 @@ nvpyrStatus launchPremultiply(const DeviceContext& ctx, const void* in, void* ou
   nvpyrStatus  st   = persistentGrid(premultiplyKernel, smem, ctx, (texels + 255u) / 256u, &grid);
   if(st != NVPYR_SUCCESS)
     return st;
-  premultiplyKernel<<<grid, 256, smem, stream>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out),
-                                                 texels, ctx.tables);
-  NVPYR_CUDA(cudaGetLastError());
+  NVPYR_CUDA(launchKernel(premultiplyKernel, grid, 256, smem, stream, static_cast<const uint32_t*>(in),
+                          static_cast<uint32_t*>(out), texels, static_cast<const DeviceTables*>(ctx.tables)));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
@@ -483,8 +503,7 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
   nvpyrStatus  st   = persistentGrid(tailKernel<TF>, smem, ctx, work, &grid);
   if(st != NVPYR_SUCCESS)
     return st;
-  tailKernel<TF><<<grid, 256, smem, r.stream>>>(tp);
-  NVPYR_CUDA(cudaGetLastError());
+  NVPYR_CUDA(launchKernel(tailKernel<TF>, grid, 256, smem, r.stream, tp));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }

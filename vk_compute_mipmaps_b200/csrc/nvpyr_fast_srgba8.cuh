@@ -270,6 +270,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
   Srgba8FastSmem& sm = *reinterpret_cast<Srgba8FastSmem*>(smemRaw);
   srgba8FastInit(sm, p.tables);
   __syncthreads();  // the only CTA-wide barrier
+  gridDependencyWait();    // the previous kernel's levels are complete and visible
+  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
   const unsigned char* dec = reinterpret_cast<const unsigned char*>(sm.decode);
   const unsigned char* enc = reinterpret_cast<const unsigned char*>(sm.encode);
 

@@ -57,6 +57,21 @@ struct alignas(16) DeviceTables
   uint32_t encode[kEncEntriesPadded];  // bucket table described above
 };
 
+// Programmatic dependent launch (sm_90+): every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, sets up its shared-memory tables (which depend on
+// nothing a previous kernel wrote) and only then waits for the previous kernel of the stream to complete
+// and flush.  Launch latency and table set-up of kernel n+1 thereby overlap the tail of kernel n -- the
+// reference pays a full pipeline barrier + dispatch at that point (dispatch.hpp:180-186).
+// No global memory written by an earlier kernel may be touched before gridDependencyWait().
+__device__ __forceinline__ void gridDependencyWait()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void gridLaunchDependents()
+{
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // Copies n4 uint4s global -> shared with every load of a thread in flight before its first
 // store: the per-CTA table set-up is pure latency, and it is paid by every launch.
 template <int kThreads>

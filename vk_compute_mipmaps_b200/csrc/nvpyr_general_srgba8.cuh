@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
   GenSrgba8Smem& sm = *reinterpret_cast<GenSrgba8Smem*>(smemRaw);
   genSrgba8Init(sm, p.tables);
   __syncthreads();
+  gridDependencyWait();    // the previous kernel's levels are complete and visible
+  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
   const unsigned char* dec = reinterpret_cast<const unsigned char*>(sm.decode);
   const unsigned char* enc = reinterpret_cast<const unsigned char*>(sm.encode);
 

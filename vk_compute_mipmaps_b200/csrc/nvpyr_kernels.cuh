@@ -199,6 +199,8 @@ __global__ void __launch_bounds__(256) fastKernel(const FastParams p)
   FastSmem<F>& sm = *reinterpret_cast<FastSmem<F>*>(smemRaw);
   F::sharedInit(sm.tables, p.tables);
   __syncthreads();
+  gridDependencyWait();    // the previous kernel's levels are complete and visible
+  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
   fastTileLoop<F, M, kVec>(p, sm.tables, sm.l3, blockIdx.x, gridDim.x);
 }
 
@@ -229,6 +231,8 @@ __global__ void __launch_bounds__(256) fastKernel1(const FastParams p)
   FastSmem<F>& sm = *reinterpret_cast<FastSmem<F>*>(smemRaw);
   F::sharedInit(sm.tables, p.tables);
   __syncthreads();
+  gridDependencyWait();    // the previous kernel's levels are complete and visible
+  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
   fastLoop1<F>(p, sm.tables, uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, uint64_t(gridDim.x) * blockDim.x);
 }
 
@@ -389,6 +393,8 @@ __global__ void __launch_bounds__(256) generalKernel(const GeneralParams p)
   GeneralSmem<F>& sm = *reinterpret_cast<GeneralSmem<F>*>(smemRaw);
   F::sharedInit(sm.tables, p.tables);
   __syncthreads();
+  gridDependencyWait();    // the previous kernel's levels are complete and visible
+  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
   generalTileLoop<F, kGenTile2>(p, sm.tables, sm.tile, blockIdx.x, gridDim.x);
 }
 
@@ -485,6 +491,8 @@ __global__ void __launch_bounds__(256) tailKernel(const __grid_constant__ TailPa
   TailSmem<F>& sm = *reinterpret_cast<TailSmem<F>*>(smemRaw);
   F::sharedInit(sm.tables, tp.tables);
   __syncthreads();
+  gridDependencyWait();    // the previous kernel's levels are complete and visible
+  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
 
   tailRunStep<F>(tp.steps[0], sm, tp.tables, blockIdx.x, gridDim.x);
   if(tp.numSteps == 1u)
@@ -522,6 +530,8 @@ __global__ void __launch_bounds__(256) premultiplyKernel(const uint32_t* in, uin
   Srgba8::Shared& sm = *reinterpret_cast<Srgba8::Shared*>(smemRaw);
   Srgba8::sharedInit(sm, tables);
   __syncthreads();
+  gridDependencyWait();    // the previous kernel's levels are complete and visible
+  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
   for(uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < texels; i += uint64_t(gridDim.x) * blockDim.x)
   {
     const uint32_t w = in[i];
