@@ -47,7 +47,8 @@ typedef enum nvpyrStatus
   NVPYR_ERROR_INVALID_VALUE = 1, /* null pointer, zero extent, levelCount > max, misaligned base */
   NVPYR_ERROR_UNSUPPORTED   = 2, /* unknown format / flag, device is not sm_100 */
   NVPYR_ERROR_CUDA          = 3, /* a CUDA call failed; see nvpyrGetLastCudaError */
-  NVPYR_ERROR_OUT_OF_MEMORY = 4
+  NVPYR_ERROR_OUT_OF_MEMORY = 4,
+  NVPYR_ERROR_IO            = 5 /* a file could not be opened, read or written, or is truncated */
 } nvpyrStatus;
 
 typedef struct nvpyrExtent2D
@@ -168,6 +169,24 @@ typedef struct nvpyrExternalMemory_t* nvpyrExternalMemory;
 NVPYR_API nvpyrStatus nvpyrImportExternalMemoryFd(int fd, uint64_t allocationSize, uint64_t offset, uint64_t size,
                                                   nvpyrExternalMemory* outHandle, void** outDevicePtr);
 NVPYR_API nvpyrStatus nvpyrReleaseExternalMemory(nvpyrExternalMemory handle);
+
+/* ------------------------------------------------------------- image files */
+
+/* Replaces stbi_write_tga(filename, w, h, 4, data) as the reference calls it (mipmap_storage.hpp:462):
+ * 32-bit run-length-encoded TGA, rows bottom-up, texels B,G,R,A.  Host memory, synchronous. */
+NVPYR_API nvpyrStatus nvpyrWriteTga(const char* filename, const void* rgba8, nvpyrExtent2D extent);
+/* Name of the file that holds `level`: "image.name.tga" -> "image.name.<level>.tga", level 0 keeps the
+ * base name (mipmap_storage.hpp:447-460). */
+NVPYR_API nvpyrStatus nvpyrGetLevelFilename(const char* baseFilename, uint32_t level, char* out, size_t outSize);
+/* Replaces writeMipmapsTga(mips, pBaseFilename) (mipmap_storage.hpp:441-479): one TGA per level of a packed
+ * sRGBA8 host chain (levelCount 0 = all). */
+NVPYR_API nvpyrStatus nvpyrWriteChainTga(const void* hostChain, nvpyrExtent2D extent, uint32_t levelCount,
+                                         const char* baseFilename);
+/* Stands where the reference calls stbi_load(filename, &w, &h, &n, 4) (scoped_image.hpp:217-218): returns
+ * top-down R,G,B,A texels (A = 255 if the file has no alpha) in a buffer to be released with nvpyrFree.
+ * Formats: TGA (true colour or grey, raw or RLE, 8/24/32 bits) and binary PGM/PPM; no JPEG/PNG decoder. */
+NVPYR_API nvpyrStatus nvpyrReadImage(const char* filename, void** rgba8, nvpyrExtent2D* extent);
+NVPYR_API void        nvpyrFree(void* p);
 
 /* -------------------------------------------------------------------- misc */
 

@@ -18,9 +18,10 @@ def test_header_declares_expected_entry_points():
     syms = declared_symbols()
     for s in ["nvpyrDispatch", "nvpyrDispatchEx", "nvpyrDispatchBatch", "nvpyrGetPlan", "nvpyrGetLevelCount",
               "nvpyrGetLevelOffsetTexels", "nvpyrGetChainBytes", "nvpyrGenerateHost", "nvpyrPremultiplyAlpha",
-              "nvpyrImportExternalMemoryFd", "nvpyrGetErrorString", "nvpyrShutdown"]:
+              "nvpyrImportExternalMemoryFd", "nvpyrGetErrorString", "nvpyrShutdown", "nvpyrWriteTga",
+              "nvpyrWriteChainTga", "nvpyrGetLevelFilename", "nvpyrReadImage", "nvpyrFree"]:
         assert s in syms
-    assert len(syms) >= 17
+    assert len(syms) >= 22
 
 
 def test_library_exports_every_declared_symbol(nv):

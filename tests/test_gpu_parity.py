@@ -347,6 +347,31 @@ print("banded ok", nv.launch_count())
     assert int(out.stdout.split()[-1]) > 60, out.stdout
 
 
+def test_minimal_app_equivalent(nv, cuda, oracle, tmp_path):
+    """examples/minimal_mipmaps = the reference's minimal_app with the Vulkan sequence swapped for libnvpyr:
+    same command line, same per-level TGA files.  Checked against the oracle chain of the same input,
+    with -do-premultiply-alpha and with -force-no-fast-pipeline."""
+    import subprocess
+    exe = os.path.join(_oracle.ROOT, "examples", "minimal_mipmaps")
+    assert os.path.exists(exe), "examples/minimal_mipmaps has not been built (__graft_entry__.build())"
+    w, h = 260, 136
+    l0 = _oracle.smooth_level0(w, h, 9)
+    src = str(tmp_path / "in.tga")
+    nv.write_tga(src, l0, w, h)
+    for args, pm, fg in (([], False, False), (["-do-premultiply-alpha"], True, False),
+                         (["-premultiplied-alpha", "-force-no-fast-pipeline"], False, True)):
+        base = str(tmp_path / ("out_%d%d.tga" % (pm, fg)))
+        r = subprocess.run([exe, "-i", src, "-o", base] + args, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        want, _ = oracle.shader_chain(oracle.premultiply(l0) if pm else l0, w, h, force_general=fg)
+        for level, v in enumerate(nv.level_views(want, w, h)):
+            got, gw, gh = nv.read_image(nv.level_filename(base, level))
+            assert (gh, gw) == v.shape[:2] and (got == v).all(), (args, level)
+        assert ("Wrote " + nv.level_filename(base, 8)) in r.stderr
+    r = subprocess.run([exe, "-bogus"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Unknown argument" in r.stderr
+
+
 def test_other_stream(nv, cuda, oracle):
     w, h = 320, 192
     l0 = _oracle.random_level0(w, h, 13)

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("NVPYR_LIB_PATH") or os.path.join(_HERE, "libnvpyr.so"
 NVPYR_MAX_LEVELS = 32
 NVPYR_MAX_STEPS = 40
 
-SUCCESS, ERROR_INVALID_VALUE, ERROR_UNSUPPORTED, ERROR_CUDA, ERROR_OUT_OF_MEMORY = range(5)
+SUCCESS, ERROR_INVALID_VALUE, ERROR_UNSUPPORTED, ERROR_CUDA, ERROR_OUT_OF_MEMORY, ERROR_IO = range(6)
 FORMAT_SRGBA8, FORMAT_RGBA32F = 0, 1
 FLAG_NONE, FLAG_FORCE_GENERAL, FLAG_PREMULTIPLY_ALPHA = 0, 1, 2
 
@@ -69,6 +69,11 @@ def _load():
         "nvpyrGenerateHost": (st, [vp, vp, Extent2D, u32, C.c_int, u32]),
         "nvpyrImportExternalMemoryFd": (st, [C.c_int, u64, u64, u64, C.POINTER(vp), C.POINTER(vp)]),
         "nvpyrReleaseExternalMemory": (st, [vp]),
+        "nvpyrWriteTga": (st, [C.c_char_p, vp, Extent2D]),
+        "nvpyrGetLevelFilename": (st, [C.c_char_p, u32, C.c_char_p, C.c_size_t]),
+        "nvpyrWriteChainTga": (st, [vp, Extent2D, u32, C.c_char_p]),
+        "nvpyrReadImage": (st, [C.c_char_p, C.POINTER(vp), C.POINTER(Extent2D)]),
+        "nvpyrFree": (None, [vp]),
         "nvpyrGetErrorString": (C.c_char_p, [st]),
         "nvpyrGetLastCudaError": (C.c_int, []),
         "nvpyrGetLaunchCount": (u64, []),

@@ -941,6 +941,7 @@ const char* nvpyrGetErrorString(nvpyrStatus status)
     case NVPYR_ERROR_UNSUPPORTED: return "NVPYR_ERROR_UNSUPPORTED";
     case NVPYR_ERROR_CUDA: return "NVPYR_ERROR_CUDA";
     case NVPYR_ERROR_OUT_OF_MEMORY: return "NVPYR_ERROR_OUT_OF_MEMORY";
+    case NVPYR_ERROR_IO: return "NVPYR_ERROR_IO";
   }
   return "NVPYR_ERROR_UNKNOWN";
 }

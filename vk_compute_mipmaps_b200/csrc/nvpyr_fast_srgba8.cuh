@@ -54,6 +54,10 @@ namespace nvpyr {
 #ifndef NVPYR_ENC_WAYS
 #define NVPYR_ENC_WAYS 4
 #endif
+#ifndef NVPYR_FAST_SLAB_UNROLL
+#define NVPYR_FAST_SLAB_UNROLL 1
+#endif
+constexpr int      kFastSlabUnroll = NVPYR_FAST_SLAB_UNROLL;
 constexpr uint32_t kEncWays       = NVPYR_ENC_WAYS;
 constexpr int      kFastWarps     = NVPYR_FAST_WARPS;
 constexpr int      kFastCtasPerSm = NVPYR_ENC_WAYS == 1 ? 2 : 1;
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
     unsigned char* d2 = p.lv[2].ptr + size_t(y0 >> 2) * pitch2 + size_t(x0 >> 2) * 4u;
     unsigned char* d3 = M >= 3 ? p.lv[3].ptr + size_t(y0 >> 3) * p.lv[3].pitch + size_t(x0 >> 3) * 4u : nullptr;
     const Cursor   nextTile = tileCursor(tile + tileStep);
-#pragma unroll 1
+#pragma unroll kFastSlabUnroll
     for(uint32_t slab = 0; slab < kSlabs; ++slab, y0 += 8u, d1 += 4u * pitch1, d2 += 2u * pitch2)
     {
       // Edges are multiples of 2^M >= 4: a 4x4 block is entirely inside or outside.

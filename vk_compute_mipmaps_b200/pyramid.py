@@ -10,6 +10,7 @@ command buffer is a CUDA stream, and the image is a packed linear chain in
 device memory (layout of include/mipmap_storage.hpp:53-76).
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -21,6 +22,7 @@ from ._lib import (FLAG_FORCE_GENERAL, FLAG_NONE, FLAG_PREMULTIPLY_ALPHA, FORMAT
 __all__ = [
     "PyramidPipelines", "cmd_pyramid_dispatch", "dispatch_batch", "level_count", "level_extent", "level_offset_texels",
     "chain_bytes", "chain_texels", "get_plan", "generate_host", "premultiply_alpha", "level_views", "launch_count",
+    "write_tga", "level_filename", "write_mipmaps_tga", "read_image",
     "FORMAT_SRGBA8", "FORMAT_RGBA32F", "FLAG_NONE", "FLAG_FORCE_GENERAL", "FLAG_PREMULTIPLY_ALPHA", "NvpyrError",
 ]
 
@@ -163,6 +165,41 @@ def generate_host(level0, width, height, mip_levels=0, fmt=FORMAT_SRGBA8, flags=
     check(lib.nvpyrGenerateHost(level0.ctypes.data, out.ctypes.data, Extent2D(width, height), mip_levels, fmt, flags),
           "nvpyrGenerateHost")
     return out
+
+
+def write_tga(filename, rgba8, width, height):
+    """stbi_write_tga(filename, w, h, 4, data) as the reference calls it (mipmap_storage.hpp:462)."""
+    a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+    if a.size != 4 * width * height:
+        raise ValueError("rgba8 has the wrong number of elements")
+    check(lib.nvpyrWriteTga(os.fsencode(filename), a.ctypes.data, Extent2D(width, height)), "nvpyrWriteTga")
+
+
+def level_filename(base_filename, level):
+    buf = C.create_string_buffer(4096)
+    check(lib.nvpyrGetLevelFilename(os.fsencode(base_filename), level, buf, len(buf)), "nvpyrGetLevelFilename")
+    return os.fsdecode(buf.value)
+
+
+def write_mipmaps_tga(chain, width, height, base_filename, mip_levels=0):
+    """writeMipmapsTga (mipmap_storage.hpp:441-479) for a packed sRGBA8 host chain."""
+    a = np.ascontiguousarray(chain, dtype=np.uint8)
+    if a.size != chain_bytes(width, height, mip_levels):
+        raise ValueError("chain has the wrong size")
+    check(lib.nvpyrWriteChainTga(a.ctypes.data, Extent2D(width, height), mip_levels, os.fsencode(base_filename)),
+          "nvpyrWriteChainTga")
+
+
+def read_image(filename):
+    """Stands where the reference calls stbi_load(..., 4): returns (HxWx4 uint8 array, width, height)."""
+    ptr, ext = C.c_void_p(), Extent2D()
+    check(lib.nvpyrReadImage(os.fsencode(filename), C.byref(ptr), C.byref(ext)), "nvpyrReadImage")
+    try:
+        n = 4 * ext.width * ext.height
+        a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n,)).copy()
+    finally:
+        lib.nvpyrFree(ptr)
+    return a.reshape(ext.height, ext.width, 4), ext.width, ext.height
 
 
 def level_views(chain, width, height, mip_levels=0):
