@@ -20,6 +20,8 @@
 //
 // 1/(2n+1) is one IEEE division per kernel; per-row weights cost a subtract and two multiplies.
 #pragma once
+#include <type_traits>
+
 #include "nvpyr_fast_srgba8.cuh"
 
 namespace nvpyr {
@@ -42,13 +44,7 @@ struct GenStripParams
 #ifndef NVPYR_GEN_WARPS
 #define NVPYR_GEN_WARPS 12
 #endif
-#ifndef NVPYR_GEN_DEPTH
-#define NVPYR_GEN_DEPTH 1
-#endif
 constexpr int kGenWarps = NVPYR_GEN_WARPS;  // 12 warps x 2 CTAs per SM: measured best (8: latency-bound, 16: spills)
-// Output rows whose source words are in flight ahead of the row being computed.  A lane fetches only
-// 16 bytes per output row, so the bytes in flight per SM (Little's law: ~35 KB at HBM speed) come from depth.
-constexpr int kGenDepth = NVPYR_GEN_DEPTH;
 
 __device__ __forceinline__ void genSrgba8Init(GenSrgba8Smem& sm, const DeviceTables* t)
 {
@@ -99,7 +95,9 @@ __device__ __forceinline__ V4 genReduce2(V4 v0, V4 v1)
 // srgbFromLinear with both clamps (weighted sums may exceed 1 by an ulp); code in bits 16..23.
 __device__ __forceinline__ uint32_t genEncChannel(const unsigned char* enc, float x)
 {
-  uint32_t b         = min(max(__float_as_uint(x), kEncMinBits), kEncMaxBits);
+  // Weighted sums stay below 1 + 2^-8, i.e. inside the table's last bucket (key of 1.0f): only the lower
+  // clamp is needed.
+  const uint32_t b   = max(__float_as_uint(x), kEncMinBits);
   const uint32_t off = (b >> (kEncShift - 2)) & 0x3FFFCu;
   return *reinterpret_cast<const uint32_t*>(enc + off - kEncMinKey * 4u) + b;
 }
@@ -208,42 +206,38 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
       carryA = decodeTexel(dec, laneOff, a);
       carryB = decodeTexel(dec, laneOff, b);
     }
-    // raw words of the new source rows of the next kGenDepth output rows (prefetched ring; the row loop
-    // is unrolled kGenDepth times so that ring slots are compile-time registers)
+    // Raw words of the two new source rows of an output row.  Two output rows are in flight ahead of the
+    // one being computed; the row loop is unrolled by two so that both slots, the vertical carry and the
+    // level +2 history (q0, q1) are compile-time registers that never need to be moved.
     struct Raw
     {
       uint32_t a0, b0, a1, b1;
     };
-    Raw  ring[kGenDepth];
-    auto loadRow = [&](uint32_t y, Raw& r) {  // source rows of output row y (beyond yb: untouched)
-      if(y <= yb)
+    const unsigned char* nextRows = kY3 ? src + L0.pitch : src;  // new source rows of the next row to prefetch
+    const size_t         rowStep  = 2u * size_t(L0.pitch);
+    auto                 loadRow  = [&](bool valid, Raw& r) {
+      if(valid)
       {
-        const unsigned char* q = src + size_t(2u * (y - ya) + (kY3 ? 1u : 0u)) * L0.pitch;
-        load2(q, r.a0, r.b0);
-        load2(q + L0.pitch, r.a1, r.b1);
+        load2(nextRows, r.a0, r.b0);
+        load2(nextRows + L0.pitch, r.a1, r.b1);
       }
+      nextRows += rowStep;
     };
-#pragma unroll
-    for(int d = 0; d < kGenDepth; ++d)
-    {
-      ring[d] = Raw{0u, 0u, 0u, 0u};
-      loadRow(ya + d, ring[d]);
-    }
+    Raw r0{0u, 0u, 0u, 0u}, r1{0u, 0u, 0u, 0u};
+    loadRow(true, r0);
+    loadRow(ya + 1u <= yb, r1);
     V4 q0 = zero, q1 = zero;  // last level +1 values of this column
 
-    unsigned char* d1row = L1.ptr + size_t(ya) * L1.pitch + size_t(x1) * 4u;
-    for(uint32_t yBase = ya; yBase <= yb; yBase += kGenDepth)
-    {
-#pragma unroll
-     for(int slot = 0; slot < kGenDepth; ++slot)
-     {
-      const uint32_t y = yBase + slot;
-      if(y > yb)
-        break;
-      unsigned char* d1 = d1row;
-      d1row += L1.pitch;
-      const uint32_t m0a = ring[slot].a0, m0b = ring[slot].b0, m1a = ring[slot].a1, m1b = ring[slot].b1;
-      loadRow(y + kGenDepth, ring[slot]);
+    unsigned char* d1 = L1.ptr + size_t(ya) * L1.pitch + size_t(x1) * 4u;
+    unsigned char* d2 = kLevels == 2 ? L2.ptr + size_t(r2a) * L2.pitch + size_t(x2) * 4u : nullptr;
+    uint32_t       y2 = r2a;  // next row of level +2 to emit
+
+    // One output row of level +1 (and what it completes of level +2).  kOdd: parity of the row inside the
+    // segment (segments of two-level steps start on even rows).
+    auto row = [&](uint32_t y, Raw& slot, auto parity) {
+      constexpr bool kOdd = decltype(parity)::value;
+      const uint32_t m0a = slot.a0, m0b = slot.b0, m1a = slot.a1, m1b = slot.b1;
+      loadRow(y + 2u <= yb, slot);
       // ---- vertical reduction of this lane's two source columns ----
       const V4 vA0 = decodeTexel(dec, laneOff, m0a), vB0 = decodeTexel(dec, laneOff, m0b);
       const V4 vA1 = decodeTexel(dec, laneOff, m1a), vB1 = decodeTexel(dec, laneOff, m1b);
@@ -272,22 +266,20 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
         o = genReduce2(hA, hB);
       if(out1)
         *reinterpret_cast<uint32_t*>(d1) = genEncWord(enc, toFloat4(o));
+      d1 += L1.pitch;
 
       // ---- level +2, float32 carry ----
       if(kLevels == 2)
       {
-        const uint32_t j = y - ya;  // row index inside the segment
-        V4             g    = zero;
-        bool           emit = false;
-        uint32_t       y2   = 0;
+        V4   g    = zero;
+        bool emit = false;
         if(y3b)
         {
-          // rows 2 y2, 2 y2 + 1, 2 y2 + 2: emit when the third arrives (even j >= 2)
-          if(!(j & 1u))
+          // rows 2 y2, 2 y2 + 1, 2 y2 + 2: emit when the third arrives (even row, not the segment's first)
+          if(!kOdd)
           {
-            if(j >= 2u)
+            if(y != ya)
             {
-              y2            = r2a + (j >> 1) - 1u;
               const Taps ty = genTaps(rcpY2, fH2, y2);
               g             = genReduce3(ty.w0, q0, ty.w1, q1, ty.w2, o);
               emit          = true;
@@ -299,9 +291,8 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
         }
         else
         {
-          if(j & 1u)
+          if(kOdd)
           {
-            y2   = r2a + (j >> 1);
             g    = genReduce2(q0, o);
             emit = true;
           }
@@ -320,12 +311,20 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
           else
             o2 = genReduce2(g, g1);
           if(out2)
-            *reinterpret_cast<uint32_t*>(L2.ptr + size_t(y2) * L2.pitch + size_t(x2) * 4u) =
-                genEncWord(enc, toFloat4(o2));
+            *reinterpret_cast<uint32_t*>(d2) = genEncWord(enc, toFloat4(o2));
+          d2 += L2.pitch;
+          ++y2;
         }
       }
-     }
+    };
+    uint32_t y = ya;
+    for(; y < yb; y += 2u)
+    {
+      row(y, r0, std::false_type{});
+      row(y + 1u, r1, std::true_type{});
     }
+    if(y == yb)
+      row(y, r0, std::false_type{});
   }
 }
 
