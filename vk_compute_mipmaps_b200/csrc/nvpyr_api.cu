@@ -314,7 +314,7 @@ nvpyrStatus launchGeneralSrgba8T(const DeviceContext& ctx, const GeneralParams& 
   p.lv[0] = gp.lv[0], p.lv[1] = gp.lv[1], p.lv[2] = gp.lv[2];
   p.tables            = ctx.tables;
   p.stripsX           = std::max(1u, (gp.lv[1].w - 1u + 29u) / 30u);
-  const size_t smem   = sizeof(GenSrgba8Smem);
+  const size_t smem   = kGenSmemBytes;
   int          perSm  = 0;
   nvpyrStatus  st     = blocksPerSm(reinterpret_cast<const void*>(generalSrgba8Kernel<kLevels, kX3, kY3>), smem,
                                     kGenWarps * 32, ctx.device, &perSm);

@@ -26,11 +26,22 @@
 
 namespace nvpyr {
 
-struct GenSrgba8Smem
-{
-  float                decode[256 * 64];  // [code][64]: floats 0..31 = linearFromSrgb(code) per lane
-  alignas(16) uint32_t encode[kEncEntriesPadded];
-};
+// Shared-memory layout chosen so that table look-ups need NO address arithmetic beyond the one instruction
+// that extracts the index (the kernel is instruction-issue bound; a base-address add per look-up was 8 % of
+// all instructions).  Addresses below are in the CTA's shared window, whose dynamic part starts at
+// kGenWindowBase (1 KB is reserved by the system on sm_100; checked at run time, the kernel traps otherwise):
+//   * decode table at window address 0x20000, [code][64 floats] (floats 0..31 = one copy per lane):
+//     address = 0x20000 | code << 8 | lane << 2 is produced by ONE PRMT from the packed texel and
+//     (0x20000 | lane << 2);
+//   * encode bucket table placed so that the entry of key k sits at window address 4 k: the masked, shifted
+//     float bits ARE the address.
+constexpr uint32_t kGenWindowBase = 0x400u;
+constexpr uint32_t kGenDecodeAddr = 0x20000u;
+constexpr uint32_t kGenEncodeAddr = kEncMinKey * 4u;  // window address of the first entry (key kEncMinKey)
+constexpr uint32_t kGenSmemBytes  = kGenDecodeAddr + 256u * 256u - kGenWindowBase;
+static_assert(kGenEncodeAddr >= kGenWindowBase && kGenEncodeAddr + kEncEntriesPadded * 4u <= kGenDecodeAddr,
+              "encode table must fit below the decode table");
+static_assert(kGenEncodeAddr % 16u == 0, "encode table is copied as uint4");
 
 struct GenStripParams
 {
@@ -42,22 +53,42 @@ struct GenStripParams
 };
 
 #ifndef NVPYR_GEN_WARPS
-#define NVPYR_GEN_WARPS 12
+#define NVPYR_GEN_WARPS 24
 #endif
-constexpr int kGenWarps = NVPYR_GEN_WARPS;  // 12 warps x 2 CTAs per SM: measured best (8: latency-bound, 16: spills)
+constexpr int kGenWarps = NVPYR_GEN_WARPS;  // one CTA of 24 warps per SM (80 registers per thread)
 
-__device__ __forceinline__ void genSrgba8Init(GenSrgba8Smem& sm, const DeviceTables* t)
+__device__ __forceinline__ void genSrgba8Init(unsigned char* smemRaw, const DeviceTables* t)
 {
+  float*    decode = reinterpret_cast<float*>(smemRaw + (kGenDecodeAddr - kGenWindowBase));
+  uint32_t* encode = reinterpret_cast<uint32_t*>(smemRaw + (kGenEncodeAddr - kGenWindowBase));
   for(uint32_t i = threadIdx.x; i < 512u; i += kGenWarps * 32)
   {
     const uint32_t code = i >> 1, half = i & 1u;
     const float    v    = __ldg(&t->decode[code]);
-    float4*        d    = reinterpret_cast<float4*>(&sm.decode[code * 64u + half * 16u]);
+    float4*        d    = reinterpret_cast<float4*>(&decode[code * 64u + half * 16u]);
     const float4   v4   = make_float4(v, v, v, v);
     d[0] = v4, d[1] = v4, d[2] = v4, d[3] = v4;
   }
-  copyTableWide<kGenWarps * 32>(reinterpret_cast<uint4*>(sm.encode), reinterpret_cast<const uint4*>(t->encode),
+  copyTableWide<kGenWarps * 32>(reinterpret_cast<uint4*>(encode), reinterpret_cast<const uint4*>(t->encode),
                                 kEncEntriesPadded / 4);
+}
+
+// linearFromSrgb of byte kByte (0..2) of a packed texel: PRMT builds the absolute shared address
+// (laneAddr = kGenDecodeAddr | lane << 2), LDS reads it.
+template <int kByte>
+__device__ __forceinline__ float genDec8(uint32_t w, uint32_t laneAddr)
+{
+  const uint32_t addr = __byte_perm(w, laneAddr, 0x7604u | (uint32_t(kByte) << 4));
+  float          v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ V4 genDecodeTexel(uint32_t laneAddr, uint32_t w)
+{
+  V4 r;
+  r.rg = pack2(genDec8<0>(w, laneAddr), genDec8<1>(w, laneAddr));
+  r.ba = pack2(genDec8<2>(w, laneAddr), decAlpha(w));
+  return r;
 }
 
 // Packed float32 pairs (FMUL2 / FADD2, two IEEE roundings per issue slot): see nvpyr_fast_srgba8.cuh.
@@ -93,17 +124,19 @@ __device__ __forceinline__ V4 genReduce2(V4 v0, V4 v1)
 }
 
 // srgbFromLinear with both clamps (weighted sums may exceed 1 by an ulp); code in bits 16..23.
-__device__ __forceinline__ uint32_t genEncChannel(const unsigned char* enc, float x)
+__device__ __forceinline__ uint32_t genEncChannel(float x)
 {
   // Weighted sums stay below 1 + 2^-8, i.e. inside the table's last bucket (key of 1.0f): only the lower
   // clamp is needed.
-  const uint32_t b   = max(__float_as_uint(x), kEncMinBits);
-  const uint32_t off = (b >> (kEncShift - 2)) & 0x3FFFCu;
-  return *reinterpret_cast<const uint32_t*>(enc + off - kEncMinKey * 4u) + b;
+  const uint32_t b    = max(__float_as_uint(x), kEncMinBits);
+  const uint32_t addr = (b >> (kEncShift - 2)) & 0x3FFFCu;  // = 4 * key = the entry's shared address
+  uint32_t       e;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(addr));
+  return e + b;
 }
-__device__ __forceinline__ uint32_t genEncWord(const unsigned char* enc, float4 v)
+__device__ __forceinline__ uint32_t genEncWord(float4 v)
 {
-  const uint32_t r = genEncChannel(enc, v.x), g = genEncChannel(enc, v.y), b = genEncChannel(enc, v.z);
+  const uint32_t r = genEncChannel(v.x), g = genEncChannel(v.y), b = genEncChannel(v.z);
   // uint(a * 255 + 0.5): a <= 1 + 2 ulp, so the truncation never exceeds 255
   const uint32_t a = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(v.w, 255.0f), 0.5f), 8388608.0f));
   return __byte_perm(__byte_perm(r, g, 0x0062), __byte_perm(b, a, 0x0042), 0x5410);
@@ -138,18 +171,17 @@ __device__ __forceinline__ V4 shflDown(V4 v, int d)
 
 // kLevels: 1 or 2.  kX3 / kY3: the first level uses 3 taps (odd source size) along x / y; otherwise 2.
 template <int kLevels, bool kX3, bool kY3>
-__global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const GenStripParams p)
+__global__ void __launch_bounds__(kGenWarps * 32, 1) generalSrgba8Kernel(const GenStripParams p)
 {
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  GenSrgba8Smem& sm = *reinterpret_cast<GenSrgba8Smem*>(smemRaw);
-  genSrgba8Init(sm, p.tables);
+  if(uint32_t(__cvta_generic_to_shared(smemRaw)) != kGenWindowBase)
+    __trap();  // the absolute table addresses above assume this window layout: fail loudly, never silently
+  genSrgba8Init(smemRaw, p.tables);
   __syncthreads();
   gridDependencyWait();    // the previous kernel's levels are complete and visible
   gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
-  const unsigned char* dec = reinterpret_cast<const unsigned char*>(sm.decode);
-  const unsigned char* enc = reinterpret_cast<const unsigned char*>(sm.encode);
 
-  const uint32_t  lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, laneOff = lane * 4u;
+  const uint32_t  lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, laneAddr = kGenDecodeAddr | (lane * 4u);
   const LevelView L0 = p.lv[0], L1 = p.lv[1], L2 = p.lv[2];
   const float     fH1 = float(L1.h), fW1 = float(L1.w);
   const float     rcpY1 = kY3 ? genRcp(L1.h) : 0.f, rcpX1 = kX3 ? genRcp(L1.w) : 0.f;
@@ -203,8 +235,8 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
     {
       uint32_t a, b;
       load2(src, a, b);
-      carryA = decodeTexel(dec, laneOff, a);
-      carryB = decodeTexel(dec, laneOff, b);
+      carryA = genDecodeTexel(laneAddr, a);
+      carryB = genDecodeTexel(laneAddr, b);
     }
     // Raw words of the two new source rows of an output row.  Two output rows are in flight ahead of the
     // one being computed; the row loop is unrolled by two so that both slots, the vertical carry and the
@@ -239,8 +271,8 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
       const uint32_t m0a = slot.a0, m0b = slot.b0, m1a = slot.a1, m1b = slot.b1;
       loadRow(y + 2u <= yb, slot);
       // ---- vertical reduction of this lane's two source columns ----
-      const V4 vA0 = decodeTexel(dec, laneOff, m0a), vB0 = decodeTexel(dec, laneOff, m0b);
-      const V4 vA1 = decodeTexel(dec, laneOff, m1a), vB1 = decodeTexel(dec, laneOff, m1b);
+      const V4 vA0 = genDecodeTexel(laneAddr, m0a), vB0 = genDecodeTexel(laneAddr, m0b);
+      const V4 vA1 = genDecodeTexel(laneAddr, m1a), vB1 = genDecodeTexel(laneAddr, m1b);
       V4       hA, hB;
       if(kY3)
       {
@@ -265,7 +297,7 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
       else
         o = genReduce2(hA, hB);
       if(out1)
-        *reinterpret_cast<uint32_t*>(d1) = genEncWord(enc, toFloat4(o));
+        *reinterpret_cast<uint32_t*>(d1) = genEncWord(toFloat4(o));
       d1 += L1.pitch;
 
       // ---- level +2, float32 carry ----
@@ -311,7 +343,7 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) generalSrgba8Kernel(const G
           else
             o2 = genReduce2(g, g1);
           if(out2)
-            *reinterpret_cast<uint32_t*>(d2) = genEncWord(enc, toFloat4(o2));
+            *reinterpret_cast<uint32_t*>(d2) = genEncWord(toFloat4(o2));
           d2 += L2.pitch;
           ++y2;
         }
