@@ -286,6 +286,55 @@ def test_batch_and_determinism(nv, cuda, oracle):
     assert all(bool((a == b).all()) for a, b in zip(first, imgs))
 
 
+@pytest.mark.parametrize("size,flags", [((1024, 1024), 0), ((2048, 1024), 0), ((1920, 1080), 0), ((1020, 1020), 0),
+                                        ((1024, 768), 2)])
+def test_fused_batch_bit_exact(nv, cuda, oracle, size, flags):
+    """nvpyrDispatchBatch on images of one size whose plan is 'one big fast step, then small steps': TWO
+    launches for the whole batch (all tiles of all images through one persistent grid, then one CTA per
+    image for the rest), same bits as one dispatch per image.  Sizes: fast6 + fast4; fast6 + fast4 + general;
+    fast3 + general x4; fast2 + general ...; premultiplied."""
+    w, h = size
+    count = 5
+    imgs, wants = [], []
+    for k in range(count):
+        l0 = _oracle.random_level0(w, h, 300 + k)
+        wants.append(oracle.shader_chain(oracle.premultiply(l0) if flags & 2 else l0, w, h)[0])
+        buf = cuda.empty(nv.chain_bytes(w, h), dtype=cuda.uint8, device="cuda")
+        buf.view(-1, 4)[:] = cuda.from_numpy(MAGENTA).cuda()
+        buf[:4 * w * h] = cuda.from_numpy(l0).cuda()
+        imgs.append(buf)
+    before = nv.launch_count()
+    nv.dispatch_batch(None, nv.PyramidPipelines(), imgs, w, h, flags=flags)
+    cuda.cuda.synchronize()
+    launches = nv.launch_count() - before
+    for k, (b, want) in enumerate(zip(imgs, wants)):
+        assert_same(b.cpu().numpy(), want, w, h, oracle, f"image {k}")
+    assert launches == 2 + (count if flags & 2 else 0), launches
+
+
+def test_heterogeneous_batch_falls_back(nv, cuda, oracle):
+    """Different streams or sizes cannot share a launch: one dispatch per image, same results."""
+    w, h = 1024, 1024
+    imgs, wants = [], []
+    for k in range(3):
+        l0 = _oracle.random_level0(w, h, 400 + k)
+        wants.append(oracle.shader_chain(l0, w, h)[0])
+        buf = cuda.zeros(nv.chain_bytes(w, h), dtype=cuda.uint8, device="cuda")
+        buf[:4 * w * h] = cuda.from_numpy(l0).cuda()
+        imgs.append(buf)
+    cuda.cuda.synchronize()
+    descs = (nv.pyramid.DispatchDesc * 3)()
+    streams = [cuda.cuda.Stream() for _ in range(3)]
+    for i, img in enumerate(imgs):
+        descs[i] = nv.pyramid._make_desc(img, nv.PyramidPipelines(), w, h, 0, 0, streams[i])
+    before = nv.launch_count()
+    nv.pyramid.check(nv.pyramid.lib.nvpyrDispatchBatch(descs, 3), "nvpyrDispatchBatch")
+    cuda.cuda.synchronize()
+    assert nv.launch_count() - before == 3 * 2
+    for b, want in zip(imgs, wants):
+        assert (b.cpu().numpy() == want).all()
+
+
 def test_generate_host_round_trip(nv, cuda, oracle):
     """minimal_app shape: host level 0 in, packed host chain out."""
     for (w, h) in [(256, 256), (255, 131)]:

@@ -115,6 +115,7 @@ bool buildHostTables(DeviceTables& t)
 constexpr uint32_t kTicketPool = 4096;
 
 constexpr uint32_t kMaxHostBands = 64;
+constexpr uint32_t kBatchRing    = 1u << 17;  // base pointers (1 MB); a batch takes a contiguous slice
 
 struct DeviceContext
 {
@@ -123,6 +124,9 @@ struct DeviceContext
   DeviceTables* tables   = nullptr;
   uint32_t*     tickets  = nullptr;  // kTicketPool zero-initialised counters for tailKernel
   std::atomic<uint32_t> nextTicket{0};
+  // nvpyrDispatchBatch: ring of device words holding the chain base pointers of batched launches
+  const unsigned char** batchBases = nullptr;
+  std::atomic<uint64_t> batchCursor{0};
   void*         scratch  = nullptr;  // nvpyrGenerateHost staging chain
   size_t        scratchBytes = 0;
   std::mutex    scratchMutex;
@@ -173,7 +177,17 @@ nvpyrStatus getContext(DeviceContext** out)
     g_lastCudaError = int(e);
     return NVPYR_ERROR_CUDA;
   }
+  const unsigned char** ring = nullptr;
+  e                          = cudaMalloc(&ring, size_t(kBatchRing) * sizeof(void*));
+  if(e != cudaSuccess)
+  {
+    cudaFree(d);
+    cudaFree(tickets);
+    g_lastCudaError = int(e);
+    return NVPYR_ERROR_CUDA;
+  }
   DeviceContext* c = new DeviceContext;
+  c->batchBases    = ring;
   c->device        = dev;
   c->smCount       = prop.multiProcessorCount;
   c->tables        = d;
@@ -245,19 +259,29 @@ bool fastVectorOk(const LevelView* lv)
          && (reinterpret_cast<uintptr_t>(lv[1].ptr) % a1 == 0) && (lv[1].pitch % a1 == 0);
 }
 
-// The tuned sRGBA8 kernel (nvpyr_fast_srgba8.cuh): warp-autonomous 64x64 tiles, 16 warps per CTA.
+// The tuned sRGBA8 kernel (nvpyr_fast_srgba8.cuh): warp-autonomous 64 x 2^M tiles, 32 warps per CTA.
+// batch != nullptr: one launch for batch->count chains of this size (p.lv[].ptr = offsets inside a chain).
 template <int M>
-nvpyrStatus launchFastSrgba8T(const DeviceContext& ctx, FastParams p, cudaStream_t stream)
+nvpyrStatus launchFastSrgba8T(const DeviceContext& ctx, FastParams p, cudaStream_t stream, const FastBatch* batch = nullptr)
 {
   constexpr uint32_t tileH = M >= 3 ? (1u << M) : 8u;  // one warp per 64 x tileH tile
   p.tilesX                 = (p.lv[0].w + 63u) / 64u;
   p.tilesY                 = (p.lv[0].h + tileH - 1u) / tileH;
-  const size_t smem = sizeof(Srgba8FastSmem);
-  int          grid = 1;
-  nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M>, smem, ctx, uint64_t(p.tilesX) * p.tilesY, &grid, kFastWarps * 32);
+  const size_t smem  = sizeof(Srgba8FastSmem);
+  int          grid  = 1;
+  FastBatch    b     = batch ? *batch : FastBatch{nullptr, 0u, 0u};
+  b.tilesPerImage    = p.tilesX * p.tilesY;
+  const uint64_t work = uint64_t(b.tilesPerImage) * (batch ? b.count : 1u);
+  if(work > 0xFFFFFFFFull)
+    return NVPYR_ERROR_INVALID_VALUE;
+  nvpyrStatus st = batch ? persistentGrid(fastSrgba8Kernel<M, true>, smem, ctx, work, &grid, kFastWarps * 32)
+                         : persistentGrid(fastSrgba8Kernel<M, false>, smem, ctx, work, &grid, kFastWarps * 32);
   if(st != NVPYR_SUCCESS)
     return st;
-  NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M>, grid, kFastWarps * 32, smem, stream, p));
+  if(batch)
+    NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, true>, grid, kFastWarps * 32, smem, stream, p, b));
+  else
+    NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, false>, grid, kFastWarps * 32, smem, stream, p, b));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
@@ -580,6 +604,131 @@ nvpyrStatus dispatchResolved(const ResolvedDesc& r)
   return r.format == NVPYR_FORMAT_SRGBA8 ? runPlan<Srgba8>(*ctx, r) : runPlan<Rgba32f>(*ctx, r);
 }
 
+// ------------------------------------------------------------- fused batches
+// nvpyrDispatchBatch on a HOMOGENEOUS batch (sRGBA8, one size, one stream, packed chains whose plan is
+// "one big fast step, then small steps"): two launches for the whole batch instead of two per image.  The
+// big step streams the tiles of all images through one persistent grid (no per-image launch latency, table
+// set-up or tail imbalance: a batch of 4096^2 images runs at the speed of one 16384^2-class image); the
+// small steps run one CTA per image.  Anything else falls back to one dispatch per image.
+constexpr uint64_t kBatchSoloMaxTexels = 256ull * 256ull;
+
+template <int M>
+nvpyrStatus launchFastBatchM(const DeviceContext& ctx, const FastParams& p, cudaStream_t stream, const FastBatch& b)
+{
+  return launchFastSrgba8T<M>(ctx, p, stream, &b);
+}
+
+nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDesc>& r, bool* handled)
+{
+  *handled = false;
+  const ResolvedDesc& a     = r[0];
+  const uint32_t      count = uint32_t(r.size());
+  if(count < 2 || count > kBatchRing / 4 || a.format != NVPYR_FORMAT_SRGBA8 || a.levels < 2 || g_forceGenericFast
+     || g_noTailFusion || a.fast == nullptr)
+    return NVPYR_SUCCESS;
+  for(const ResolvedDesc& d : r)
+  {
+    if(d.format != a.format || d.flags != a.flags || d.w != a.w || d.h != a.h || d.levels != a.levels || d.fast != a.fast
+       || d.stream != a.stream || reinterpret_cast<uintptr_t>(d.lv[0].ptr) % 16u != 0)
+      return NVPYR_SUCCESS;
+    for(uint32_t k = 0; k < d.levels; ++k)  // packed layout only
+      if(d.lv[k].pitch != d.lv[k].w * 4u
+         || size_t(d.lv[k].ptr - d.lv[0].ptr) != size_t(levelOffsetTexels(d.w, d.h, k)) * 4u)
+        return NVPYR_SUCCESS;
+  }
+  nvpyrPlanStep steps[NVPYR_MAX_STEPS];
+  const int     n = buildPlan(a.w, a.h, a.levels, defaultGeneralDispatcher, a.fast, steps, NVPYR_MAX_STEPS);
+  if(n < 1)
+    return NVPYR_SUCCESS;
+  auto texels = [&](int i) { return uint64_t(steps[i].srcWidth) * steps[i].srcHeight; };
+  if(steps[0].pipeline != 1 || steps[0].levelCount < 2 || texels(0) <= kTailMaxTexels || n - 1 > int(kMaxTailSteps))
+    return NVPYR_SUCCESS;
+  for(int i = 1; i < n; ++i)
+    if(texels(i) > kBatchSoloMaxTexels)
+      return NVPYR_SUCCESS;
+  if(!fastVectorOk<Srgba8>(a.lv))
+    return NVPYR_SUCCESS;
+
+  // chain base pointers -> a slice of the device ring
+  std::vector<const unsigned char*> hostBases(count);
+  for(uint32_t i = 0; i < count; ++i)
+    hostBases[i] = r[i].lv[0].ptr;
+  uint64_t start;
+  for(;;)
+  {
+    start = ctx.batchCursor.fetch_add(count) % kBatchRing;
+    if(start + count <= kBatchRing)
+      break;  // (a slice that would wrap is skipped)
+  }
+  const unsigned char** devBases = ctx.batchBases + start;
+  NVPYR_CUDA(cudaMemcpyAsync(devBases, hostBases.data(), size_t(count) * sizeof(void*), cudaMemcpyHostToDevice, a.stream));
+  *handled = true;  // from here on errors are real errors
+
+  if(a.flags & NVPYR_FLAG_PREMULTIPLY_ALPHA)
+    for(const ResolvedDesc& d : r)
+    {
+      nvpyrStatus st = launchPremultiply(ctx, d.lv[0].ptr, d.lv[0].ptr, uint64_t(d.w) * d.h, d.stream);
+      if(st != NVPYR_SUCCESS)
+        return st;
+    }
+
+  auto offsetView = [&](uint32_t level) {
+    LevelView v = a.lv[level];
+    v.ptr       = reinterpret_cast<unsigned char*>(size_t(a.lv[level].ptr - a.lv[0].ptr));
+    return v;
+  };
+  FastParams p{};
+  for(uint32_t k = 0; k <= steps[0].levelCount; ++k)
+    p.lv[k] = offsetView(k);
+  p.tables = ctx.tables;
+  FastBatch   b{devBases, 0u, count};
+  nvpyrStatus st;
+  switch(steps[0].levelCount)
+  {
+    case 2: st = launchFastBatchM<2>(ctx, p, a.stream, b); break;
+    case 3: st = launchFastBatchM<3>(ctx, p, a.stream, b); break;
+    case 4: st = launchFastBatchM<4>(ctx, p, a.stream, b); break;
+    case 5: st = launchFastBatchM<5>(ctx, p, a.stream, b); break;
+    default: st = launchFastBatchM<6>(ctx, p, a.stream, b); break;
+  }
+  if(st != NVPYR_SUCCESS || n == 1)
+    return st;
+
+  using TF = Srgba8Lite;
+  TailParams tp{};
+  tp.numSteps = uint32_t(n - 1);
+  tp.tables   = ctx.tables;
+  for(int i = 1; i < n; ++i)
+  {
+    const nvpyrPlanStep& s  = steps[i];
+    TailStep&            ts = tp.steps[i - 1];
+    ts.pipeline             = s.pipeline;
+    ts.levels               = s.levelCount;
+    LevelView real[7];
+    for(uint32_t k = 0; k <= s.levelCount; ++k)
+    {
+      real[k]  = a.lv[s.inputLevel + k];
+      ts.lv[k] = offsetView(s.inputLevel + k);
+    }
+    if(s.pipeline == 1)
+    {
+      ts.vec    = fastVectorOk<Srgba8>(real) ? 1u : 0u;  // every base is 16-byte aligned: same answer for all images
+      ts.tilesX = (ts.lv[0].w + 63u) / 64u;
+      ts.tilesY = (ts.lv[0].h + 63u) / 64u;
+    }
+    else
+      generalTiles(ts.lv, s.levelCount, kGenTile2Small, &ts.tilesX, &ts.tilesY);
+  }
+  const size_t smem = sizeof(TailSmem<TF>);
+  int          grid = 1;
+  st                = persistentGrid(tailBatchKernel<TF>, smem, ctx, count, &grid);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  NVPYR_CUDA(launchKernel(tailBatchKernel<TF>, grid, 256, smem, a.stream, tp, static_cast<const unsigned char* const*>(devBases), count));
+  ++g_launchCount;
+  return NVPYR_SUCCESS;
+}
+
 // ------------------------------------------------- host round trip, pipelined
 nvpyrStatus hostPipelineInit(DeviceContext& ctx)
 {
@@ -805,9 +954,19 @@ nvpyrStatus nvpyrDispatchBatch(const nvpyrDispatchDesc* descs, uint32_t count)
     if(st != NVPYR_SUCCESS)
       return st;
   }
+  if(count == 0)
+    return NVPYR_SUCCESS;
+  DeviceContext* ctx = nullptr;
+  nvpyrStatus    st  = getContext(&ctx);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  bool fused = false;
+  st         = dispatchBatchFused(*ctx, r, &fused);
+  if(fused || st != NVPYR_SUCCESS)
+    return st;
   for(uint32_t i = 0; i < count; ++i)
   {
-    nvpyrStatus st = dispatchResolved(r[i]);
+    st = dispatchResolved(r[i]);
     if(st != NVPYR_SUCCESS)
       return st;
   }
@@ -966,6 +1125,7 @@ nvpyrStatus nvpyrShutdown(void)
     cudaSetDevice(c->device);
     cudaFree(c->tables);
     cudaFree(c->tickets);
+    cudaFree(c->batchBases);
     if(c->scratch)
       cudaFree(c->scratch);
     if(c->hostUp != nullptr)

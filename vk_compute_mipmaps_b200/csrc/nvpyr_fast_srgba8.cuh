@@ -266,8 +266,17 @@ __device__ __forceinline__ V4 shflXor(V4 a, int mask)
   return r;
 }
 
-template <int M>
-__global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Kernel(const FastParams p)
+// Batch mode (nvpyrDispatchBatch on images of one size): ONE launch streams the same step of `count`
+// independent packed chains.  p.lv[k].ptr then holds the byte offset of level k inside a chain, bases[i]
+// the chain of image i; tile t belongs to image t / tilesPerImage.
+struct FastBatch
+{
+  const unsigned char* const* bases;
+  uint32_t                    tilesPerImage, count;
+};
+
+template <int M, bool kBatch>
+__global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Kernel(const FastParams p, const FastBatch batch)
 {
   static_assert(M >= 2 && M <= 6, "2..6 levels");
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -283,7 +292,13 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
   const uint32_t tx = lane & 15u, ty = lane >> 4;  // lane = 4x4 texels at (4 tx, 4 ty) of a 64x8 slab
   const uint32_t laneOff = lane * 4u;
   const uint32_t W = p.lv[0].w, H = p.lv[0].h;
-  const uint32_t numTiles = p.tilesX * p.tilesY;
+  const uint32_t numTiles = p.tilesX * p.tilesY * (kBatch ? batch.count : 1u);
+  // base address of level k of the image that tile t belongs to
+  auto levelPtr = [&](int k, uint32_t t) -> unsigned char* {
+    if(!kBatch)
+      return p.lv[k].ptr;
+    return reinterpret_cast<unsigned char*>(__ldg(reinterpret_cast<const unsigned long long*>(batch.bases) + t / batch.tilesPerImage)) + reinterpret_cast<size_t>(p.lv[k].ptr);
+  };
   const size_t   pitch0 = p.lv[0].pitch, pitch1 = p.lv[1].pitch, pitch2 = p.lv[2].pitch;
   float*         myL3 = &sm.l3[warp][0][0][0];
 
@@ -308,10 +323,11 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
   };
   constexpr uint32_t kTileH = M >= 3 ? (1u << M) : 8u, kSlabs = kTileH / 8u;
   auto tileCursor = [&](uint32_t t) {
-    const uint32_t x0 = (t % p.tilesX) * 64u + tx * 4u, y0 = (t / p.tilesX) * kTileH + ty * 4u;
+    const uint32_t tt = kBatch ? t % batch.tilesPerImage : t;  // tile inside its image
+    const uint32_t x0 = (tt % p.tilesX) * 64u + tx * 4u, y0 = (tt / p.tilesX) * kTileH + ty * 4u;
     Cursor         c;
-    c.src    = p.lv[0].ptr + size_t(y0) * pitch0 + size_t(x0) * 4u;
     c.active = t < numTiles && x0 < W && y0 < H;
+    c.src    = (kBatch && t >= numTiles ? nullptr : levelPtr(0, t)) + size_t(y0) * pitch0 + size_t(x0) * 4u;
     return c;
   };
   uint4 row[4];
@@ -329,13 +345,14 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
 
   for(; tile < numTiles; tile += tileStep)
   {
-    const uint32_t tileX = tile % p.tilesX, tileY = tile / p.tilesX;
+    const uint32_t tileInImage = kBatch ? tile % batch.tilesPerImage : tile;
+    const uint32_t tileX = tileInImage % p.tilesX, tileY = tileInImage / p.tilesX;
     const uint32_t x0 = tileX * 64u + tx * 4u;
     uint32_t       y0 = tileY * kTileH + ty * 4u;
     // Output cursors of this lane (advance by one slab = 8 input rows per iteration).
-    unsigned char* d1 = p.lv[1].ptr + size_t(y0 >> 1) * pitch1 + size_t(x0 >> 1) * 4u;
-    unsigned char* d2 = p.lv[2].ptr + size_t(y0 >> 2) * pitch2 + size_t(x0 >> 2) * 4u;
-    unsigned char* d3 = M >= 3 ? p.lv[3].ptr + size_t(y0 >> 3) * p.lv[3].pitch + size_t(x0 >> 3) * 4u : nullptr;
+    unsigned char* d1 = levelPtr(1, tile) + size_t(y0 >> 1) * pitch1 + size_t(x0 >> 1) * 4u;
+    unsigned char* d2 = levelPtr(2, tile) + size_t(y0 >> 2) * pitch2 + size_t(x0 >> 2) * 4u;
+    unsigned char* d3 = M >= 3 ? levelPtr(3, tile) + size_t(y0 >> 3) * p.lv[3].pitch + size_t(x0 >> 3) * 4u : nullptr;
     const Cursor   nextTile = tileCursor(tile + tileStep);
 #pragma unroll kFastSlabUnroll
     for(uint32_t slab = 0; slab < kSlabs; ++slab, y0 += 8u, d1 += 4u * pitch1, d2 += 2u * pitch2)
@@ -431,7 +448,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
         const V4      ul = toV4(l3[(2 * j) * 8 + 2 * i]), ur = toV4(l3[(2 * j) * 8 + 2 * i + 1]);
         const V4      ll = toV4(l3[(2 * j + 1) * 8 + 2 * i]), lr = toV4(l3[(2 * j + 1) * 8 + 2 * i + 1]);
         s4               = sum4Paired(fastPairingIsHorizontal(4, M), ul, ur, ll, lr);
-        *reinterpret_cast<uint32_t*>(p.lv[4].ptr + size_t(oy >> 4) * p.lv[4].pitch + size_t(ox >> 4) * 4u) =
+        *reinterpret_cast<uint32_t*>(levelPtr(4, tile) + size_t(oy >> 4) * p.lv[4].pitch + size_t(ox >> 4) * 4u) =
             encWordScaled<4>(enc, s4);
       }
       if(M >= 5)
@@ -440,14 +457,14 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
         const V4 a  = add4(s4, shflXor(s4, 4));
         const V4 s5 = add4(a, shflXor(a, 1));
         if(valid && !(i & 1u) && !(j & 1u))
-          *reinterpret_cast<uint32_t*>(p.lv[5].ptr + size_t(oy >> 5) * p.lv[5].pitch + size_t(ox >> 5) * 4u) =
+          *reinterpret_cast<uint32_t*>(levelPtr(5, tile) + size_t(oy >> 5) * p.lv[5].pitch + size_t(ox >> 5) * 4u) =
               encWordScaled<5>(enc, s5);
         if(M >= 6)
         {
           const V4 c  = add4(s5, shflXor(s5, 8));
           const V4 s6 = add4(c, shflXor(c, 2));
           if(valid && lane == 0u)
-            *reinterpret_cast<uint32_t*>(p.lv[6].ptr + size_t(oy >> 6) * p.lv[6].pitch + size_t(ox >> 6) * 4u) =
+            *reinterpret_cast<uint32_t*>(levelPtr(6, tile) + size_t(oy >> 6) * p.lv[6].pitch + size_t(ox >> 6) * 4u) =
                 encWordScaled<6>(enc, s6);
         }
       }

@@ -521,6 +521,35 @@ __global__ void __launch_bounds__(256) tailKernel(const __grid_constant__ TailPa
   }
 }
 
+// Batch tail: the remaining (small) steps of `count` independent chains of one size in ONE launch.  CTA c
+// runs every step of images c, c + gridDim.x, ... alone; tp.steps[].lv[].ptr hold byte offsets inside a
+// chain, bases[i] the chain of image i.  (tp.ticket is unused: nothing crosses CTAs.)
+template <class F>
+__global__ void __launch_bounds__(256) tailBatchKernel(const __grid_constant__ TailParams tp,
+                                                        const unsigned char* const* bases, uint32_t count)
+{
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  TailSmem<F>& sm = *reinterpret_cast<TailSmem<F>*>(smemRaw);
+  F::sharedInit(sm.tables, tp.tables);
+  __syncthreads();
+  gridDependencyWait();
+  gridLaunchDependents();
+  for(uint32_t image = blockIdx.x; image < count; image += gridDim.x)
+  {
+    unsigned char* base = reinterpret_cast<unsigned char*>(__ldg(reinterpret_cast<const unsigned long long*>(bases) + image));
+    for(uint32_t s = 0; s < tp.numSteps; ++s)
+    {
+      TailStep st = tp.steps[s];
+#pragma unroll
+      for(int k = 0; k < 7; ++k)
+        st.lv[k].ptr = base + reinterpret_cast<size_t>(st.lv[k].ptr);
+      tailRunStep<F>(st, sm, tp.tables, 0u, 1u);
+      __threadfence_block();
+      __syncthreads();  // the reference's inter-dispatch pipeline barrier
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Premultiply-alpha pre-pass, include/scoped_image.hpp:233-255 (sRGBA8 only).
 __global__ void __launch_bounds__(256) premultiplyKernel(const uint32_t* in, uint32_t* out, uint64_t texels,
