@@ -332,6 +332,38 @@ def run_gpu_arm(args):
             torch.cuda.synchronize()
     t_wall2 = time.time()
 
+    # ---- BASELINE configs[4]: a batch of independent 4096^2 textures per rank (texture k -> rank k mod G, no
+    # collective), nvpyrDispatchBatch = two launches for the whole batch ----
+    batch = None
+    if not args.no_batch:
+        bw = bh = 4096
+        per_rank = 32
+        b_bytes = nv.chain_bytes(bw, bh)
+        imgs = []
+        for k in range(per_rank):
+            t = torch.empty(b_bytes, dtype=torch.uint8, device=dev)
+            t[:4 * bw * bh] = torch.randint(0, 256, (4 * bw * bh,), dtype=torch.uint8, device=dev, generator=gen)
+            imgs.append(t)
+        for _ in range(2):
+            nv.dispatch_batch(stream, pipes, imgs, bw, bh)
+        barrier()
+        b_reps = 5
+        bev0, bev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        bev0.record(stream)
+        for _ in range(b_reps):
+            nv.dispatch_batch(stream, pipes, imgs, bw, bh)
+        bev1.record(stream)
+        barrier()
+        b_ms = torch.tensor([bev0.elapsed_time(bev1) / b_reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(b_ms, op=dist.ReduceOp.MAX)
+        b_ms = float(b_ms.item())
+        batch = {"workload": f"{per_rank} independent 4096x4096 sRGBA8 textures per rank (uniform random bytes), one "
+                             "nvpyrDispatchBatch per pass; 2.9 GB per rank per pass (> L2)",
+                 "textures_per_s": world * per_rank / (b_ms * 1e-3), "us_per_texture_per_gpu": 1e3 * b_ms / per_rank,
+                 "GBps": world * per_rank * b_bytes / (b_ms * 1e-3) / 1e9, "launches_per_batch": 2}
+        del imgs
+
     # ---- end to end through the host-buffer entry point (nvpyrGenerateHost) ----
     # Headline: the reference's staging-buffer model (one host chain whose level 0 is filled, all other
     # levels filled on return -- scoped_image.hpp:436-453, and what cpuGenerateMipmaps_sRGBA does to a
@@ -413,7 +445,7 @@ def run_gpu_arm(args):
                    "input": {"random": "uniform random bytes, all four channels (worst case for the encode table's bank "
                                        "conflicts)", "julia": "Julia set of the reference demo", "gradient":
                              "opaque smooth gradient"}[args.input],
-                   "other_inputs": other_inputs},
+                   "other_inputs": other_inputs, "batch_of_4096": batch},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "fastKernel<Srgba8,6> (level 0 -> levels 1..6)",
                      "algorithmic_bytes_per_launch": k_bytes, "us_per_launch": 1e3 * k_ms, "peak_source": peak_src},
@@ -433,6 +465,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-inputs", action="store_true")
+    ap.add_argument("--no-batch", action="store_true")
     ap.add_argument("--input", default="julia", choices=["random", "julia", "gradient"],
                     help="level-0 content of the headline loop. Default: the Julia-set texture the reference demo "
                          "regenerates and mip-maps every frame at its default size 16384x16384 "
