@@ -234,6 +234,33 @@ def test_premultiply(nv, cuda, oracle):
     assert (s2.cpu().numpy() == op).all()
 
 
+@pytest.mark.parametrize("size", [(1024, 1024), (1920, 1080), (1028, 1028), (768, 2048)])
+def test_premultiply_fused_into_level0_read(nv, cuda, oracle, size):
+    """Large images whose chain starts with a tuned fast step premultiply level 0 inside that launch
+    (scoped_image.hpp:233-255 fused into the read): same level 0 and same chain as premultiplying first.
+    Inputs: random alpha; mostly opaque with transparent and zero-colour patches (unchanged blocks are not
+    rewritten)."""
+    w, h = size
+    rnd = _oracle.random_level0(w, h, 31)
+    patch = _oracle.random_level0(w, h, 32, opaque=True).reshape(h, w, 4).copy()
+    patch[h // 4:h // 2, w // 4:w // 2, 3] = 0          # fully transparent block
+    patch[h // 2:h // 2 + 9, :, 3] = 128                 # a semi-transparent stripe
+    patch[:7, :11, :3] = 0                               # black, opaque
+    patch[-5:, -5:] = [0, 0, 0, 77]                      # black, translucent
+    for l0 in (rnd, patch.reshape(-1)):
+        pm = oracle.premultiply(l0)
+        want, _ = oracle.shader_chain(pm, w, h)
+        before = nv.launch_count()
+        got = gpu_chain(nv, cuda, l0, w, h, flags=nv.FLAG_PREMULTIPLY_ALPHA)
+        launches = nv.launch_count() - before
+        assert (got[:4 * w * h] == pm).all(), "level 0 is not the premultiplied image"
+        assert_same(got, want, w, h, oracle, "fused premultiply")
+        # no separate premultiply launch: as many launches as without the flag
+        before = nv.launch_count()
+        gpu_chain(nv, cuda, pm, w, h)
+        assert nv.launch_count() - before == launches
+
+
 def test_partial_level_count(nv, cuda, oracle):
     w, h = 256, 256
     l0 = _oracle.random_level0(w, h, 6)
@@ -309,7 +336,7 @@ def test_fused_batch_bit_exact(nv, cuda, oracle, size, flags):
     launches = nv.launch_count() - before
     for k, (b, want) in enumerate(zip(imgs, wants)):
         assert_same(b.cpu().numpy(), want, w, h, oracle, f"image {k}")
-    assert launches == 2 + (count if flags & 2 else 0), launches
+    assert launches == 2, launches  # the premultiply pre-pass rides in the first launch
 
 
 def test_heterogeneous_batch_falls_back(nv, cuda, oracle):

@@ -261,33 +261,50 @@ bool fastVectorOk(const LevelView* lv)
 
 // The tuned sRGBA8 kernel (nvpyr_fast_srgba8.cuh): warp-autonomous 64 x 2^M tiles, 32 warps per CTA.
 // batch != nullptr: one launch for batch->count chains of this size (p.lv[].ptr = offsets inside a chain).
-template <int M>
-nvpyrStatus launchFastSrgba8T(const DeviceContext& ctx, FastParams p, cudaStream_t stream, const FastBatch* batch = nullptr)
+// The tuned sRGBA8 fast kernel takes this step (else the functor-template kernel does).
+template <class F>
+bool tunedFastOk(const LevelView* lv)
 {
-  constexpr uint32_t tileH = M >= 3 ? (1u << M) : 8u;  // one warp per 64 x tileH tile
-  p.tilesX                 = (p.lv[0].w + 63u) / 64u;
-  p.tilesY                 = (p.lv[0].h + tileH - 1u) / tileH;
-  const size_t smem  = sizeof(Srgba8FastSmem);
-  int          grid  = 1;
-  FastBatch    b     = batch ? *batch : FastBatch{nullptr, 0u, 0u};
-  b.tilesPerImage    = p.tilesX * p.tilesY;
-  const uint64_t work = uint64_t(b.tilesPerImage) * (batch ? b.count : 1u);
-  if(work > 0xFFFFFFFFull)
-    return NVPYR_ERROR_INVALID_VALUE;
-  nvpyrStatus st = batch ? persistentGrid(fastSrgba8Kernel<M, true>, smem, ctx, work, &grid, kFastWarps * 32)
-                         : persistentGrid(fastSrgba8Kernel<M, false>, smem, ctx, work, &grid, kFastWarps * 32);
+  return std::is_same<F, Srgba8>::value && !g_forceGenericFast && fastVectorOk<F>(lv);
+}
+
+template <int M, bool kBatch, bool kPremul>
+nvpyrStatus launchFastSrgba8K(const DeviceContext& ctx, const FastParams& p, const FastBatch& b, uint64_t work,
+                              cudaStream_t stream)
+{
+  const size_t smem = sizeof(Srgba8FastSmem);
+  int          grid = 1;
+  nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M, kBatch, kPremul>, smem, ctx, work, &grid, kFastWarps * 32);
   if(st != NVPYR_SUCCESS)
     return st;
-  if(batch)
-    NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, true>, grid, kFastWarps * 32, smem, stream, p, b));
-  else
-    NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, false>, grid, kFastWarps * 32, smem, stream, p, b));
+  NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, kBatch, kPremul>, grid, kFastWarps * 32, smem, stream, p, b));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
 
+// premul: level 0 has straight alpha; premultiply it on the fly (scoped_image.hpp:233-255 fused into the read).
+template <int M>
+nvpyrStatus launchFastSrgba8T(const DeviceContext& ctx, FastParams p, cudaStream_t stream, const FastBatch* batch = nullptr,
+                              bool premul = false)
+{
+  constexpr uint32_t tileH = M >= 3 ? (1u << M) : 8u;  // one warp per 64 x tileH tile
+  p.tilesX                 = (p.lv[0].w + 63u) / 64u;
+  p.tilesY                 = (p.lv[0].h + tileH - 1u) / tileH;
+  FastBatch b              = batch ? *batch : FastBatch{nullptr, 0u, 0u};
+  b.tilesPerImage          = p.tilesX * p.tilesY;
+  const uint64_t work      = uint64_t(b.tilesPerImage) * (batch ? b.count : 1u);
+  if(work > 0xFFFFFFFFull)
+    return NVPYR_ERROR_INVALID_VALUE;
+  if(batch)
+    return premul ? launchFastSrgba8K<M, true, true>(ctx, p, b, work, stream)
+                  : launchFastSrgba8K<M, true, false>(ctx, p, b, work, stream);
+  return premul ? launchFastSrgba8K<M, false, true>(ctx, p, b, work, stream)
+                : launchFastSrgba8K<M, false, false>(ctx, p, b, work, stream);
+}
+
+// premul (sRGBA8 tuned kernel only, see fusedPremultiplyOk): premultiply level 0 on the fly.
 template <class F>
-nvpyrStatus launchFast(const DeviceContext& ctx, FastParams p, uint32_t M, cudaStream_t stream)
+nvpyrStatus launchFast(const DeviceContext& ctx, FastParams p, uint32_t M, cudaStream_t stream, bool premul = false)
 {
   p.tables = ctx.tables;
   if(M == 1)
@@ -307,8 +324,8 @@ nvpyrStatus launchFast(const DeviceContext& ctx, FastParams p, uint32_t M, cudaS
   const bool vec = fastVectorOk<F>(p.lv);
 #define NVPYR_FAST_CASE(m)                                                                                        \
   case m:                                                                                                         \
-    if(std::is_same<F, Srgba8>::value && vec && !g_forceGenericFast)                                              \
-      return launchFastSrgba8T<m>(ctx, p, stream);                                                                \
+    if(tunedFastOk<F>(p.lv))                                                                                      \
+      return launchFastSrgba8T<m>(ctx, p, stream, nullptr, premul);                                               \
     return vec ? launchFastT<F, m, true>(ctx, p, stream) : launchFastT<F, m, false>(ctx, p, stream);
   switch(M)
   {
@@ -534,8 +551,9 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
 
 // firstStep > 0: the steps before it have been enqueued by the caller (nvpyrGenerateHost runs step 0
 // band by band).
+// premulFirst: step 0 also premultiplies level 0 on the fly (the caller checked canFusePremultiply).
 template <class F>
-nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0)
+nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0, bool premulFirst = false)
 {
   nvpyrPlanStep steps[NVPYR_MAX_STEPS];
   const int     n = buildPlan(r.w, r.h, r.levels, defaultGeneralDispatcher, r.fast, steps, NVPYR_MAX_STEPS);
@@ -563,7 +581,7 @@ nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0
         FastParams p{};
         for(uint32_t k = 0; k <= s.levelCount; ++k)
           p.lv[k] = r.lv[s.inputLevel + k];
-        st = launchFast<F>(ctx, p, s.levelCount, r.stream);
+        st = launchFast<F>(ctx, p, s.levelCount, r.stream, premulFirst && i == 0);
       }
       else
       {
@@ -581,17 +599,36 @@ nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0
   return NVPYR_SUCCESS;
 }
 
+// The premultiply pre-pass can ride in the first launch when that launch is the tuned sRGBA8 fast kernel
+// (tiles never overlap, so rewriting level 0 in place is safe; the general pipeline re-reads halo columns).
+bool canFusePremultiply(const ResolvedDesc& r)
+{
+  if(r.format != NVPYR_FORMAT_SRGBA8 || r.levels < 2 || r.fast == nullptr)
+    return false;
+  nvpyrPlanStep steps[NVPYR_MAX_STEPS];
+  const int     n = buildPlan(r.w, r.h, r.levels, defaultGeneralDispatcher, r.fast, steps, NVPYR_MAX_STEPS);
+  if(n < 1 || steps[0].pipeline != 1 || steps[0].levelCount < 2)
+    return false;
+  if(!g_noTailFusion && uint64_t(steps[0].srcWidth) * steps[0].srcHeight <= kTailMaxTexels)
+    return false;  // small images start in tailKernel
+  return tunedFastOk<Srgba8>(r.lv);
+}
+
 nvpyrStatus dispatchResolved(const ResolvedDesc& r)
 {
   DeviceContext* ctx = nullptr;
   nvpyrStatus    st  = getContext(&ctx);
   if(st != NVPYR_SUCCESS)
     return st;
+  bool fusePremul = false;
   if(r.flags & NVPYR_FLAG_PREMULTIPLY_ALPHA)
   {
+    fusePremul = canFusePremultiply(r);
     // Level 0 is tight in the packed layout; with a pitched level 0 go row by row.
     const LevelView& v = r.lv[0];
-    if(v.pitch == v.w * 4u)
+    if(fusePremul)
+      ;
+    else if(v.pitch == v.w * 4u)
       st = launchPremultiply(*ctx, v.ptr, v.ptr, uint64_t(v.w) * v.h, r.stream);
     else
       for(uint32_t y = 0; y < v.h && st == NVPYR_SUCCESS; ++y)
@@ -601,7 +638,7 @@ nvpyrStatus dispatchResolved(const ResolvedDesc& r)
   }
   if(r.levels <= 1)
     return NVPYR_SUCCESS;
-  return r.format == NVPYR_FORMAT_SRGBA8 ? runPlan<Srgba8>(*ctx, r) : runPlan<Rgba32f>(*ctx, r);
+  return r.format == NVPYR_FORMAT_SRGBA8 ? runPlan<Srgba8>(*ctx, r, 0, fusePremul) : runPlan<Rgba32f>(*ctx, r);
 }
 
 // ------------------------------------------------------------- fused batches
@@ -613,9 +650,10 @@ nvpyrStatus dispatchResolved(const ResolvedDesc& r)
 constexpr uint64_t kBatchSoloMaxTexels = 256ull * 256ull;
 
 template <int M>
-nvpyrStatus launchFastBatchM(const DeviceContext& ctx, const FastParams& p, cudaStream_t stream, const FastBatch& b)
+nvpyrStatus launchFastBatchM(const DeviceContext& ctx, const FastParams& p, cudaStream_t stream, const FastBatch& b,
+                             bool premul)
 {
-  return launchFastSrgba8T<M>(ctx, p, stream, &b);
+  return launchFastSrgba8T<M>(ctx, p, stream, &b, premul);
 }
 
 nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDesc>& r, bool* handled)
@@ -664,13 +702,7 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
   NVPYR_CUDA(cudaMemcpyAsync(devBases, hostBases.data(), size_t(count) * sizeof(void*), cudaMemcpyHostToDevice, a.stream));
   *handled = true;  // from here on errors are real errors
 
-  if(a.flags & NVPYR_FLAG_PREMULTIPLY_ALPHA)
-    for(const ResolvedDesc& d : r)
-    {
-      nvpyrStatus st = launchPremultiply(ctx, d.lv[0].ptr, d.lv[0].ptr, uint64_t(d.w) * d.h, d.stream);
-      if(st != NVPYR_SUCCESS)
-        return st;
-    }
+  const bool premul = a.flags & NVPYR_FLAG_PREMULTIPLY_ALPHA;  // fused into the level-0 read of the big step
 
   auto offsetView = [&](uint32_t level) {
     LevelView v = a.lv[level];
@@ -685,11 +717,11 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
   nvpyrStatus st;
   switch(steps[0].levelCount)
   {
-    case 2: st = launchFastBatchM<2>(ctx, p, a.stream, b); break;
-    case 3: st = launchFastBatchM<3>(ctx, p, a.stream, b); break;
-    case 4: st = launchFastBatchM<4>(ctx, p, a.stream, b); break;
-    case 5: st = launchFastBatchM<5>(ctx, p, a.stream, b); break;
-    default: st = launchFastBatchM<6>(ctx, p, a.stream, b); break;
+    case 2: st = launchFastBatchM<2>(ctx, p, a.stream, b, premul); break;
+    case 3: st = launchFastBatchM<3>(ctx, p, a.stream, b, premul); break;
+    case 4: st = launchFastBatchM<4>(ctx, p, a.stream, b, premul); break;
+    case 5: st = launchFastBatchM<5>(ctx, p, a.stream, b, premul); break;
+    default: st = launchFastBatchM<6>(ctx, p, a.stream, b, premul); break;
   }
   if(st != NVPYR_SUCCESS || n == 1)
     return st;
@@ -812,12 +844,6 @@ nvpyrStatus generateHostPipelined(DeviceContext& ctx, const ResolvedDesc& r, con
     NVPYR_CUDA(cudaMemcpyAsync(dev + row0 * rowBytes, hin + row0 * rowBytes, rows * rowBytes, cudaMemcpyHostToDevice, ctx.hostUp));
     NVPYR_CUDA(cudaEventRecord(ctx.hostEvUp[band], ctx.hostUp));
     NVPYR_CUDA(cudaStreamWaitEvent(ctx.hostRun, ctx.hostEvUp[band], 0));
-    if(premul)
-    {
-      nvpyrStatus st = launchPremultiply(ctx, dev + row0 * rowBytes, dev + row0 * rowBytes, uint64_t(rows) * r.w, ctx.hostRun);
-      if(st != NVPYR_SUCCESS)
-        return st;
-    }
     FastParams p{};
     for(uint32_t k = 0; k <= M; ++k)
     {
@@ -825,7 +851,14 @@ nvpyrStatus generateHostPipelined(DeviceContext& ctx, const ResolvedDesc& r, con
       p.lv[k].ptr = r.lv[k].ptr + size_t(row0 >> k) * r.lv[k].pitch;
       p.lv[k].h   = rows >> k;  // rows and row0 are multiples of 2^M (H is, too)
     }
-    nvpyrStatus st = launchFast<F>(ctx, p, M, ctx.hostRun);
+    const bool fusePremul = premul && tunedFastOk<F>(p.lv);
+    if(premul && !fusePremul)
+    {
+      nvpyrStatus st = launchPremultiply(ctx, dev + row0 * rowBytes, dev + row0 * rowBytes, uint64_t(rows) * r.w, ctx.hostRun);
+      if(st != NVPYR_SUCCESS)
+        return st;
+    }
+    nvpyrStatus st = launchFast<F>(ctx, p, M, ctx.hostRun, fusePremul);
     if(st != NVPYR_SUCCESS)
       return st;
     NVPYR_CUDA(cudaEventRecord(ctx.hostEvRun[band], ctx.hostRun));

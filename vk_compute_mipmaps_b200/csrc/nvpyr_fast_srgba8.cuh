@@ -128,6 +128,7 @@ __device__ __forceinline__ void srgba8FastInit(Srgba8FastSmem& sm, const DeviceT
   }
   if(threadIdx.x == 0)
   {
+    putZeroWord<0>(sm);  // premultiply pre-pass (K = 0: values are not sums)
     putZeroWord<1>(sm), putZeroWord<2>(sm), putZeroWord<3>(sm);
     putZeroWord<4>(sm), putZeroWord<5>(sm), putZeroWord<6>(sm);
   }
@@ -266,6 +267,31 @@ __device__ __forceinline__ V4 shflXor(V4 a, int mask)
   return r;
 }
 
+// Premultiply-alpha pre-pass of the reference's image loader (include/scoped_image.hpp:233-255), fused into
+// the level-0 read: c' = srgbFromLinear(linearFromSrgb(c) * (A * (1/255))) per colour channel, alpha kept.
+// Opaque texels are returned unchanged without any work: srgbFromLinear(linearFromSrgb(c)) == c for all 256
+// codes (tests/test_oracle_pins.py).  Uses the scaled tables: 2^-100 commutes with the rounding of the product.
+__device__ __forceinline__ uint32_t premultiplyWord(const unsigned char* dec, const unsigned char* enc, uint32_t laneOff,
+                                                    uint32_t encWay, uint32_t w)
+{
+  if((w >> 24) == 255u)
+    return w;
+  const float    a = decAlpha(w);
+  const uint32_t r = encScaled<0>(enc, __fmul_rn(dec8<0>(dec, w, laneOff), a), encWay);
+  const uint32_t g = encScaled<0>(enc, __fmul_rn(dec8<1>(dec, w, laneOff), a), encWay);
+  const uint32_t b = encScaled<0>(enc, __fmul_rn(dec8<2>(dec, w, laneOff), a), encWay);
+  // codes sit in byte 2 of r, g, b; alpha stays in byte 3 of w
+  return __byte_perm(__byte_perm(r, g, 0x0062), __byte_perm(b, w, 0x0072), 0x5410);
+}
+__device__ __forceinline__ bool premultiplyRow(const unsigned char* dec, const unsigned char* enc, uint32_t laneOff,
+                                               uint32_t encWay, uint4& c)
+{
+  const uint4 o = c;
+  c.x = premultiplyWord(dec, enc, laneOff, encWay, c.x), c.y = premultiplyWord(dec, enc, laneOff, encWay, c.y);
+  c.z = premultiplyWord(dec, enc, laneOff, encWay, c.z), c.w = premultiplyWord(dec, enc, laneOff, encWay, c.w);
+  return (o.x != c.x) | (o.y != c.y) | (o.z != c.z) | (o.w != c.w);
+}
+
 // Batch mode (nvpyrDispatchBatch on images of one size): ONE launch streams the same step of `count`
 // independent packed chains.  p.lv[k].ptr then holds the byte offset of level k inside a chain, bases[i]
 // the chain of image i; tile t belongs to image t / tilesPerImage.
@@ -275,7 +301,10 @@ struct FastBatch
   uint32_t                    tilesPerImage, count;
 };
 
-template <int M, bool kBatch>
+// kPremul: level 0 holds straight (un-premultiplied) alpha; it is premultiplied on the fly, written back in
+// place (only 4x4 blocks that changed) and the chain is generated from the premultiplied codes -- exactly what
+// premultiplyKernel followed by this kernel produce, minus one full read + write pass over level 0.
+template <int M, bool kBatch, bool kPremul>
 __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Kernel(const FastParams p, const FastBatch batch)
 {
   static_assert(M >= 2 && M <= 6, "2..6 levels");
@@ -361,7 +390,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
       const bool active = nxt.active;
       if(!kFastPrefetch)
         loadRows(nxt);  // no software prefetch: more resident warps hide the latency instead
-      const uint4 c0 = row[0], c1 = row[1], c2 = row[2], c3 = row[3];
+      uint4 c0 = row[0], c1 = row[1], c2 = row[2], c3 = row[3];
+      unsigned char* const curSrc = const_cast<unsigned char*>(nxt.src);
       // the next slab (of this tile, or the first one of this warp's next tile)
       if(slab + 1u < kSlabs)
       {
@@ -373,6 +403,21 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
       if(kFastPrefetch)
         loadRows(nxt);
 
+      if(kPremul && active)
+      {
+        const uint32_t way = kEncWays == 1 ? 0u : (lane & (kEncWays - 1u)) * 4u;
+        bool           changed = premultiplyRow(dec, enc, laneOff, way, c0);
+        changed |= premultiplyRow(dec, enc, laneOff, way, c1);
+        changed |= premultiplyRow(dec, enc, laneOff, way, c2);
+        changed |= premultiplyRow(dec, enc, laneOff, way, c3);
+        if(changed)
+        {
+          *reinterpret_cast<uint4*>(curSrc)              = c0;
+          *reinterpret_cast<uint4*>(curSrc + pitch0)      = c1;
+          *reinterpret_cast<uint4*>(curSrc + 2u * pitch0) = c2;
+          *reinterpret_cast<uint4*>(curSrc + 3u * pitch0) = c3;
+        }
+      }
       V4 s2 = toV4(make_float4(0.f, 0.f, 0.f, 0.f));
       if(active)
       {
