@@ -232,6 +232,18 @@ def test_premultiply(nv, cuda, oracle):
     s2 = cuda.from_numpy(op).cuda()
     nv.premultiply_alpha(None, s2, s2, 64 * 64)
     assert (s2.cpu().numpy() == op).all()
+    # texel counts that are not multiples of four, buffers that are only 4-byte aligned, in place and not
+    big = _oracle.random_level0(257, 129, 8)
+    want_big = oracle.premultiply(big)
+    for first, count in ((0, 257 * 129), (0, 1002), (1, 1003), (3, 4099), (2, 3)):
+        src = cuda.from_numpy(big).cuda()
+        dst = cuda.zeros_like(src)
+        nv.premultiply_alpha(None, src[4 * first:], dst[4 * first:], count)
+        nv.premultiply_alpha(None, src[4 * first:], src[4 * first:], count)
+        cuda.cuda.synchronize()
+        sl = slice(4 * first, 4 * (first + count))
+        assert (dst.cpu().numpy()[sl] == want_big[sl]).all() and (src.cpu().numpy()[sl] == want_big[sl]).all(), (first, count)
+        assert (dst.cpu().numpy()[4 * (first + count):] == 0).all() and (dst.cpu().numpy()[:4 * first] == 0).all()
 
 
 @pytest.mark.parametrize("size", [(1024, 1024), (1920, 1080), (1028, 1028), (768, 2048)])

@@ -19,9 +19,28 @@ for (w, h, fmt, fg) in cases:
     want = o.shader_chain(l0, w, h, fmt=fmt, force_general=fg)[0]
     got = buf.cpu().numpy()
     assert (got.view(np.uint8) == want.view(np.uint8)).all(), (w, h, fmt, fg)
+# fused batch (+ premultiply in the first launch), fused premultiply, stand-alone premultiply, banded host pipeline
+w, h = 1024, 512
+imgs, wants = [], []
+for k in range(3):
+    l0 = _oracle.random_level0(w, h, 40 + k)
+    wants.append(o.shader_chain(o.premultiply(l0), w, h)[0])
+    b = torch.zeros(nv.chain_bytes(w, h), dtype=torch.uint8, device='cuda'); b[:4 * w * h] = torch.from_numpy(l0).cuda(); imgs.append(b)
+nv.dispatch_batch(None, nv.PyramidPipelines(), imgs, w, h, flags=nv.FLAG_PREMULTIPLY_ALPHA)
+torch.cuda.synchronize()
+assert all((b.cpu().numpy() == x).all() for b, x in zip(imgs, wants)), 'batch'
+for (w, h) in [(1024, 768), (1023, 300)]:
+    l0 = _oracle.random_level0(w, h, 50)
+    b = torch.zeros(nv.chain_bytes(w, h), dtype=torch.uint8, device='cuda'); b[:4 * w * h] = torch.from_numpy(l0).cuda()
+    nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(), w, h, image=b, flags=nv.FLAG_PREMULTIPLY_ALPHA)
+    torch.cuda.synchronize()
+    assert (b.cpu().numpy() == o.shader_chain(o.premultiply(l0), w, h)[0]).all(), ('premultiply', w, h)
+w, h = 512, 1088
+l0 = _oracle.random_level0(w, h, 60)
+assert (nv.generate_host(l0, w, h) == o.shader_chain(l0, w, h)[0]).all(), 'host pipeline'
 print('sanitize driver ok')
 PY
 for tail in 262144 0; do
   echo "== $TOOL NVPYR_TAIL_MAX_TEXELS=$tail"
-  NVPYR_TAIL_MAX_TEXELS=$tail compute-sanitizer --tool $TOOL --kernel-regex kns=nvpyr --print-limit 20 python /tmp/san_driver.py 2>&1 | tail -6
+  NVPYR_HOST_BAND_BYTES=131072 NVPYR_TAIL_MAX_TEXELS=$tail compute-sanitizer --tool $TOOL --kernel-regex kns=nvpyr --print-limit 20 python /tmp/san_driver.py 2>&1 | tail -6
 done

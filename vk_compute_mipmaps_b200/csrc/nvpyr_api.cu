@@ -408,13 +408,33 @@ nvpyrStatus launchGeneral(const DeviceContext& ctx, GeneralParams p, cudaStream_
 nvpyrStatus launchPremultiply(const DeviceContext& ctx, const void* in, void* out, uint64_t texels,
                               cudaStream_t stream)
 {
+  // 16-byte aligned buffers: groups of four texels through the conflict-free tables of the fast kernel;
+  // the (at most three) texels left over, and unaligned buffers, through the functor-table kernel.
+  uint64_t done = 0;
+  if(reinterpret_cast<uintptr_t>(in) % 16u == 0 && reinterpret_cast<uintptr_t>(out) % 16u == 0 && texels >= 4u
+     && !g_forceGenericFast)
+  {
+    const uint64_t n4   = texels / 4u;
+    const size_t   smem = sizeof(Srgba8FastSmem);
+    int            grid = 1;
+    nvpyrStatus    st   = persistentGrid(premultiplySrgba8Kernel, smem, ctx, (n4 + kFastWarps * 32 - 1) / (kFastWarps * 32), &grid,
+                                         kFastWarps * 32);
+    if(st != NVPYR_SUCCESS)
+      return st;
+    NVPYR_CUDA(launchKernel(premultiplySrgba8Kernel, grid, kFastWarps * 32, smem, stream, static_cast<const uint4*>(in),
+                            static_cast<uint4*>(out), n4, static_cast<const DeviceTables*>(ctx.tables)));
+    ++g_launchCount;
+    done = n4 * 4u;
+    if(done == texels)
+      return NVPYR_SUCCESS;
+  }
   const size_t smem = sizeof(Srgba8::Shared);
   int          grid = 1;
-  nvpyrStatus  st   = persistentGrid(premultiplyKernel, smem, ctx, (texels + 255u) / 256u, &grid);
+  nvpyrStatus  st   = persistentGrid(premultiplyKernel, smem, ctx, (texels - done + 255u) / 256u, &grid);
   if(st != NVPYR_SUCCESS)
     return st;
-  NVPYR_CUDA(launchKernel(premultiplyKernel, grid, 256, smem, stream, static_cast<const uint32_t*>(in),
-                          static_cast<uint32_t*>(out), texels, static_cast<const DeviceTables*>(ctx.tables)));
+  NVPYR_CUDA(launchKernel(premultiplyKernel, grid, 256, smem, stream, static_cast<const uint32_t*>(in) + done,
+                          static_cast<uint32_t*>(out) + done, texels - done, static_cast<const DeviceTables*>(ctx.tables)));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }

@@ -292,6 +292,40 @@ __device__ __forceinline__ bool premultiplyRow(const unsigned char* dec, const u
   return (o.x != c.x) | (o.y != c.y) | (o.z != c.z) | (o.w != c.w);
 }
 
+// Stand-alone premultiply pre-pass over n4 groups of four texels (16-byte aligned in and out; in == out
+// allowed), with the conflict-free tables of the fast kernel.  Used where the pre-pass cannot ride in a
+// fast step (chains that start with the general pipeline, nvpyrPremultiplyAlpha).
+__global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
+    premultiplySrgba8Kernel(const uint4* in, uint4* out, uint64_t n4, const DeviceTables* tables)
+{
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  Srgba8FastSmem& sm = *reinterpret_cast<Srgba8FastSmem*>(smemRaw);
+  srgba8FastInit(sm, tables);
+  __syncthreads();
+  gridDependencyWait();
+  gridLaunchDependents();
+  const unsigned char* dec = reinterpret_cast<const unsigned char*>(sm.decode);
+  const unsigned char* enc = reinterpret_cast<const unsigned char*>(sm.encode);
+  const uint32_t       lane = threadIdx.x & 31u, laneOff = lane * 4u;
+  const uint32_t       way  = kEncWays == 1 ? 0u : (lane & (kEncWays - 1u)) * 4u;
+  const uint64_t       step = uint64_t(gridDim.x) * blockDim.x;
+  for(uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += 2u * step)
+  {
+    // two independent groups per trip: more loads in flight
+    const bool second = i + step < n4;
+    uint4      a = __ldg(in + i), b = second ? __ldg(in + i + step) : make_uint4(0u, 0u, 0u, 0u);
+    const bool ca = premultiplyRow(dec, enc, laneOff, way, a);
+    if(ca || in != out)
+      out[i] = a;
+    if(second)
+    {
+      const bool cb = premultiplyRow(dec, enc, laneOff, way, b);
+      if(cb || in != out)
+        out[i + step] = b;
+    }
+  }
+}
+
 // Batch mode (nvpyrDispatchBatch on images of one size): ONE launch streams the same step of `count`
 // independent packed chains.  p.lv[k].ptr then holds the byte offset of level k inside a chain, bases[i]
 // the chain of image i; tile t belongs to image t / tilesPerImage.
