@@ -73,7 +73,11 @@ typedef enum nvpyrFlags
   NVPYR_FLAG_FORCE_GENERAL = 1u << 0,
   /* Run the premultiply-alpha pre-pass of include/scoped_image.hpp:233-255 on level 0
    * (in place) before generating. sRGBA8 only. */
-  NVPYR_FLAG_PREMULTIPLY_ALPHA = 1u << 1
+  NVPYR_FLAG_PREMULTIPLY_ALPHA = 1u << 1,
+  /* The reference's optional F16_SHARED build of the sRGBA8 shaders (srgba8_mipmap_preamble.glsl:103-108,
+   * demo_app alternative "f16Shared"): values that pass through shared memory inside a dispatch are rounded
+   * to IEEE binary16.  Non-default and lossy; sRGBA8 only; runs on the functor-template kernels. */
+  NVPYR_FLAG_F16_SHARED = 1u << 2
 } nvpyrFlags;
 
 typedef struct CUstream_st* nvpyrStream; /* == cudaStream_t == CUstream */

@@ -69,6 +69,7 @@ struct uvec4
 };
 
 struct vec4;
+struct f16vec4;  // GL_EXT_shader_explicit_arithmetic_types, used by the F16_SHARED build of the preamble
 struct Prod  // a * v, not yet rounded: lets "p + q" and "v + p" contract into an fma like a GPU compiler
 {
   float a;
@@ -82,12 +83,22 @@ struct vec4
   vec4(Float x_, Float y_, Float z_, Float w_) : x(x_), y(y_), z(z_), w(w_) {}
   vec4(const Prod& p) : x(p.a * p.v[0]), y(p.a * p.v[1]), z(p.a * p.v[2]), w(p.a * p.v[3]) {}
   vec4(const vec4& o) : x(o.x), y(o.y), z(o.z), w(o.w) {}
+  explicit vec4(const f16vec4& h);
   vec4& operator=(const vec4& o)
   {
     x = o.x, y = o.y, z = o.z, w = o.w;
     return *this;
   }
 };
+// f16vec4(vec4) rounds every component to IEEE binary16, round to nearest even (the conversion mode GPUs
+// use for OpFConvert unless decorated otherwise); vec4(f16vec4) widens exactly.
+struct f16vec4
+{
+  _Float16 x, y, z, w;
+  f16vec4() = default;
+  explicit f16vec4(const vec4& v) : x(_Float16(v.x.v)), y(_Float16(v.y.v)), z(_Float16(v.z.v)), w(_Float16(v.w.v)) {}
+};
+inline vec4::vec4(const f16vec4& h) : x(float(h.x)), y(float(h.y)), z(float(h.z)), w(float(h.w)) {}
 inline vec4 operator+(const vec4& a, const vec4& b) { return vec4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 inline Prod operator*(Float s, const vec4& v) { return Prod{s.v, {v.x.v, v.y.v, v.z.v, v.w.v}}; }
 inline vec4 operator+(const vec4& c, const Prod& p)

@@ -305,7 +305,21 @@ typedef struct
   uint64_t off[33];
   uint32_t lw[33], lh[33];
   uint64_t stores; /* number of NVPRO_PYRAMID_STORE executed */
+  int      shared_f16; /* F16_SHARED build of the shaders (srgba8_mipmap_preamble.glsl:103-108) */
 } actx;
+
+/* NVPRO_PYRAMID_SHARED_STORE followed by NVPRO_PYRAMID_SHARED_LOAD.  Default: the shared type is the value
+ * type (nvpro_pyramid.glsl:204-206).  F16_SHARED: f16vec4(in_) then vec4(smem_), i.e. every component is
+ * rounded to IEEE binary16 (round to nearest even) and widened again. */
+static inline vec4 a_shared_round(const actx* c, vec4 v)
+{
+  if(c->shared_f16)
+  {
+    v.x = (float)(_Float16)v.x, v.y = (float)(_Float16)v.y;
+    v.z = (float)(_Float16)v.z, v.w = (float)(_Float16)v.w;
+  }
+  return v;
+}
 
 static void actx_init(actx* c, int fmt, void* chain, uint32_t w, uint32_t h, uint32_t levels)
 {
@@ -533,7 +547,7 @@ static void a_handle_tile(actx* c, fast_wg_state* s, const ivec2* srcTileOffset,
       nxt[l] = a_reduce4(s00, s01, s10, s11);
       a_store(c, s->dstSubTile[l], s->dstLevel[l], nxt[l]);
       if(sharedMemoryWrite)
-        s->sharedTile[sharedMemoryIdx[l]] = nxt[l];
+        s->sharedTile[sharedMemoryIdx[l]] = a_shared_round(c, nxt[l]);
     }
   }
   memcpy(s->out, nxt, sizeof nxt);
@@ -803,7 +817,7 @@ static void a_general_workgroup(actx* c, uint32_t wg, uint32_t pc)
             break;
         }
         vec4 v = a_reduce_store_sample(c, &s, src, inputLevel, 0, kernelSize, dstSize, dst, level1);
-        s.sharedLevel[sh.y][sh.x] = v;
+        s.sharedLevel[sh.y][sh.x] = a_shared_round(c, v);
       }
     }
   }
@@ -827,7 +841,7 @@ static void a_general_workgroup(actx* c, uint32_t wg, uint32_t pc)
 }
 
 /* Whole chain in shader order.  fmt 0: chain = uint8 RGBA; fmt 1: float RGBA.
- * flags bit0: force general pipeline (no fast pipeline available).
+ * flags bit0: force general pipeline (no fast pipeline available); bit1: F16_SHARED build.
  * Returns number of dispatches, <0 on error.  stores_out (optional) receives
  * the number of texel stores executed (coverage accounting). */
 int nvo_shader_chain(int fmt, void* chain, uint32_t w, uint32_t h, uint32_t mip_levels, uint32_t flags,
@@ -845,6 +859,7 @@ int nvo_shader_chain(int fmt, void* chain, uint32_t w, uint32_t h, uint32_t mip_
     return n;
   actx c;
   actx_init(&c, fmt, chain, w, h, mip_levels);
+  c.shared_f16 = (flags & 2u) != 0;
   for(int i = 0; i < n; ++i)
   {
     for(uint32_t wg = 0; wg < steps[i].workgroups; ++wg)

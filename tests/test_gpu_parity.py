@@ -273,6 +273,27 @@ def test_premultiply_fused_into_level0_read(nv, cuda, oracle, size):
         assert nv.launch_count() - before == launches
 
 
+@pytest.mark.parametrize("size", [(256, 256), (1024, 512), (96, 160), (32, 32), (260, 260), (255, 255), (511, 300),
+                                  (136, 512), (1920, 1080), (100, 37), (64, 4096)])
+def test_f16_shared_variant_bit_exact(nv, cuda, oracle, size):
+    """NVPYR_FLAG_F16_SHARED = the reference's F16_SHARED build of the sRGBA8 shaders (values passing through
+    shared memory inside a dispatch are rounded to binary16): bit-exact against Oracle A's restatement, which
+    is pinned by executing the reference's shaders with the macro set (tests/test_oracle_pins.py).  Also with
+    the fast pipeline disabled, through the host round trip, and rejected for rgba32f."""
+    w, h = size
+    l0 = _oracle.random_level0(w, h, 21)
+    for fg in (False, True):
+        want, _ = oracle.shader_chain(l0, w, h, force_general=fg, f16_shared=True)
+        got = gpu_chain(nv, cuda, l0, w, h, pipelines=nv.PyramidPipelines(fast_pipeline=not fg), flags=nv.FLAG_F16_SHARED)
+        assert_same(got, want, w, h, oracle, f"f16 shared, force_general={fg}")
+    want, _ = oracle.shader_chain(l0, w, h, f16_shared=True)
+    assert (nv.generate_host(l0, w, h, flags=nv.FLAG_F16_SHARED) == want).all()
+    if size == (256, 256):
+        assert (want != oracle.shader_chain(l0, w, h)[0]).any()
+        with pytest.raises(nv.NvpyrError):
+            gpu_chain(nv, cuda, _oracle.random_level0(64, 64, 1, fmt=1), 64, 64, fmt=1, flags=nv.FLAG_F16_SHARED)
+
+
 def test_partial_level_count(nv, cuda, oracle):
     w, h = 256, 256
     l0 = _oracle.random_level0(w, h, 6)
@@ -472,6 +493,49 @@ def test_other_stream(nv, cuda, oracle):
         nv.cmd_pyramid_dispatch(s, nv.PyramidPipelines(), w, h, image=buf)
     s.synchronize()
     assert (buf.cpu().numpy() == want).all()
+
+
+def test_reentrant_from_several_host_threads(nv, cuda, oracle):
+    """SURVEY 8b threading contract: the entry points are reentrant and safe from several host threads on
+    different streams (dispatch, batch and the host round trip share per-device state: ticket pool, base
+    pointer ring, staging chain).  Eight threads, each with its own stream and images, many rounds."""
+    import threading
+    sizes = [(1024, 512), (260, 260), (255, 131), (1024, 1024)]
+    jobs = []
+    for t in range(8):
+        w, h = sizes[t % len(sizes)]
+        l0 = _oracle.random_level0(w, h, 900 + t)
+        jobs.append((w, h, l0, oracle.shader_chain(l0, w, h)[0]))
+    errors = []
+
+    def worker(t):
+        try:
+            w, h, l0, want = jobs[t]
+            stream = cuda.cuda.Stream()
+            bufs = [cuda.zeros(nv.chain_bytes(w, h), dtype=cuda.uint8, device="cuda") for _ in range(3)]
+            for rnd in range(6):
+                for b in bufs:
+                    b.zero_()
+                    b[:4 * w * h] = cuda.from_numpy(l0).cuda()
+                cuda.cuda.synchronize()
+                nv.cmd_pyramid_dispatch(stream, nv.PyramidPipelines(), w, h, image=bufs[0])
+                nv.dispatch_batch(stream, nv.PyramidPipelines(), bufs[1:], w, h)
+                host = nv.generate_host(l0, w, h)
+                stream.synchronize()
+                for b in bufs:
+                    if not (b.cpu().numpy() == want).all():
+                        errors.append((t, rnd, "device"))
+                if not (host == want).all():
+                    errors.append((t, rnd, "host"))
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:5]
 
 
 def test_negative_control_is_detected(nv, cuda, oracle):

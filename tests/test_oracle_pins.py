@@ -191,6 +191,29 @@ def test_oracle_a_equals_executed_reference_shaders_partial_levels(oracle, emu):
         assert (got == want).all(), levels
 
 
+F16_SIZES = [(64, 64), (256, 256), (128, 64), (16, 48), (32, 32), (96, 160), (192, 320), (63, 63), (100, 37), (260, 260),
+             (136, 512), (120, 72), (255, 255), (17, 129), (129, 129), (511, 300)]
+
+
+@pytest.mark.parametrize("size", F16_SIZES, ids=lambda s: f"{s[0]}x{s[1]}")
+def test_oracle_a_f16_shared_equals_executed_reference_shaders(oracle, emu, size):
+    """The F16_SHARED build (srgba8_mipmap_preamble.glsl:103-108): the reference's shaders compiled with the macro
+    set, f16vec4 = IEEE binary16 round-to-nearest-even, against Oracle A's restatement of it.  The variant must
+    differ from the default build somewhere (else the test would prove nothing)."""
+    w, h = size
+    differs = False
+    for seed, make in ((1, _oracle.random_level0), (2, lambda w, h, s: _oracle.smooth_level0(w, h, s))):
+        l0 = make(w, h, seed)
+        for have_fast in (1, 0):
+            want, stores = oracle.shader_chain(l0, w, h, force_general=not have_fast, f16_shared=True)
+            got, _, emu_stores = emu.run_chain(oracle.new_chain(l0, w, h), w, h, 0, have_fast, f16_shared=1)
+            assert (got == want).all(), (size, have_fast)
+            assert emu_stores == stores
+            differs |= bool((want != oracle.shader_chain(l0, w, h, force_general=not have_fast)[0]).any())
+    if max(w, h) >= 64:
+        assert differs
+
+
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_golden_fixtures_through_executed_shaders(oracle, emu, path):
     g = np.load(path)

@@ -457,9 +457,9 @@ nvpyrStatus resolve(const nvpyrDispatchDesc* d, ResolvedDesc& r)
     return NVPYR_ERROR_INVALID_VALUE;
   if(d->format != NVPYR_FORMAT_SRGBA8 && d->format != NVPYR_FORMAT_RGBA32F)
     return NVPYR_ERROR_UNSUPPORTED;
-  if(d->flags & ~uint32_t(NVPYR_FLAG_FORCE_GENERAL | NVPYR_FLAG_PREMULTIPLY_ALPHA))
+  if(d->flags & ~uint32_t(NVPYR_FLAG_FORCE_GENERAL | NVPYR_FLAG_PREMULTIPLY_ALPHA | NVPYR_FLAG_F16_SHARED))
     return NVPYR_ERROR_UNSUPPORTED;
-  if((d->flags & NVPYR_FLAG_PREMULTIPLY_ALPHA) && d->format != NVPYR_FORMAT_SRGBA8)
+  if((d->flags & (NVPYR_FLAG_PREMULTIPLY_ALPHA | NVPYR_FLAG_F16_SHARED)) && d->format != NVPYR_FORMAT_SRGBA8)
     return NVPYR_ERROR_UNSUPPORTED;
   r.format         = d->format;
   r.flags          = d->flags;
@@ -623,7 +623,7 @@ nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0
 // (tiles never overlap, so rewriting level 0 in place is safe; the general pipeline re-reads halo columns).
 bool canFusePremultiply(const ResolvedDesc& r)
 {
-  if(r.format != NVPYR_FORMAT_SRGBA8 || r.levels < 2 || r.fast == nullptr)
+  if(r.format != NVPYR_FORMAT_SRGBA8 || r.levels < 2 || r.fast == nullptr || (r.flags & NVPYR_FLAG_F16_SHARED))
     return false;
   nvpyrPlanStep steps[NVPYR_MAX_STEPS];
   const int     n = buildPlan(r.w, r.h, r.levels, defaultGeneralDispatcher, r.fast, steps, NVPYR_MAX_STEPS);
@@ -658,6 +658,8 @@ nvpyrStatus dispatchResolved(const ResolvedDesc& r)
   }
   if(r.levels <= 1)
     return NVPYR_SUCCESS;
+  if(r.flags & NVPYR_FLAG_F16_SHARED)
+    return runPlan<Srgba8F16Shared>(*ctx, r);
   return r.format == NVPYR_FORMAT_SRGBA8 ? runPlan<Srgba8>(*ctx, r, 0, fusePremul) : runPlan<Rgba32f>(*ctx, r);
 }
 
@@ -682,7 +684,7 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
   const ResolvedDesc& a     = r[0];
   const uint32_t      count = uint32_t(r.size());
   if(count < 2 || count > kBatchRing / 4 || a.format != NVPYR_FORMAT_SRGBA8 || a.levels < 2 || g_forceGenericFast
-     || g_noTailFusion || a.fast == nullptr)
+     || g_noTailFusion || a.fast == nullptr || (a.flags & NVPYR_FLAG_F16_SHARED))
     return NVPYR_SUCCESS;
   for(const ResolvedDesc& d : r)
   {
@@ -1080,8 +1082,11 @@ nvpyrStatus nvpyrGenerateHost(const void* hostLevel0, void* hostChain, nvpyrExte
   st = resolve(&d, r);
   if(st != NVPYR_SUCCESS)
     return st;
-  st = r.format == NVPYR_FORMAT_SRGBA8 ? generateHostPipelined<Srgba8>(*ctx, r, hostLevel0, hostChain, bytes)
-                                       : generateHostPipelined<Rgba32f>(*ctx, r, hostLevel0, hostChain, bytes);
+  if(r.flags & NVPYR_FLAG_F16_SHARED)
+    st = generateHostPipelined<Srgba8F16Shared>(*ctx, r, hostLevel0, hostChain, bytes);
+  else
+    st = r.format == NVPYR_FORMAT_SRGBA8 ? generateHostPipelined<Srgba8>(*ctx, r, hostLevel0, hostChain, bytes)
+                                         : generateHostPipelined<Rgba32f>(*ctx, r, hostLevel0, hostChain, bytes);
   // Never leave work in flight on the shared scratch chain, success or not.
   const cudaError_t e0 = cudaStreamSynchronize(ctx->hostUp), e1 = cudaStreamSynchronize(ctx->hostRun),
                     e2 = cudaStreamSynchronize(ctx->hostDown);

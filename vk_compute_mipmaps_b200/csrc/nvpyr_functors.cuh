@@ -18,6 +18,7 @@
 //     static Value reduce(float a0, Value v0, float a1, Value v1, float a2, Value v2);  // _REDUCE
 //     static Value reduce2(Value, Value);                               // _REDUCE2
 //     static Value reduce4(Value v00, Value v01, Value v10, Value v11); // _REDUCE4
+//     static Value sharedRound(Value);   // _SHARED_STORE followed by _SHARED_LOAD (identity by default)
 //   };
 //
 // Shipped instances: Srgba8 (nvpro_pyramid/srgba8_mipmap_preamble.glsl) and
@@ -26,6 +27,7 @@
 // is float32, round-to-nearest, the pairing order of the reference shader, and
 // exactly one explicit contraction (the 3-tap REDUCE = mul, fma, fma).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -121,6 +123,11 @@ struct LinearReduce
                        reduce1(a0, v0.z, a1, v1.z, a2, v2.z), reduce1(a0, v0.w, a1, v1.w, a2, v2.w));
   }
   __device__ __forceinline__ static Value reduce2(Value v0, Value v1) { return f4scale(0.5f, f4add(v0, v1)); }
+  // NVPRO_PYRAMID_SHARED_STORE + NVPRO_PYRAMID_SHARED_LOAD: what a value becomes on its way through the
+  // reference's shared memory (sharedTile_, glsl:253,395,487-512; sharedLevel_, glsl:555,664,717).  The
+  // default shared type is the value type itself (glsl:204-206): identity.  Our kernels keep such values in
+  // registers or float4 shared memory and apply this function where the reference stores them.
+  __device__ __forceinline__ static Value sharedRound(Value v) { return v; }
   // 0.25 * ((v00 + v01) + (v10 + v11)): the caller chooses which neighbours share a
   // bracket (pairing order differs per site in the reference, SURVEY.md section 8a note 1).
   __device__ __forceinline__ static Value reduce4(Value v00, Value v01, Value v10, Value v11)
@@ -232,6 +239,19 @@ struct Srgba8T : LinearReduce
 
 using Srgba8     = Srgba8T<32>;
 using Srgba8Lite = Srgba8T<1>;
+
+// F16_SHARED variant of the sRGBA8 instance (srgba8_mipmap_preamble.glsl:103-108): the shared type is
+// f16vec4, i.e. values that pass through shared memory are rounded to IEEE binary16 (round to nearest even,
+// the conversion of f16vec4(vec4)) and widened again.  Non-default in the reference; runs on the
+// functor-template kernels only.
+struct Srgba8F16Shared : Srgba8T<1>
+{
+  __device__ __forceinline__ static Value sharedRound(Value v)
+  {
+    return make_float4(__half2float(__float2half_rn(v.x)), __half2float(__float2half_rn(v.y)),
+                       __half2float(__float2half_rn(v.z)), __half2float(__float2half_rn(v.w)));
+  }
+};
 
 // ---------------------------------------------------------------------------
 // RGBA32F: the template of nvpro_pyramid.glsl:27-49 instantiated with identity

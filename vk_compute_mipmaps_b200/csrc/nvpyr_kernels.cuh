@@ -146,8 +146,10 @@ __device__ __forceinline__ void fastTileLoop(const FastParams& p, const typename
       {
         F::template store<false>(
             tables, p.lv[3].ptr + size_t(y0 >> 3) * p.lv[3].pitch + size_t(x0 >> 3) * F::kTexelBytes, l3);
+        // The reference hands the last shuffle-made level to its tail through sharedTile_ (glsl:395): that is
+        // level +3 for M = 4, 5 and level +4 for M = 6 (where +3 travels by shuffle, full precision).
         if(M >= 4)
-          l3buf[parity][ty >> 1][tx >> 1] = l3;
+          l3buf[parity][ty >> 1][tx >> 1] = M == 6 ? l3 : F::sharedRound(l3);
       }
     }
 
@@ -171,6 +173,8 @@ __device__ __forceinline__ void fastTileLoop(const FastParams& p, const typename
         }
         if(M >= 5)
         {
+          if(M == 6)
+            l4 = F::sharedRound(l4);  // sharedTile_ of the 6-level step holds level +4
           const V sx = shflXor(l4, 1), sy = shflXor(l4, 4), sxy = shflXor(l4, 5);
           const V l5 = reduce4Paired<F>(fastPairingIsHorizontal(5, M), l4, sx, sy, sxy);
           if(valid && !(i & 1u) && !(j & 1u))
@@ -371,7 +375,7 @@ __device__ __forceinline__ void generalTileLoop(const GeneralParams& p, const ty
       // The halo column/row is also produced (with identical bits) by the neighbouring
       // tile, exactly like the reference's overlapping work groups.
       F::template store<true>(tables, L1.ptr + size_t(y) * L1.pitch + size_t(x) * F::kTexelBytes, out);
-      l1buf[ly][lx] = out;
+      l1buf[ly][lx] = F::sharedRound(out);  // sharedLevel_ (glsl:717)
     }
     __syncthreads();
     const uint32_t tw = x2b - x2a, th = y2b - y2a;
