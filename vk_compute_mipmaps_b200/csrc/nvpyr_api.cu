@@ -561,10 +561,10 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
     work = (uint64_t(tp.steps[0].lv[1].w) * tp.steps[0].lv[1].h + 255u) / 256u;
   const size_t smem = sizeof(TailSmem<TF>);
   int          grid = 1;
-  nvpyrStatus  st   = persistentGrid(tailKernel<TF>, smem, ctx, work, &grid);
+  nvpyrStatus  st   = persistentGrid(tailKernel<TF>, smem, ctx, work, &grid, kTailThreads);
   if(st != NVPYR_SUCCESS)
     return st;
-  NVPYR_CUDA(launchKernel(tailKernel<TF>, grid, 256, smem, r.stream, tp));
+  NVPYR_CUDA(launchKernel(tailKernel<TF>, grid, kTailThreads, smem, r.stream, tp));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
@@ -775,10 +775,11 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
   }
   const size_t smem = sizeof(TailSmem<TF>);
   int          grid = 1;
-  st                = persistentGrid(tailBatchKernel<TF>, smem, ctx, count, &grid);
+  st                = persistentGrid(tailBatchKernel<TF>, smem, ctx, count, &grid, kTailThreads);
   if(st != NVPYR_SUCCESS)
     return st;
-  NVPYR_CUDA(launchKernel(tailBatchKernel<TF>, grid, 256, smem, a.stream, tp, static_cast<const unsigned char* const*>(devBases), count));
+  NVPYR_CUDA(launchKernel(tailBatchKernel<TF>, grid, kTailThreads, smem, a.stream, tp,
+                          static_cast<const unsigned char* const*>(devBases), count));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }

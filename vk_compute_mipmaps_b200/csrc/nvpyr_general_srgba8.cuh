@@ -30,14 +30,18 @@ namespace nvpyr {
 // that extracts the index (the kernel is instruction-issue bound; a base-address add per look-up was 8 % of
 // all instructions).  Addresses below are in the CTA's shared window, whose dynamic part starts at
 // kGenWindowBase (1 KB is reserved by the system on sm_100; checked at run time, the kernel traps otherwise):
-//   * decode table at window address 0x20000, [code][64 floats] (floats 0..31 = one copy per lane):
-//     address = 0x20000 | code << 8 | lane << 2 is produced by ONE PRMT from the packed texel and
-//     (0x20000 | lane << 2);
-//   * encode bucket table placed so that the entry of key k sits at window address 4 k: the masked, shifted
-//     float bits ARE the address.
+//   * decode table at window address 0x10000, [code][64 floats] (floats 0..31 = one copy per lane):
+//     address = 0x10000 | code << 8 | lane << 2 is produced by ONE PRMT from the packed texel and
+//     (0x10000 | lane << 2);
+//   * encode bucket table placed so that the entry of key k sits at window address (4 k) mod 2^16: the
+//     masked, shifted float bits ARE the address (keys 0x7200..0x7F00 -> 0xC800..0xFC00, no wrap inside).
+// 127 KB per CTA, one CTA per SM; ~100 KB stay free for the next kernel's CTAs (programmatic dependent launch).
 constexpr uint32_t kGenWindowBase = 0x400u;
-constexpr uint32_t kGenDecodeAddr = 0x20000u;
-constexpr uint32_t kGenEncodeAddr = kEncMinKey * 4u;  // window address of the first entry (key kEncMinKey)
+constexpr uint32_t kGenDecodeAddr = 0x10000u;
+constexpr uint32_t kGenEncodeMask = 0xFFFCu;
+constexpr uint32_t kGenEncodeAddr = (kEncMinKey * 4u) & kGenEncodeMask;  // window address of the first entry
+static_assert(((kEncMaxKey * 4u) & kGenEncodeMask) == kGenEncodeAddr + (kEncMaxKey - kEncMinKey) * 4u,
+              "the key range must not wrap inside the 16-bit window");
 constexpr uint32_t kGenSmemBytes  = kGenDecodeAddr + 256u * 256u - kGenWindowBase;
 static_assert(kGenEncodeAddr >= kGenWindowBase && kGenEncodeAddr + kEncEntriesPadded * 4u <= kGenDecodeAddr,
               "encode table must fit below the decode table");
@@ -129,7 +133,7 @@ __device__ __forceinline__ uint32_t genEncChannel(float x)
   // Weighted sums stay below 1 + 2^-8, i.e. inside the table's last bucket (key of 1.0f): only the lower
   // clamp is needed.
   const uint32_t b    = max(__float_as_uint(x), kEncMinBits);
-  const uint32_t addr = (b >> (kEncShift - 2)) & 0x3FFFCu;  // = 4 * key = the entry's shared address
+  const uint32_t addr = (b >> (kEncShift - 2)) & kGenEncodeMask;  // = (4 * key) mod 2^16 = the entry's shared address
   uint32_t       e;
   asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(addr));
   return e + b;

@@ -91,8 +91,9 @@ __device__ __forceinline__ void fastTileLoop(const FastParams& p, const typename
   {
     const uint32_t tileX = tile % p.tilesX, tileY = tile / p.tilesX;
     const uint32_t x0 = tileX * 64u + tx * 4u, y0 = tileY * 64u + ty * 4u;
-    // Edges are multiples of 2^M >= 4: a 4x4 block is entirely inside or outside.
-    const bool active = x0 < W && y0 < H;
+    // Edges are multiples of 2^M >= 4: a 4x4 block is entirely inside or outside.  A CTA may have more than
+    // 256 threads (tailKernel): the extra ones only take part in the barriers.
+    const bool active = tid < 256u && x0 < W && y0 < H;
 
     V l1[2][2];
     V l2 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -413,6 +414,12 @@ __global__ void __launch_bounds__(256) generalKernel(const GeneralParams p)
 // needed.  Carry groups (and therefore bits) are unchanged: each step still re-reads the
 // 8-bit level written by the previous step.
 constexpr uint32_t kMaxTailSteps = 12;
+// 512 threads: the general steps stride over all of them (fewer serial rounds per tile: 2047^2 29.1 -> 27.5 us,
+// 1080p 15.3 -> 14.7 us; 1024 brings nothing more), fast tiles use the first 256.
+#ifndef NVPYR_TAIL_THREADS
+#define NVPYR_TAIL_THREADS 512
+#endif
+constexpr int kTailThreads = NVPYR_TAIL_THREADS;
 
 struct TailStep
 {
@@ -489,7 +496,7 @@ __device__ __forceinline__ void tailRunStep(const TailStep& st, TailSmem<F>& sm,
 }
 
 template <class F>
-__global__ void __launch_bounds__(256) tailKernel(const __grid_constant__ TailParams tp)
+__global__ void __launch_bounds__(kTailThreads) tailKernel(const __grid_constant__ TailParams tp)
 {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   TailSmem<F>& sm = *reinterpret_cast<TailSmem<F>*>(smemRaw);
@@ -529,7 +536,7 @@ __global__ void __launch_bounds__(256) tailKernel(const __grid_constant__ TailPa
 // runs every step of images c, c + gridDim.x, ... alone; tp.steps[].lv[].ptr hold byte offsets inside a
 // chain, bases[i] the chain of image i.  (tp.ticket is unused: nothing crosses CTAs.)
 template <class F>
-__global__ void __launch_bounds__(256) tailBatchKernel(const __grid_constant__ TailParams tp,
+__global__ void __launch_bounds__(kTailThreads) tailBatchKernel(const __grid_constant__ TailParams tp,
                                                         const unsigned char* const* bases, uint32_t count)
 {
   extern __shared__ __align__(16) unsigned char smemRaw[];
