@@ -347,53 +347,81 @@ inline void generalTiles(const LevelView* lv, uint32_t levels, uint32_t tile2, u
   *ty                  = (out.h + t - 1u) / t;
 }
 
-// The tuned sRGBA8 general kernel (nvpyr_general_srgba8.cuh): warp strips, streaming rows.
-template <int kLevels, bool kX3, bool kY3>
-nvpyrStatus launchGeneralSrgba8T(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
+// The tuned general kernel (nvpyr_general_srgba8.cuh): warp strips, streaming rows; C = texel codec.
+template <class C, int kLevels, bool kX3, bool kY3>
+nvpyrStatus launchGeneralStripT(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
 {
   GenStripParams p{};
   p.lv[0] = gp.lv[0], p.lv[1] = gp.lv[1], p.lv[2] = gp.lv[2];
   p.tables            = ctx.tables;
   p.stripsX           = std::max(1u, (gp.lv[1].w - 1u + 29u) / 30u);
-  const size_t smem   = kGenSmemBytes;
+  const size_t smem   = C::kSmemBytes;
   int          perSm  = 0;
-  nvpyrStatus  st     = blocksPerSm(reinterpret_cast<const void*>(generalSrgba8Kernel<kLevels, kX3, kY3>), smem,
-                                    kGenWarps * 32, ctx.device, &perSm);
+  nvpyrStatus  st     = blocksPerSm(reinterpret_cast<const void*>(generalStripKernel<C, kLevels, kX3, kY3>), smem,
+                                    C::kWarps * 32, ctx.device, &perSm);
   if(st != NVPYR_SUCCESS)
     return st;
   // Rows per warp task: aim at ~4 tasks per resident warp, at least 4 rows (halo/prologue overhead).
   const uint32_t rows    = kLevels == 2 ? gp.lv[2].h : gp.lv[1].h;
-  const uint64_t warps   = uint64_t(perSm) * ctx.smCount * kGenWarps;
+  const uint64_t warps   = uint64_t(perSm) * ctx.smCount * C::kWarps;
   const uint32_t wantSeg = uint32_t(std::max<uint64_t>(1, (4 * warps + p.stripsX - 1) / p.stripsX));
   p.segRows              = std::min(64u, std::max(kLevels == 2 ? 4u : 8u, (rows + wantSeg - 1) / wantSeg));
   p.segsY                = (rows + p.segRows - 1) / p.segRows;
   const uint64_t tasks   = uint64_t(p.stripsX) * p.segsY;
-  const uint64_t ctas    = std::min<uint64_t>(uint64_t(perSm) * ctx.smCount, (tasks + kGenWarps - 1) / kGenWarps);
-  NVPYR_CUDA(launchKernel(generalSrgba8Kernel<kLevels, kX3, kY3>, int(std::max<uint64_t>(1, ctas)), kGenWarps * 32, smem,
+  const uint64_t ctas    = std::min<uint64_t>(uint64_t(perSm) * ctx.smCount, (tasks + C::kWarps - 1) / C::kWarps);
+  NVPYR_CUDA(launchKernel(generalStripKernel<C, kLevels, kX3, kY3>, int(std::max<uint64_t>(1, ctas)), C::kWarps * 32, smem,
                           stream, p));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
 
-template <int kLevels>
-nvpyrStatus launchGeneralSrgba8(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
+template <class C, int kLevels>
+nvpyrStatus launchGeneralStrip(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
 {
   const bool x3 = gp.lv[0].w & 1u, y3 = gp.lv[0].h & 1u;
   if(x3)
-    return y3 ? launchGeneralSrgba8T<kLevels, true, true>(ctx, gp, stream)
-              : launchGeneralSrgba8T<kLevels, true, false>(ctx, gp, stream);
-  return y3 ? launchGeneralSrgba8T<kLevels, false, true>(ctx, gp, stream)
-            : launchGeneralSrgba8T<kLevels, false, false>(ctx, gp, stream);
+    return y3 ? launchGeneralStripT<C, kLevels, true, true>(ctx, gp, stream)
+              : launchGeneralStripT<C, kLevels, true, false>(ctx, gp, stream);
+  return y3 ? launchGeneralStripT<C, kLevels, false, true>(ctx, gp, stream)
+            : launchGeneralStripT<C, kLevels, false, false>(ctx, gp, stream);
+}
+
+// The strip kernel's codec for a functor set (void: only the functor-template kernel applies).
+template <class F>
+struct StripCodec
+{
+  using type = void;
+};
+template <>
+struct StripCodec<Srgba8>
+{
+  using type = GenCodecSrgba8;
+};
+template <>
+struct StripCodec<Rgba32f>
+{
+  using type = GenCodecRgba32f;
+};
+template <class C>
+nvpyrStatus launchGeneralTuned(const DeviceContext& ctx, const GeneralParams& p, cudaStream_t stream)
+{
+  return p.levels == 1 ? launchGeneralStrip<C, 1>(ctx, p, stream) : launchGeneralStrip<C, 2>(ctx, p, stream);
+}
+template <>
+nvpyrStatus launchGeneralTuned<void>(const DeviceContext&, const GeneralParams&, cudaStream_t)
+{
+  return NVPYR_ERROR_UNSUPPORTED;
 }
 
 template <class F>
 nvpyrStatus launchGeneral(const DeviceContext& ctx, GeneralParams p, cudaStream_t stream)
 {
   p.tables = ctx.tables;
-  // Tuned path: sRGBA8, no 1-texel-wide/high level involved (those use kernel size 1).
-  if(std::is_same<F, Srgba8>::value && !g_forceGenericFast && p.lv[0].w >= 2 && p.lv[0].h >= 2
+  // Tuned path (sRGBA8, rgba32f): no 1-texel-wide/high level involved (those use kernel size 1).
+  using Codec = typename StripCodec<F>::type;
+  if(!std::is_same<Codec, void>::value && !g_forceGenericFast && p.lv[0].w >= 2 && p.lv[0].h >= 2
      && (p.levels == 1 || (p.lv[1].w >= 2 && p.lv[1].h >= 2)))
-    return p.levels == 1 ? launchGeneralSrgba8<1>(ctx, p, stream) : launchGeneralSrgba8<2>(ctx, p, stream);
+    return launchGeneralTuned<Codec>(ctx, p, stream);
   generalTiles(p.lv, p.levels, kGenTile2, &p.tilesX, &p.tilesY);
   const size_t smem = sizeof(GeneralSmem<F>);
   int          grid = 1;

@@ -173,15 +173,49 @@ __device__ __forceinline__ V4 shflDown(V4 v, int d)
   return r;
 }
 
+// The strip kernel is written once and instantiated with a texel codec: how a raw texel is fetched, turned
+// into a float vector and stored again (the NVPRO_PYRAMID_LOAD / _STORE macros of this kernel).
+struct GenCodecSrgba8
+{
+  using Raw                              = uint32_t;
+  static constexpr uint32_t kTexelBytes  = 4;
+  static constexpr bool     kTables      = true;  // sRGB tables in shared memory (absolute addresses above)
+  static constexpr int      kWarps       = kGenWarps;
+  static constexpr size_t   kSmemBytes   = kGenSmemBytes;
+  __device__ __forceinline__ static Raw  zero() { return 0u; }
+  __device__ __forceinline__ static Raw  load(const unsigned char* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+  __device__ __forceinline__ static V4   decode(uint32_t laneAddr, Raw w) { return genDecodeTexel(laneAddr, w); }
+  __device__ __forceinline__ static void store(unsigned char* p, V4 v) { *reinterpret_cast<uint32_t*>(p) = genEncWord(toFloat4(v)); }
+};
+// rgba32f: identity load / store (nvpro_pyramid.glsl:27-49 instantiated with trivial macros), 16-byte texels.
+struct GenCodecRgba32f
+{
+  using Raw                              = float4;
+  static constexpr uint32_t kTexelBytes  = 16;
+  static constexpr bool     kTables      = false;
+  static constexpr int      kWarps       = 16;  // 512 threads, up to 128 registers: the raw prefetch slots are 4x larger
+  static constexpr size_t   kSmemBytes   = 0;
+  __device__ __forceinline__ static Raw  zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ static Raw  load(const unsigned char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ static V4   decode(uint32_t, Raw w) { return toV4(w); }
+  __device__ __forceinline__ static void store(unsigned char* p, V4 v) { *reinterpret_cast<float4*>(p) = toFloat4(v); }
+};
+
 // kLevels: 1 or 2.  kX3 / kY3: the first level uses 3 taps (odd source size) along x / y; otherwise 2.
-template <int kLevels, bool kX3, bool kY3>
-__global__ void __launch_bounds__(kGenWarps * 32, 1) generalSrgba8Kernel(const GenStripParams p)
+template <class C, int kLevels, bool kX3, bool kY3>
+__global__ void __launch_bounds__(C::kWarps * 32, 1) generalStripKernel(const GenStripParams p)
 {
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  if(uint32_t(__cvta_generic_to_shared(smemRaw)) != kGenWindowBase)
-    __trap();  // the absolute table addresses above assume this window layout: fail loudly, never silently
-  genSrgba8Init(smemRaw, p.tables);
-  __syncthreads();
+  using Raw                 = typename C::Raw;
+  constexpr uint32_t TB     = C::kTexelBytes;
+  constexpr uint32_t kWarps = uint32_t(C::kWarps);
+  if(C::kTables)
+  {
+    if(uint32_t(__cvta_generic_to_shared(smemRaw)) != kGenWindowBase)
+      __trap();  // the absolute table addresses above assume this window layout: fail loudly, never silently
+    genSrgba8Init(smemRaw, p.tables);
+    __syncthreads();
+  }
   gridDependencyWait();    // the previous kernel's levels are complete and visible
   gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
 
@@ -195,7 +229,7 @@ __global__ void __launch_bounds__(kGenWarps * 32, 1) generalSrgba8Kernel(const G
   const float rcpY2 = y3b ? genRcp(L2.h) : 0.f, rcpX2 = x3b ? genRcp(L2.w) : 0.f;
 
   const uint32_t numTasks = p.stripsX * p.segsY;
-  for(uint32_t task = blockIdx.x + gridDim.x * warp; task < numTasks; task += gridDim.x * kGenWarps)
+  for(uint32_t task = blockIdx.x + gridDim.x * warp; task < numTasks; task += gridDim.x * kWarps)
   {
     const uint32_t sx = task % p.stripsX, sy = task / p.stripsX;
     const uint32_t x1 = sx * 30u + lane;  // this lane's column of level +1
@@ -228,30 +262,30 @@ __global__ void __launch_bounds__(kGenWarps * 32, 1) generalSrgba8Kernel(const G
       yb = min(ya + p.segRows, L1.h) - 1u;
     }
 
-    const unsigned char* src = L0.ptr + size_t(2u * ya) * L0.pitch + size_t(c0) * 4u;  // source row 2*ya
-    auto                 load2 = [&](const unsigned char* row, uint32_t& a, uint32_t& b) {
-      a = srcA ? __ldg(reinterpret_cast<const uint32_t*>(row)) : 0u;
-      b = srcB ? __ldg(reinterpret_cast<const uint32_t*>(row + 4)) : 0u;
+    const unsigned char* src = L0.ptr + size_t(2u * ya) * L0.pitch + size_t(c0) * TB;  // source row 2*ya
+    auto                 load2 = [&](const unsigned char* row, Raw& a, Raw& b) {
+      a = srcA ? C::load(row) : C::zero();
+      b = srcB ? C::load(row + TB) : C::zero();
     };
 
     V4 carryA = zero, carryB = zero;  // decoded source row 2y (3-tap only)
     if(kY3)
     {
-      uint32_t a, b;
+      Raw a, b;
       load2(src, a, b);
-      carryA = genDecodeTexel(laneAddr, a);
-      carryB = genDecodeTexel(laneAddr, b);
+      carryA = C::decode(laneAddr, a);
+      carryB = C::decode(laneAddr, b);
     }
     // Raw words of the two new source rows of an output row.  Two output rows are in flight ahead of the
     // one being computed; the row loop is unrolled by two so that both slots, the vertical carry and the
     // level +2 history (q0, q1) are compile-time registers that never need to be moved.
-    struct Raw
+    struct Slot
     {
-      uint32_t a0, b0, a1, b1;
+      Raw a0, b0, a1, b1;
     };
     const unsigned char* nextRows = kY3 ? src + L0.pitch : src;  // new source rows of the next row to prefetch
     const size_t         rowStep  = 2u * size_t(L0.pitch);
-    auto                 loadRow  = [&](bool valid, Raw& r) {
+    auto                 loadRow  = [&](bool valid, Slot& r) {
       if(valid)
       {
         load2(nextRows, r.a0, r.b0);
@@ -259,24 +293,24 @@ __global__ void __launch_bounds__(kGenWarps * 32, 1) generalSrgba8Kernel(const G
       }
       nextRows += rowStep;
     };
-    Raw r0{0u, 0u, 0u, 0u}, r1{0u, 0u, 0u, 0u};
+    Slot r0{C::zero(), C::zero(), C::zero(), C::zero()}, r1{C::zero(), C::zero(), C::zero(), C::zero()};
     loadRow(true, r0);
     loadRow(ya + 1u <= yb, r1);
     V4 q0 = zero, q1 = zero;  // last level +1 values of this column
 
-    unsigned char* d1 = L1.ptr + size_t(ya) * L1.pitch + size_t(x1) * 4u;
-    unsigned char* d2 = kLevels == 2 ? L2.ptr + size_t(r2a) * L2.pitch + size_t(x2) * 4u : nullptr;
+    unsigned char* d1 = L1.ptr + size_t(ya) * L1.pitch + size_t(x1) * TB;
+    unsigned char* d2 = kLevels == 2 ? L2.ptr + size_t(r2a) * L2.pitch + size_t(x2) * TB : nullptr;
     uint32_t       y2 = r2a;  // next row of level +2 to emit
 
     // One output row of level +1 (and what it completes of level +2).  kOdd: parity of the row inside the
     // segment (segments of two-level steps start on even rows).
-    auto row = [&](uint32_t y, Raw& slot, auto parity) {
+    auto row = [&](uint32_t y, Slot& slot, auto parity) {
       constexpr bool kOdd = decltype(parity)::value;
-      const uint32_t m0a = slot.a0, m0b = slot.b0, m1a = slot.a1, m1b = slot.b1;
+      const Raw      m0a = slot.a0, m0b = slot.b0, m1a = slot.a1, m1b = slot.b1;
       loadRow(y + 2u <= yb, slot);
       // ---- vertical reduction of this lane's two source columns ----
-      const V4 vA0 = genDecodeTexel(laneAddr, m0a), vB0 = genDecodeTexel(laneAddr, m0b);
-      const V4 vA1 = genDecodeTexel(laneAddr, m1a), vB1 = genDecodeTexel(laneAddr, m1b);
+      const V4 vA0 = C::decode(laneAddr, m0a), vB0 = C::decode(laneAddr, m0b);
+      const V4 vA1 = C::decode(laneAddr, m1a), vB1 = C::decode(laneAddr, m1b);
       V4       hA, hB;
       if(kY3)
       {
@@ -301,7 +335,7 @@ __global__ void __launch_bounds__(kGenWarps * 32, 1) generalSrgba8Kernel(const G
       else
         o = genReduce2(hA, hB);
       if(out1)
-        *reinterpret_cast<uint32_t*>(d1) = genEncWord(toFloat4(o));
+        C::store(d1, o);
       d1 += L1.pitch;
 
       // ---- level +2, float32 carry ----
@@ -347,7 +381,7 @@ __global__ void __launch_bounds__(kGenWarps * 32, 1) generalSrgba8Kernel(const G
           else
             o2 = genReduce2(g, g1);
           if(out2)
-            *reinterpret_cast<uint32_t*>(d2) = genEncWord(toFloat4(o2));
+            C::store(d2, o2);
           d2 += L2.pitch;
           ++y2;
         }
