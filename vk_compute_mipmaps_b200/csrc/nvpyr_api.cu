@@ -347,6 +347,14 @@ inline void generalTiles(const LevelView* lv, uint32_t levels, uint32_t tile2, u
   *ty                  = (out.h + t - 1u) / t;
 }
 
+// Task granularity of the strip kernels: a warp task is a strip x a segment of rows.  Measured on B200
+// (tools/bench_configs.py): ONE task per resident warp with segments as short as one row of level +2 wins --
+// large levels get long segments (few prologues), small levels get enough tasks to occupy every warp
+// (4095^2 55.7 -> 50.8 us, 2052^2 22.7 -> 18.2 us against "4 tasks per warp, at least 4 rows").
+// NVPYR_GEN_TPW / NVPYR_GEN_MINSEG override for experiments.
+const uint32_t g_genTasksPerWarp = getenv("NVPYR_GEN_TPW") ? uint32_t(std::max(1, atoi(getenv("NVPYR_GEN_TPW")))) : 1u;
+const uint32_t g_genMinSegRows   = getenv("NVPYR_GEN_MINSEG") ? uint32_t(std::max(1, atoi(getenv("NVPYR_GEN_MINSEG")))) : 1u;
+
 // The tuned general kernel (nvpyr_general_srgba8.cuh): warp strips, streaming rows; C = texel codec.
 template <class C, int kLevels, bool kX3, bool kY3>
 nvpyrStatus launchGeneralStripT(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
@@ -361,11 +369,11 @@ nvpyrStatus launchGeneralStripT(const DeviceContext& ctx, const GeneralParams& g
                                     C::kWarps * 32, ctx.device, &perSm);
   if(st != NVPYR_SUCCESS)
     return st;
-  // Rows per warp task: aim at ~4 tasks per resident warp, at least 4 rows (halo/prologue overhead).
+  // Rows per warp task: see g_genTasksPerWarp.
   const uint32_t rows    = kLevels == 2 ? gp.lv[2].h : gp.lv[1].h;
   const uint64_t warps   = uint64_t(perSm) * ctx.smCount * C::kWarps;
-  const uint32_t wantSeg = uint32_t(std::max<uint64_t>(1, (4 * warps + p.stripsX - 1) / p.stripsX));
-  p.segRows              = std::min(64u, std::max(kLevels == 2 ? 4u : 8u, (rows + wantSeg - 1) / wantSeg));
+  const uint32_t wantSeg = uint32_t(std::max<uint64_t>(1, (g_genTasksPerWarp * warps + p.stripsX - 1) / p.stripsX));
+  p.segRows = std::min(64u, std::max(kLevels == 2 ? g_genMinSegRows : 2u * g_genMinSegRows, (rows + wantSeg - 1) / wantSeg));
   p.segsY                = (rows + p.segRows - 1) / p.segRows;
   const uint64_t tasks   = uint64_t(p.stripsX) * p.segsY;
   const uint64_t ctas    = std::min<uint64_t>(uint64_t(perSm) * ctx.smCount, (tasks + C::kWarps - 1) / C::kWarps);
@@ -373,6 +381,51 @@ nvpyrStatus launchGeneralStripT(const DeviceContext& ctx, const GeneralParams& g
                           stream, p));
   ++g_launchCount;
   return NVPYR_SUCCESS;
+}
+
+// NVPYR_GEN_STRIP2=1: sRGBA8 through the two-column strip kernel instead of the four-column one (A/B).
+const bool g_genStrip2 = [] {
+  const char* e = getenv("NVPYR_GEN_STRIP2");
+  return e != nullptr && e[0] == '1';
+}();
+
+// The four-columns-per-lane sRGBA8 strip kernel (generalStrip4Kernel): strips of 62 (+1 halo) level +1 columns.
+template <int kLevels, bool kX3, bool kY3>
+nvpyrStatus launchGeneralStrip4T(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
+{
+  GenStripParams p{};
+  p.lv[0] = gp.lv[0], p.lv[1] = gp.lv[1], p.lv[2] = gp.lv[2];
+  p.tables            = ctx.tables;
+  p.stripsX           = std::max(1u, (gp.lv[1].w - 1u + 61u) / 62u);
+  const size_t smem   = kGenSmemBytes;
+  int          perSm  = 0;
+  nvpyrStatus  st     = blocksPerSm(reinterpret_cast<const void*>(generalStrip4Kernel<kLevels, kX3, kY3>), smem,
+                                    kGen4Warps * 32, ctx.device, &perSm);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  // Rows per warp task: see g_genTasksPerWarp.
+  const uint32_t rows    = kLevels == 2 ? gp.lv[2].h : gp.lv[1].h;
+  const uint64_t warps   = uint64_t(perSm) * ctx.smCount * kGen4Warps;
+  const uint32_t wantSeg = uint32_t(std::max<uint64_t>(1, (g_genTasksPerWarp * warps + p.stripsX - 1) / p.stripsX));
+  p.segRows = std::min(64u, std::max(kLevels == 2 ? g_genMinSegRows : 2u * g_genMinSegRows, (rows + wantSeg - 1) / wantSeg));
+  p.segsY                = (rows + p.segRows - 1) / p.segRows;
+  const uint64_t tasks   = uint64_t(p.stripsX) * p.segsY;
+  const uint64_t ctas    = std::min<uint64_t>(uint64_t(perSm) * ctx.smCount, (tasks + kGen4Warps - 1) / kGen4Warps);
+  NVPYR_CUDA(launchKernel(generalStrip4Kernel<kLevels, kX3, kY3>, int(std::max<uint64_t>(1, ctas)), kGen4Warps * 32, smem,
+                          stream, p));
+  ++g_launchCount;
+  return NVPYR_SUCCESS;
+}
+
+template <int kLevels>
+nvpyrStatus launchGeneralStrip4(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
+{
+  const bool x3 = gp.lv[0].w & 1u, y3 = gp.lv[0].h & 1u;
+  if(x3)
+    return y3 ? launchGeneralStrip4T<kLevels, true, true>(ctx, gp, stream)
+              : launchGeneralStrip4T<kLevels, true, false>(ctx, gp, stream);
+  return y3 ? launchGeneralStrip4T<kLevels, false, true>(ctx, gp, stream)
+            : launchGeneralStrip4T<kLevels, false, false>(ctx, gp, stream);
 }
 
 template <class C, int kLevels>
@@ -405,6 +458,10 @@ struct StripCodec<Rgba32f>
 template <class C>
 nvpyrStatus launchGeneralTuned(const DeviceContext& ctx, const GeneralParams& p, cudaStream_t stream)
 {
+  // Four columns per lane (fewer instructions per texel, fewer warps) pays on large levels; small levels need
+  // the warp-level parallelism of the two-column kernel (measured cross-over around 2048^2).
+  if(std::is_same<C, GenCodecSrgba8>::value && !g_genStrip2 && uint64_t(p.lv[0].w) * p.lv[0].h >= (1ull << 22))
+    return p.levels == 1 ? launchGeneralStrip4<1>(ctx, p, stream) : launchGeneralStrip4<2>(ctx, p, stream);
   return p.levels == 1 ? launchGeneralStrip<C, 1>(ctx, p, stream) : launchGeneralStrip<C, 2>(ctx, p, stream);
 }
 template <>

@@ -61,11 +61,12 @@ struct GenStripParams
 #endif
 constexpr int kGenWarps = NVPYR_GEN_WARPS;  // one CTA of 24 warps per SM (80 registers per thread)
 
+template <int kThreads = kGenWarps * 32>
 __device__ __forceinline__ void genSrgba8Init(unsigned char* smemRaw, const DeviceTables* t)
 {
   float*    decode = reinterpret_cast<float*>(smemRaw + (kGenDecodeAddr - kGenWindowBase));
   uint32_t* encode = reinterpret_cast<uint32_t*>(smemRaw + (kGenEncodeAddr - kGenWindowBase));
-  for(uint32_t i = threadIdx.x; i < 512u; i += kGenWarps * 32)
+  for(uint32_t i = threadIdx.x; i < 512u; i += kThreads)
   {
     const uint32_t code = i >> 1, half = i & 1u;
     const float    v    = __ldg(&t->decode[code]);
@@ -73,8 +74,8 @@ __device__ __forceinline__ void genSrgba8Init(unsigned char* smemRaw, const Devi
     const float4   v4   = make_float4(v, v, v, v);
     d[0] = v4, d[1] = v4, d[2] = v4, d[3] = v4;
   }
-  copyTableWide<kGenWarps * 32>(reinterpret_cast<uint4*>(encode), reinterpret_cast<const uint4*>(t->encode),
-                                kEncEntriesPadded / 4);
+  copyTableWide<kThreads>(reinterpret_cast<uint4*>(encode), reinterpret_cast<const uint4*>(t->encode),
+                          kEncEntriesPadded / 4);
 }
 
 // linearFromSrgb of byte kByte (0..2) of a packed texel: PRMT builds the absolute shared address
@@ -382,6 +383,224 @@ __global__ void __launch_bounds__(C::kWarps * 32, 1) generalStripKernel(const Ge
             o2 = genReduce2(g, g1);
           if(out2)
             C::store(d2, o2);
+          d2 += L2.pitch;
+          ++y2;
+        }
+      }
+    };
+    uint32_t y = ya;
+    for(; y < yb; y += 2u)
+    {
+      row(y, r0, std::false_type{});
+      row(y + 1u, r1, std::true_type{});
+    }
+    if(y == yb)
+      row(y, r0, std::false_type{});
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generalStrip4Kernel: the sRGBA8 strip kernel with FOUR source columns per lane.
+//
+// The 2-column strip kernel above is instruction-issue bound: per source texel it spends ~47 warp
+// instructions, more than half of them per-row overhead (row weights, pointer updates, control flow, the
+// horizontal reduction and both encodes) that does not depend on how many columns a lane owns, and its
+// level +2 encode runs on half the lanes.  Here a lane owns source columns c0..c0+3 = level +1 columns
+// xa, xa+1 = ONE level +2 column; a strip is 63 columns of level +1 (the last one is the halo the next
+// strip recomputes, strips advance by 62) and 31 columns of level +2.  Same float32 expression tree per
+// output texel (vertical reduction of each source column, then horizontal; weights (n - i, n, 1 - w0 - w1)
+// / (2n + 1); float32 carry to level +2), hence the same bits, with ~half the instructions per texel.
+constexpr int kGen4Warps = 16;  // 512 threads per CTA, one CTA per SM, up to 128 registers per thread
+
+template <int kLevels, bool kX3, bool kY3>
+__global__ void __launch_bounds__(kGen4Warps * 32, 1) generalStrip4Kernel(const GenStripParams p)
+{
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  if(uint32_t(__cvta_generic_to_shared(smemRaw)) != kGenWindowBase)
+    __trap();  // the absolute table addresses assume this window layout: fail loudly, never silently
+  genSrgba8Init<kGen4Warps * 32>(smemRaw, p.tables);
+  __syncthreads();
+  gridDependencyWait();    // the previous kernel's levels are complete and visible
+  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
+
+  const uint32_t  lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, laneAddr = kGenDecodeAddr | (lane * 4u);
+  const LevelView L0 = p.lv[0], L1 = p.lv[1], L2 = p.lv[2];
+  const float     fH1 = float(L1.h), fW1 = float(L1.w);
+  const float     rcpY1 = kY3 ? genRcp(L1.h) : 0.f, rcpX1 = kX3 ? genRcp(L1.w) : 0.f;
+  // second level (uniform run-time branches)
+  const bool  x3b = kLevels == 2 && (L1.w & 1u), y3b = kLevels == 2 && (L1.h & 1u);
+  const float fH2 = kLevels == 2 ? float(L2.h) : 0.f, fW2 = kLevels == 2 ? float(L2.w) : 0.f;
+  const float rcpY2 = y3b ? genRcp(L2.h) : 0.f, rcpX2 = x3b ? genRcp(L2.w) : 0.f;
+  const V4    zero = toV4(make_float4(0.f, 0.f, 0.f, 0.f));
+
+  const uint32_t numTasks = p.stripsX * p.segsY;
+  for(uint32_t task = blockIdx.x + gridDim.x * warp; task < numTasks; task += gridDim.x * kGen4Warps)
+  {
+    const uint32_t sx = task % p.stripsX, sy = task / p.stripsX;
+    const uint32_t xa = sx * 62u + 2u * lane;  // this lane's level +1 columns: xa, xa + 1
+    const uint32_t c0 = 2u * xa;               // its source columns: c0 .. c0 + 3
+    const bool     src0 = c0 < L0.w, src1 = c0 + 1u < L0.w, src2 = c0 + 2u < L0.w, src3 = c0 + 3u < L0.w;
+    const bool     out1a = xa < L1.w, out1b = xa + 1u < L1.w && lane < 31u;  // lane 31 has no right-hand halo
+    Taps           txa{zero.rg, zero.rg, zero.rg}, txb{zero.rg, zero.rg, zero.rg};
+    if(kX3)
+    {
+      txa = genTaps(rcpX1, fW1, xa);
+      txb = genTaps(rcpX1, fW1, xa + 1u);
+    }
+    const uint32_t x2   = sx * 31u + lane;  // its level +2 column
+    const bool     out2 = kLevels == 2 && lane < 31u && x2 < L2.w;
+    Taps           tx2{zero.rg, zero.rg, zero.rg};
+    if(kLevels == 2 && x3b)
+      tx2 = genTaps(rcpX2, fW2, x2);
+
+    // rows of level +1 handled by this task: [ya, yb]
+    uint32_t ya, yb, r2a = 0;
+    if(kLevels == 2)
+    {
+      r2a                = sy * p.segRows;
+      const uint32_t r2b = min(r2a + p.segRows, L2.h);
+      ya                 = 2u * r2a;
+      yb                 = min(y3b ? 2u * r2b : 2u * r2b - 1u, L1.h - 1u);
+    }
+    else
+    {
+      ya = sy * p.segRows;
+      yb = min(ya + p.segRows, L1.h) - 1u;
+    }
+
+    struct Row4
+    {
+      uint32_t w0, w1, w2, w3;
+    };
+    const unsigned char* src   = L0.ptr + size_t(2u * ya) * L0.pitch + size_t(c0) * 4u;  // source row 2*ya
+    auto                 load4 = [&](const unsigned char* row, Row4& r) {
+      r.w0 = src0 ? __ldg(reinterpret_cast<const uint32_t*>(row)) : 0u;
+      r.w1 = src1 ? __ldg(reinterpret_cast<const uint32_t*>(row + 4)) : 0u;
+      r.w2 = src2 ? __ldg(reinterpret_cast<const uint32_t*>(row + 8)) : 0u;
+      r.w3 = src3 ? __ldg(reinterpret_cast<const uint32_t*>(row + 12)) : 0u;
+    };
+
+    V4 carry0 = zero, carry1 = zero, carry2 = zero, carry3 = zero;  // decoded source row 2y (3-tap only)
+    if(kY3)
+    {
+      Row4 r;
+      load4(src, r);
+      carry0 = genDecodeTexel(laneAddr, r.w0), carry1 = genDecodeTexel(laneAddr, r.w1);
+      carry2 = genDecodeTexel(laneAddr, r.w2), carry3 = genDecodeTexel(laneAddr, r.w3);
+    }
+    struct Slot
+    {
+      Row4 a, b;  // the two new source rows of an output row
+    };
+    const unsigned char* nextRows = kY3 ? src + L0.pitch : src;
+    const size_t         rowStep  = 2u * size_t(L0.pitch);
+    auto                 loadRow  = [&](bool valid, Slot& s) {
+      if(valid)
+      {
+        load4(nextRows, s.a);
+        load4(nextRows + L0.pitch, s.b);
+      }
+      nextRows += rowStep;
+    };
+    Slot r0{{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}}, r1{{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
+    loadRow(true, r0);
+    loadRow(ya + 1u <= yb, r1);
+    V4 q0a = zero, q1a = zero, q0b = zero, q1b = zero;  // last level +1 values of the lane's two columns
+
+    unsigned char* d1 = L1.ptr + size_t(ya) * L1.pitch + size_t(xa) * 4u;
+    unsigned char* d2 = kLevels == 2 ? L2.ptr + size_t(r2a) * L2.pitch + size_t(x2) * 4u : nullptr;
+    uint32_t       y2 = r2a;  // next row of level +2 to emit
+
+    auto row = [&](uint32_t y, Slot& slot, auto parity) {
+      constexpr bool kOdd = decltype(parity)::value;
+      const Slot     m    = slot;
+      loadRow(y + 2u <= yb, slot);
+      // ---- vertical reduction of the lane's four source columns ----
+      const V4 a0 = genDecodeTexel(laneAddr, m.a.w0), a1 = genDecodeTexel(laneAddr, m.a.w1);
+      const V4 a2 = genDecodeTexel(laneAddr, m.a.w2), a3 = genDecodeTexel(laneAddr, m.a.w3);
+      const V4 b0 = genDecodeTexel(laneAddr, m.b.w0), b1 = genDecodeTexel(laneAddr, m.b.w1);
+      const V4 b2 = genDecodeTexel(laneAddr, m.b.w2), b3 = genDecodeTexel(laneAddr, m.b.w3);
+      V4       h0, h1, h2, h3;
+      if(kY3)
+      {
+        const Taps ty = genTaps(rcpY1, fH1, y);
+        h0            = genReduce3(ty.w0, carry0, ty.w1, a0, ty.w2, b0);
+        h1            = genReduce3(ty.w0, carry1, ty.w1, a1, ty.w2, b1);
+        h2            = genReduce3(ty.w0, carry2, ty.w1, a2, ty.w2, b2);
+        h3            = genReduce3(ty.w0, carry3, ty.w1, a3, ty.w2, b3);
+        carry0 = b0, carry1 = b1, carry2 = b2, carry3 = b3;
+      }
+      else
+      {
+        h0 = genReduce2(a0, b0), h1 = genReduce2(a1, b1);
+        h2 = genReduce2(a2, b2), h3 = genReduce2(a3, b3);
+      }
+      // ---- horizontal reduction: level +1 columns xa (source c0, c0+1[, c0+2]) and xa+1 (c0+2, c0+3[, c0+4]) ----
+      V4 oa, ob;
+      if(kX3)
+      {
+        const V4 h4 = shflDown(h0, 1);  // source column c0 + 4 = first column of lane + 1
+        oa          = genReduce3(txa.w0, h0, txa.w1, h1, txa.w2, h2);
+        ob          = genReduce3(txb.w0, h2, txb.w1, h3, txb.w2, h4);
+      }
+      else
+      {
+        oa = genReduce2(h0, h1);
+        ob = genReduce2(h2, h3);
+      }
+      const uint32_t wa = genEncWord(toFloat4(oa)), wb = genEncWord(toFloat4(ob));
+      if(out1a)
+        *reinterpret_cast<uint32_t*>(d1) = wa;
+      if(out1b)
+        *reinterpret_cast<uint32_t*>(d1 + 4) = wb;
+      d1 += L1.pitch;
+
+      // ---- level +2, float32 carry ----
+      if(kLevels == 2)
+      {
+        V4   ga = zero, gb = zero;
+        bool emit = false;
+        if(y3b)
+        {
+          // rows 2 y2, 2 y2 + 1, 2 y2 + 2: emit when the third arrives (even row, not the segment's first)
+          if(!kOdd)
+          {
+            if(y != ya)
+            {
+              const Taps ty = genTaps(rcpY2, fH2, y2);
+              ga            = genReduce3(ty.w0, q0a, ty.w1, q1a, ty.w2, oa);
+              gb            = genReduce3(ty.w0, q0b, ty.w1, q1b, ty.w2, ob);
+              emit          = true;
+            }
+            q0a = oa, q0b = ob;
+          }
+          else
+            q1a = oa, q1b = ob;
+        }
+        else
+        {
+          if(kOdd)
+          {
+            ga   = genReduce2(q0a, oa);
+            gb   = genReduce2(q0b, ob);
+            emit = true;
+          }
+          else
+            q0a = oa, q0b = ob;
+        }
+        if(emit)  // warp-uniform
+        {
+          V4 o2;
+          if(x3b)
+          {
+            const V4 gc = shflDown(ga, 1);  // level +1 column xa + 2 = first column of lane + 1
+            o2          = genReduce3(tx2.w0, ga, tx2.w1, gb, tx2.w2, gc);
+          }
+          else
+            o2 = genReduce2(ga, gb);
+          const uint32_t w2 = genEncWord(toFloat4(o2));
+          if(out2)
+            *reinterpret_cast<uint32_t*>(d2) = w2;
           d2 += L2.pitch;
           ++y2;
         }
