@@ -548,7 +548,34 @@ def test_negative_control_is_detected(nv, cuda, oracle):
     assert oracle.compare(full, want, w, h).worst > 100
 
 
-@pytest.mark.parametrize("size", [(4096, 4096), (4095, 4095), (2047, 2047)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_four_column_strip_kernel_on_every_size(nv, cuda, oracle):
+    """generalStrip4Kernel normally takes only large levels; NVPYR_GEN_STRIP4_MIN_TEXELS=0 (with the tail fusion
+    off so that small levels reach the stand-alone kernels) runs all its variants -- 1 / 2 levels, 2 or 3 taps
+    per axis on either level, ragged strips and segments -- on sizes the oracle handles quickly."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import vk_compute_mipmaps_b200 as nv, _oracle\n"
+        "o = _oracle.load_oracle()\n"
+        "sizes = [(63, 63), (100, 37), (255, 255), (511, 300), (254, 254), (17, 513), (129, 129), (6, 10), (1023, 511),\n"
+        "         (1022, 766), (777, 1031), (1200, 900), (125, 3), (126, 126), (127, 2), (249, 251), (250, 250), (2047, 700)]\n"
+        "for (w, h) in sizes:\n"
+        "    for fg in (True, False):\n"
+        "        l0 = _oracle.random_level0(w, h, w * 7 + h)\n"
+        "        buf = torch.zeros(nv.chain_bytes(w, h), dtype=torch.uint8, device='cuda')\n"
+        "        buf[:4 * w * h] = torch.from_numpy(l0).cuda()\n"
+        "        nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(fast_pipeline=not fg), w, h, image=buf)\n"
+        "        torch.cuda.synchronize()\n"
+        "        assert (buf.cpu().numpy() == o.shader_chain(l0, w, h, force_general=fg)[0]).all(), (w, h, fg)\n"
+        "print('strip4 ok')\n") % (_oracle.ROOT, os.path.join(_oracle.ROOT, "tests"))
+    env = dict(os.environ, NVPYR_GEN_STRIP4_MIN_TEXELS="0", NVPYR_TAIL_MAX_TEXELS="0")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "strip4 ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("size", [(4096, 4096), (4095, 4095), (2047, 2047), (4094, 2049)], ids=lambda s: f"{s[0]}x{s[1]}")
 def test_baseline_config_sizes_bit_exact(nv, cuda, oracle, size):
     """BASELINE configs 1 and 2 at full size (oracle runs ~1 s)."""
     w, h = size

@@ -389,6 +389,13 @@ const bool g_genStrip2 = [] {
   return e != nullptr && e[0] == '1';
 }();
 
+// NVPYR_GEN_STRIP4_MIN_TEXELS: smallest input level (texels) that takes the four-column kernel (tests use 0 to
+// run it on every size).
+const uint64_t g_genStrip4MinTexels = [] {
+  const char* e = getenv("NVPYR_GEN_STRIP4_MIN_TEXELS");
+  return e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : 1ull << 22;
+}();
+
 // The four-columns-per-lane sRGBA8 strip kernel (generalStrip4Kernel): strips of 62 (+1 halo) level +1 columns.
 template <int kLevels, bool kX3, bool kY3>
 nvpyrStatus launchGeneralStrip4T(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
@@ -460,7 +467,7 @@ nvpyrStatus launchGeneralTuned(const DeviceContext& ctx, const GeneralParams& p,
 {
   // Four columns per lane (fewer instructions per texel, fewer warps) pays on large levels; small levels need
   // the warp-level parallelism of the two-column kernel (measured cross-over around 2048^2).
-  if(std::is_same<C, GenCodecSrgba8>::value && !g_genStrip2 && uint64_t(p.lv[0].w) * p.lv[0].h >= (1ull << 22))
+  if(std::is_same<C, GenCodecSrgba8>::value && !g_genStrip2 && uint64_t(p.lv[0].w) * p.lv[0].h >= g_genStrip4MinTexels)
     return p.levels == 1 ? launchGeneralStrip4<1>(ctx, p, stream) : launchGeneralStrip4<2>(ctx, p, stream);
   return p.levels == 1 ? launchGeneralStrip<C, 1>(ctx, p, stream) : launchGeneralStrip<C, 2>(ctx, p, stream);
 }
