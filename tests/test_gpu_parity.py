@@ -548,6 +548,20 @@ def test_negative_control_is_detected(nv, cuda, oracle):
     assert oracle.compare(full, want, w, h).worst > 100
 
 
+@pytest.mark.parametrize("size", [(1024, 1024), (2048, 1024), (512, 2048), (1024, 768), (1040, 528), (1056, 1056)])
+def test_slab_tasks_of_the_fast_kernel(nv, cuda, oracle, size):
+    """Images with few 64 x 2^M tiles for the resident warps run the tuned fast kernel in slab-task mode (a warp
+    takes one 64x8 slab; the last warp to arrive at a tile finishes levels +4..+M): M = 6, 5 (1056 = 32 * 33)
+    and 4 (1040 = 16 * 65, 528 = 16 * 33); same bits as the tile mode (NVPYR_NO_SLAB_TASKS=1 covers that one in
+    every other test of sizes >= 4096 tiles)."""
+    w, h = size
+    l0 = _oracle.random_level0(w, h, 55)
+    want, _ = oracle.shader_chain(l0, w, h)
+    for _ in range(3):  # arrival order varies from run to run
+        got = gpu_chain(nv, cuda, l0, w, h)
+        assert_same(got, want, w, h, oracle, "slab tasks")
+
+
 def test_four_column_strip_kernel_on_every_size(nv, cuda, oracle):
     """generalStrip4Kernel normally takes only large levels; NVPYR_GEN_STRIP4_MIN_TEXELS=0 (with the tail fusion
     off so that small levels reach the stand-alone kernels) runs all its variants -- 1 / 2 levels, 2 or 3 taps

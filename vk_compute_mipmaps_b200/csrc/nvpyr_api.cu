@@ -268,16 +268,22 @@ bool tunedFastOk(const LevelView* lv)
   return std::is_same<F, Srgba8>::value && !g_forceGenericFast && fastVectorOk<F>(lv);
 }
 
-template <int M, bool kBatch, bool kPremul>
+// NVPYR_NO_SLAB_TASKS=1: always one warp per tile in the tuned fast kernel (A/B timing).
+const bool g_noSlabTasks = [] {
+  const char* e = getenv("NVPYR_NO_SLAB_TASKS");
+  return e != nullptr && e[0] == '1';
+}();
+
+template <int M, bool kBatch, bool kPremul, bool kSlabTasks>
 nvpyrStatus launchFastSrgba8K(const DeviceContext& ctx, const FastParams& p, const FastBatch& b, uint64_t work,
                               cudaStream_t stream)
 {
   const size_t smem = sizeof(Srgba8FastSmem);
   int          grid = 1;
-  nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M, kBatch, kPremul>, smem, ctx, work, &grid, kFastWarps * 32);
+  nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M, kBatch, kPremul, kSlabTasks>, smem, ctx, work, &grid, kFastWarps * 32);
   if(st != NVPYR_SUCCESS)
     return st;
-  NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, kBatch, kPremul>, grid, kFastWarps * 32, smem, stream, p, b));
+  NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, kBatch, kPremul, kSlabTasks>, grid, kFastWarps * 32, smem, stream, p, b));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
@@ -296,13 +302,21 @@ nvpyrStatus launchFastSrgba8T(const DeviceContext& ctx, FastParams p, cudaStream
   if(work > 0xFFFFFFFFull)
     return NVPYR_ERROR_INVALID_VALUE;
   if(batch)
-    return premul ? launchFastSrgba8K<M, true, true>(ctx, p, b, work, stream)
-                  : launchFastSrgba8K<M, true, false>(ctx, p, b, work, stream);
-  return premul ? launchFastSrgba8K<M, false, true>(ctx, p, b, work, stream)
-                : launchFastSrgba8K<M, false, false>(ctx, p, b, work, stream);
+    return premul ? launchFastSrgba8K<M, true, true, false>(ctx, p, b, work, stream)
+                  : launchFastSrgba8K<M, true, false, false>(ctx, p, b, work, stream);
+  // Few tiles for the resident warps (images up to ~2048^2): warps take single slabs, not whole tiles.  With a
+  // tile or more per warp the tile mode wins (the slab-to-slab prefetch stays inside one warp): measured
+  // 1024^2 9.7 -> 5.7 us, 2048^2 14.2 -> 12.8 us, but 2560x1440 16.1 -> 16.5 us and 4096^2 26.6 -> 28.4 us.
+  constexpr bool kCanSlab = M >= 4;
+  const uint64_t ctas     = std::min<uint64_t>(work, uint64_t(ctx.smCount));
+  if(kCanSlab && !g_noSlabTasks && (work + ctas - 1) / ctas <= uint64_t(kFastWarps)
+     && 4u * work <= uint64_t(ctx.smCount) * kFastWarps)
+    return premul ? launchFastSrgba8K<M, false, true, kCanSlab>(ctx, p, b, work, stream)
+                  : launchFastSrgba8K<M, false, false, kCanSlab>(ctx, p, b, work, stream);
+  return premul ? launchFastSrgba8K<M, false, true, false>(ctx, p, b, work, stream)
+                : launchFastSrgba8K<M, false, false, false>(ctx, p, b, work, stream);
 }
 
-// premul (sRGBA8 tuned kernel only, see fusedPremultiplyOk): premultiply level 0 on the fly.
 template <class F>
 nvpyrStatus launchFast(const DeviceContext& ctx, FastParams p, uint32_t M, cudaStream_t stream, bool premul = false)
 {

@@ -338,12 +338,23 @@ struct FastBatch
 // kPremul: level 0 holds straight (un-premultiplied) alpha; it is premultiplied on the fly, written back in
 // place (only 4x4 blocks that changed) and the chain is generated from the premultiplied codes -- exactly what
 // premultiplyKernel followed by this kernel produce, minus one full read + write pass over level 0.
-template <int M, bool kBatch, bool kPremul>
+// kSlabTasks (M >= 4, images of up to 32 tiles per CTA, i.e. up to ~4096^2): the unit of work of a warp is ONE
+// 64x8 slab instead of a whole 64 x 2^M tile.  A CTA owns tiles c, c + G, ... (local index j < 32); its warps
+// take the slabs of those tiles round-robin, drop their row of level +3 sums into the tile's stash (sm.l3[j])
+// and the warp that arrives last at the tile (shared-memory counter, nobody waits) finishes levels +4..+M.
+// A 1024^2 image has 256 tiles for 4736 resident warps: in tile mode 5 % of the warps walk 8 slabs each, in
+// slab mode 43 % walk one.  Same expression trees, same bits.
+template <int M, bool kBatch, bool kPremul, bool kSlabTasks>
 __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Kernel(const FastParams p, const FastBatch batch)
 {
   static_assert(M >= 2 && M <= 6, "2..6 levels");
+  static_assert(!kSlabTasks || (M >= 4 && !kBatch), "slab tasks: single image, levels beyond +3");
+  constexpr uint32_t kTileH = M >= 3 ? (1u << M) : 8u, kSlabs = kTileH / 8u;
   extern __shared__ __align__(16) unsigned char smemRaw[];
+  __shared__ uint32_t tileArrivals[kFastWarps];  // slab tasks: slabs of local tile j that have arrived
   Srgba8FastSmem& sm = *reinterpret_cast<Srgba8FastSmem*>(smemRaw);
+  if(kSlabTasks && threadIdx.x < kFastWarps)
+    tileArrivals[threadIdx.x] = 0u;
   srgba8FastInit(sm, p.tables);
   __syncthreads();  // the only CTA-wide barrier
   gridDependencyWait();    // the previous kernel's levels are complete and visible
@@ -376,7 +387,9 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
 
   // Tiles are dealt CTA-major so that mid-size images still spread over every SM.
   const uint32_t tileStep = gridDim.x * kFastWarps;
-  uint32_t       tile     = blockIdx.x + gridDim.x * warp;
+  uint32_t       task     = warp;  // slab tasks: local task index = local tile * kSlabs + slab
+  uint32_t       tile     = kSlabTasks ? blockIdx.x + gridDim.x * (task / kSlabs) : blockIdx.x + gridDim.x * warp;
+  uint32_t       slab0    = kSlabTasks ? task % kSlabs : 0u;  // first slab of this warp's current unit of work
 
   // Per-lane cursor of the slab being prefetched: source pointer + "inside the image".
   struct Cursor
@@ -384,10 +397,9 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
     const unsigned char* src;
     bool                 active;
   };
-  constexpr uint32_t kTileH = M >= 3 ? (1u << M) : 8u, kSlabs = kTileH / 8u;
-  auto tileCursor = [&](uint32_t t) {
+  auto tileCursor = [&](uint32_t t, uint32_t firstSlab) {
     const uint32_t tt = kBatch ? t % batch.tilesPerImage : t;  // tile inside its image
-    const uint32_t x0 = (tt % p.tilesX) * 64u + tx * 4u, y0 = (tt / p.tilesX) * kTileH + ty * 4u;
+    const uint32_t x0 = (tt % p.tilesX) * 64u + tx * 4u, y0 = (tt / p.tilesX) * kTileH + firstSlab * 8u + ty * 4u;
     Cursor         c;
     c.active = t < numTiles && x0 < W && y0 < H;
     c.src    = (kBatch && t >= numTiles ? nullptr : levelPtr(0, t)) + size_t(y0) * pitch0 + size_t(x0) * 4u;
@@ -402,23 +414,30 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
         row[i] = __ldg(reinterpret_cast<const uint4*>(c.src + size_t(i) * pitch0));
     }
   };
-  Cursor nxt = tileCursor(tile);
+  Cursor nxt = tileCursor(tile, slab0);
   if(kFastPrefetch)
     loadRows(nxt);
 
-  for(; tile < numTiles; tile += tileStep)
+  while(tile < numTiles)
   {
+    // this unit of work, and the one after it (for the prefetch)
+    const uint32_t nextTask  = task + kFastWarps;
+    const uint32_t nextTileI = kSlabTasks ? blockIdx.x + gridDim.x * (nextTask / kSlabs) : tile + tileStep;
+    const uint32_t nextSlab0 = kSlabTasks ? nextTask % kSlabs : 0u;
+    if(kSlabTasks)
+      myL3 = &sm.l3[task / kSlabs][0][0][0];  // the tile's stash (local tile index < kFastWarps, see the launch code)
     const uint32_t tileInImage = kBatch ? tile % batch.tilesPerImage : tile;
     const uint32_t tileX = tileInImage % p.tilesX, tileY = tileInImage / p.tilesX;
     const uint32_t x0 = tileX * 64u + tx * 4u;
-    uint32_t       y0 = tileY * kTileH + ty * 4u;
+    uint32_t       y0 = tileY * kTileH + slab0 * 8u + ty * 4u;
     // Output cursors of this lane (advance by one slab = 8 input rows per iteration).
     unsigned char* d1 = levelPtr(1, tile) + size_t(y0 >> 1) * pitch1 + size_t(x0 >> 1) * 4u;
     unsigned char* d2 = levelPtr(2, tile) + size_t(y0 >> 2) * pitch2 + size_t(x0 >> 2) * 4u;
     unsigned char* d3 = M >= 3 ? levelPtr(3, tile) + size_t(y0 >> 3) * p.lv[3].pitch + size_t(x0 >> 3) * 4u : nullptr;
-    const Cursor   nextTile = tileCursor(tile + tileStep);
+    const Cursor   nextTile = tileCursor(nextTileI, nextSlab0);
+    const uint32_t slabEnd  = kSlabTasks ? slab0 + 1u : kSlabs;
 #pragma unroll kFastSlabUnroll
-    for(uint32_t slab = 0; slab < kSlabs; ++slab, y0 += 8u, d1 += 4u * pitch1, d2 += 2u * pitch2)
+    for(uint32_t slab = slab0; slab < slabEnd; ++slab, y0 += 8u, d1 += 4u * pitch1, d2 += 2u * pitch2)
     {
       // Edges are multiples of 2^M >= 4: a 4x4 block is entirely inside or outside.
       const bool active = nxt.active;
@@ -427,7 +446,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
       uint4 c0 = row[0], c1 = row[1], c2 = row[2], c3 = row[3];
       unsigned char* const curSrc = const_cast<unsigned char*>(nxt.src);
       // the next slab (of this tile, or the first one of this warp's next tile)
-      if(slab + 1u < kSlabs)
+      if(!kSlabTasks && slab + 1u < kSlabs)
       {
         nxt.src += 8u * pitch0;
         nxt.active = x0 < W && y0 + 8u < H;
@@ -513,7 +532,21 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
       }
     }
 
-    if(M >= 4)
+    bool finishTile = M >= 4;
+    if(M >= 4 && kSlabTasks)
+    {
+      // Publish this slab's row of level +3 sums; the warp that completes the tile finishes it.
+      __syncwarp();
+      __threadfence_block();
+      uint32_t arrived = 0;
+      if(lane == 0u)
+        arrived = atomicAdd(&tileArrivals[task / kSlabs], 1u);
+      arrived    = __shfl_sync(0xffffffffu, arrived, 0);
+      finishTile = arrived == kSlabs - 1u;
+      if(finishTile)
+        __threadfence_block();
+    }
+    if(finishTile)
     {
       __syncwarp();
       // 16 lanes <-> 4 x 4 texels of level +4; +5 and +6 with butterflies.
@@ -549,6 +582,15 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
       }
       __syncwarp();  // the warp's level +3 tile is free again
     }
+    // next unit of work
+    if(kSlabTasks)
+    {
+      task  = nextTask;
+      tile  = nextTileI;
+      slab0 = nextSlab0;
+    }
+    else
+      tile += tileStep;
   }
 }
 
