@@ -13,6 +13,6 @@ for inp in julia random; do
   ncu --set full --import-source on --clock-control none -k regex:fastSrgba8Kernel --launch-skip 3 -c 1 -o $O/fast6_$inp \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-inputs --no-batch --input $inp > $O/ncu_fast6_$inp.log 2>&1
 done
-ncu --set full --import-source on --clock-control none -k regex:generalSrgba8Kernel -c 1 -o $O/gen4095 \
+ncu --set full --import-source on --clock-control none -k regex:generalStrip4Kernel -c 1 -o $O/gen4095 \
     python tools/launch_probe.py --only 4095.jpg --reps 1 > $O/ncu_gen.log 2>&1
 ls -la $O
