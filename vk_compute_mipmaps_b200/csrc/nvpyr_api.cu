@@ -80,20 +80,19 @@ float bitsToFloat(uint32_t b)
   return f;
 }
 
-// Builds the encode bucket table of nvpyr_functors.cuh from the 255 pinned thresholds.
-// Returns false if a bucket would hold two thresholds (cannot happen with the pinned data;
+// Builds one encode bucket table of nvpyr_functors.cuh (keys = float bits >> shift) from the 255 pinned
+// thresholds.  Returns false if a bucket would hold two thresholds (cannot happen with the pinned data;
 // checked anyway so a regenerated table cannot silently break the encode).
-bool buildHostTables(DeviceTables& t)
+bool buildEncodeTable(uint32_t* out, uint32_t shift, uint32_t entriesPadded)
 {
-  for(int c = 0; c < 256; ++c)
-    t.decode[c] = bitsToFloat(NVPYR_SRGB_DECODE_BITS[c]);
   const uint32_t* thr = NVPYR_SRGB_ENCODE_THRESHOLD_BITS;  // thr[c-1] = first bits with code >= c
   if(thr[0] <= kEncMinBits || thr[254] > kEncMaxBits)
     return false;
-  uint32_t code = 0;  // number of thresholds <= bucket start
-  for(uint32_t key = kEncMinKey; key <= kEncMaxKey; ++key)
+  const uint32_t minKey = kEncMinBits >> shift, maxKey = kEncMaxBits >> shift;
+  uint32_t       code   = 0;  // number of thresholds <= bucket start
+  for(uint32_t key = minKey; key <= maxKey; ++key)
   {
-    const uint32_t lo = key << kEncShift, hi = lo + (1u << kEncShift);  // [lo, hi)
+    const uint32_t lo = key << shift, hi = lo + (1u << shift);  // [lo, hi)
     while(code < 255 && thr[code] <= lo)
       ++code;
     uint32_t entry = code << 16;
@@ -103,11 +102,20 @@ bool buildHostTables(DeviceTables& t)
         return false;
       entry += 0x10000u - (thr[code] - lo);
     }
-    t.encode[key - kEncMinKey] = entry - lo;  // pre-biased: kernel adds the full bit pattern
+    out[key - minKey] = entry - lo;  // pre-biased: kernel adds the full bit pattern
   }
-  for(uint32_t i = kEncEntries; i < kEncEntriesPadded; ++i)
-    t.encode[i] = 0;
+  for(uint32_t i = maxKey - minKey + 1; i < entriesPadded; ++i)
+    out[i] = 0;
   return true;
+}
+
+bool buildHostTables(DeviceTables& t)
+{
+  static_assert(kEncShift <= 16 && kFastEncShift <= 16, "entry + bits must not carry past the code byte");
+  for(int c = 0; c < 256; ++c)
+    t.decode[c] = bitsToFloat(NVPYR_SRGB_DECODE_BITS[c]);
+  return buildEncodeTable(t.encode, kEncShift, kEncEntriesPadded)
+         && buildEncodeTable(t.encodeFast, kFastEncShift, kFastEncEntriesPadded);
 }
 
 // ------------------------------------------------------------ device context

@@ -14,9 +14,10 @@
 //    S = (a+b)+(c+d) = 4^k * value, and the decode table is pre-scaled by 2^-100.  Scaling
 //    by a power of two commutes with rounding (nothing here is subnormal or overflows), so
 //    every deeper sum and every stored code is bit-identical; the FMULs disappear and the
-//    encode needs no clamp: the bucket table is extended downwards to the smallest non-zero
-//    sum, and an exact zero (bit pattern 0) indexes a dedicated word placed in the unused
-//    half of a decode-table row.  Alpha uses the exact constant 255 / 4^k.
+//    encode of levels +1 and +2 (15 of every 16 encodes) needs no clamp: the bucket table is
+//    extended downwards to their smallest non-zero sum, and an exact zero (bit pattern 0)
+//    indexes a dedicated word placed in the unused half of a decode-table row.  Deeper
+//    levels clamp with one FMNMX.  Alpha uses the exact constant 255 / 4^k.
 //  * level +3 is a "transpose-reduce": in two shuffle steps the four threads of a 2x2 block
 //    end up holding ONE channel each of the common result (3 SHFL + 3 FADD per thread
 //    instead of 12 + 12), encode it in parallel and gather the four bytes with two PRMTs.
@@ -30,11 +31,14 @@
 //  * the next slab's four 16-byte rows are prefetched into registers before the current
 //    slab is processed.
 //
-//  * the encode bucket table is stored 4-way bank-partitioned (entry k occupies 16 bytes, lane l
-//    reads copy l & 3): lanes with different l & 3 can never collide on a bank.  Measured on
-//    16384^2: 328 -> 284 us on uniform-random input, 317 -> 252 us on a smooth gradient.
+//  * the encode bucket table (bucket = exponent + 7 mantissa bits) is stored 8-way bank-partitioned
+//    (entry k occupies 32 bytes, lane l reads copy l & 7): lanes with different l & 7 can never
+//    collide on a bank.  Measured on 16384^2, uniform-random input: 328 us un-replicated, 284 us
+//    4-way (8 mantissa bits), 273 us 8-way.
 //
-// CTA = 1024 threads = 32 warps sharing the tables (197 KB of shared memory); one CTA per SM.
+// CTA = 1024 threads = 32 warps sharing the tables (163 KB of shared memory); one CTA per SM.
+// Shared memory beyond ~200 KB leaves the SM too little L1 for the loads in flight (a 213 KB
+// variant of the same code ran 19 % slower).
 #pragma once
 #include <stddef.h>
 
@@ -48,24 +52,66 @@ namespace nvpyr {
 #ifndef NVPYR_FAST_PREFETCH
 #define NVPYR_FAST_PREFETCH 1
 #endif
-// NVPYR_ENC_WAYS = 4: every bucket entry is stored 4 times (16 bytes) and lane l reads copy l & 3,
-// so lanes with different l & 3 can never collide on a bank (the un-replicated table costs ~3.8
+// NVPYR_ENC_WAYS = W: every bucket entry is stored W times (4 W bytes) and lane l reads copy l & (W - 1),
+// so lanes with different l & (W - 1) can never collide on a bank (the un-replicated table costs ~3.8
 // wavefronts per warp-wide lookup on random data).  Needs one 1024-thread CTA per SM.
+// NVPYR_FAST_ENC_LOW_OCTAVES = n: the table is extended n octaves below 2^-13 (everything there encodes to 0).
+// A level whose smallest non-zero value, linearFromSrgb(1) / 4^K, still lies inside the table is encoded
+// without a clamp; the other levels clamp the value from below with one FMNMX first.  n = 11 (default) covers
+// all six levels; n = 3 covers levels +1 and +2 (15 of every 16 encodes) with a table 33 % shorter (164 KB per
+// CTA instead of 197 KB).  NVPYR_FAST_ENC_CLAMP = 1 clamps everywhere (n = 0).  Measured at 16384^2 (us, Julia /
+// uniform-random input): n = 11: 242.4 / 273.4;  n = 3: 247.4 / 268.1;  clamp everywhere: 249.3 / 268.8.
+// Shared memory beyond ~200 KB leaves the SM too little L1 for the loads in flight: the same code padded to
+// 213 KB runs at 311 / 335 us.
 #ifndef NVPYR_ENC_WAYS
-#define NVPYR_ENC_WAYS 4
+#define NVPYR_ENC_WAYS 8
 #endif
+#ifndef NVPYR_FAST_ENC_CLAMP
+#define NVPYR_FAST_ENC_CLAMP 0
+#endif
+#ifndef NVPYR_FAST_ENC_LOW_OCTAVES
+#define NVPYR_FAST_ENC_LOW_OCTAVES 11
+#endif
+// NVPYR_FAST_SLAB_UNROLL = 2: the prefetch registers of one slab are the working registers of the next, so the
+// register moves of the rotating double buffer disappear (422 -> 350 instructions per slab) -- and the kernel
+// gets SLOWER (258 us): ptxas tracks every LDG of the loop with one scoreboard, so the first use of slab s+1
+// also waits for the just-issued loads of slab s+2 (long-scoreboard stalls 0.29 -> 3.6 warps per issue, ncu).
+// NVPYR_FAST_PIN_PREFETCH = 1 orders the new loads after that first use through a fake address dependency
+// (260 us: ptxas then spills inside the loop).  NVPYR_FAST_UNCOND_LOADS = 1 loads unconditionally (lanes outside
+// the image read its first rows).  All three are kept for A/B runs only; the measured best is the default.
 #ifndef NVPYR_FAST_SLAB_UNROLL
 #define NVPYR_FAST_SLAB_UNROLL 1
 #endif
+#ifndef NVPYR_FAST_PAD_BYTES
+#define NVPYR_FAST_PAD_BYTES 16
+#endif
+#ifndef NVPYR_FAST_PIN_PREFETCH
+#define NVPYR_FAST_PIN_PREFETCH 0
+#endif
+#ifndef NVPYR_FAST_UNCOND_LOADS
+#define NVPYR_FAST_UNCOND_LOADS 0
+#endif
+constexpr bool     kFastUncondLoads = NVPYR_FAST_UNCOND_LOADS != 0;
 constexpr int      kFastSlabUnroll = NVPYR_FAST_SLAB_UNROLL;
 constexpr uint32_t kEncWays       = NVPYR_ENC_WAYS;
+constexpr bool     kEncClamp      = NVPYR_FAST_ENC_CLAMP != 0;
 constexpr int      kFastWarps     = NVPYR_FAST_WARPS;
 constexpr int      kFastCtasPerSm = NVPYR_ENC_WAYS == 1 ? 2 : 1;
 constexpr bool     kFastPrefetch  = NVPYR_FAST_PREFETCH != 0;
 constexpr int      kDecScaleExp   = 100;  // decode table holds 2^-100 * linearFromSrgb(code)
-constexpr uint32_t kEncLowOctaves = 11;   // bucket table extended below 2^-13 down to d(1) / 4^6
-constexpr uint32_t kEncMinKeyExt  = kEncMinKey - kEncLowOctaves * (1u << (23 - kEncShift));
-constexpr uint32_t kEncEntriesExt = kEncEntries + kEncLowOctaves * (1u << (23 - kEncShift));
+constexpr uint32_t kEncKeysPerOctave = 1u << (23 - kFastEncShift);
+constexpr uint32_t kEncLowOctaves = kEncClamp ? 0 : NVPYR_FAST_ENC_LOW_OCTAVES;  // bucket table extended below 2^-13
+// Is every non-zero value of level K inside the extended table?  linearFromSrgb(1) = 2^-11.7: sums of level K
+// are >= 2^-(11.7 + 2K); the premultiply pre-pass (K = 0) makes products down to 2^-19.7.
+constexpr bool encCovered(int K)
+{
+  return K == 0 ? kEncLowOctaves >= 7 : 2u * uint32_t(K) <= kEncLowOctaves + 1u;
+}
+constexpr uint32_t kEncMinKeyExt  = kFastEncMinKey - kEncLowOctaves * kEncKeysPerOctave;
+constexpr uint32_t kEncEntriesExt = kFastEncEntries + kEncLowOctaves * kEncKeysPerOctave;
+constexpr uint32_t kEncStride     = 4u * kEncWays;  // bytes per bucket entry (all copies)
+constexpr uint32_t kEncStrideLog2 = kEncWays == 1 ? 2 : kEncWays == 2 ? 3 : kEncWays == 4 ? 4 : kEncWays == 8 ? 5 : 6;
+static_assert((1u << kEncStrideLog2) == kEncStride, "1, 2, 4, 8 or 16 copies");
 
 struct Srgba8FastSmem
 {
@@ -73,28 +119,34 @@ struct Srgba8FastSmem
   float    pad[32];                 // keeps the zero words in the spare halves (see encScaled)
   alignas(16) uint32_t encode[(kEncEntriesExt + 3) * kEncWays];  // bucket table, extended downwards, kEncWays copies per entry
   alignas(16) float l3[kFastWarps][8][8][4];  // per warp: level +3 sums of its 64x64 tile, [slab][x][channel]
+  uint32_t tileArrivals[kFastWarps];           // slab tasks: slabs of local tile j that have arrived
+  unsigned char unused[NVPYR_FAST_PAD_BYTES];  // A/B experiments on the shared-memory carve-out
 };
-
-static_assert(offsetof(Srgba8FastSmem, encode) == 65536 + 128, "encScaled's zero words assume this layout");
+static_assert(offsetof(Srgba8FastSmem, decode) == 0 && offsetof(Srgba8FastSmem, encode) == 65536 + 128,
+              "encScaled's zero words assume this layout");
 
 // Per-level constants of the scaled encode.  The carried value is S' = 2^-E * 4^K * x, so
-// bits(x) = bits(S') + ((E - 2K) << 23) and key(x) = key(S') + (E - 2K) * 256.
+// bits(x) = bits(S') + ((E - 2K) << 23) and key(x) = key(S') + (E - 2K) * kEncKeysPerOctave.
 template <int K>
 struct EncConst
 {
   static constexpr uint32_t kAdd  = uint32_t(kDecScaleExp - 2 * K) << 23;
-  static constexpr int32_t  kBias = (int32_t(kEncMinKeyExt) - (kDecScaleExp - 2 * K) * 256) * 4 * int32_t(kEncWays);  // bytes, > 0
+  static constexpr int32_t  kBias = (int32_t(kEncMinKeyExt) - (kDecScaleExp - 2 * K) * int32_t(kEncKeysPerOctave)) * int32_t(kEncStride);  // bytes, > 0
   // float index (into Srgba8FastSmem::decode) of the word that an exact zero reads
-  static constexpr int32_t kZeroIndex = (65536 + 128 - kBias) / 4;
-  static_assert(kBias > 0 && kBias <= 65536 && (65536 + 128 - kBias) % 256 == 128,
+  static constexpr int32_t kZeroIndex = (65536 + 128 - kBias) / 4;  // meaningful where !kClamp
+  static constexpr bool kClamp = !encCovered(K);
+  static_assert(kClamp || (kBias > 0 && kBias <= 65536 && (65536 + 128 - kBias) % 256 == 128),
                 "zero word must fall into a spare half row");
+  // clamped levels: S' of 2^-13 (below the first threshold; inside the table)
+  static constexpr uint32_t kMinBits = kEncMinBits - kAdd;
 };
 
 template <int K>
 __device__ __forceinline__ void putZeroWord(Srgba8FastSmem& sm)
 {
-  for(uint32_t w = 0; w < kEncWays; ++w)
-    sm.decode[EncConst<K>::kZeroIndex + w] = __uint_as_float(0u - EncConst<K>::kAdd);
+  if constexpr(!EncConst<K>::kClamp)
+    for(uint32_t w = 0; w < kEncWays; ++w)
+      sm.decode[EncConst<K>::kZeroIndex + w] = __uint_as_float(0u - EncConst<K>::kAdd);
 }
 
 __device__ __forceinline__ void srgba8FastInit(Srgba8FastSmem& sm, const DeviceTables* t)
@@ -108,22 +160,27 @@ __device__ __forceinline__ void srgba8FastInit(Srgba8FastSmem& sm, const DeviceT
     const float4   v4   = make_float4(v, v, v, v);
     d[0] = v4, d[1] = v4, d[2] = v4, d[3] = v4;
   }
-  constexpr uint32_t kLow = kEncEntriesExt - kEncEntries;
+  constexpr uint32_t kLow = kEncEntriesExt - kFastEncEntries;
   static_assert(kLow % 4 == 0, "upper part of the table must stay 16-byte aligned");
   if(kEncWays == 1)
   {
     for(uint32_t i = threadIdx.x; i < kLow; i += blockDim.x)
-      sm.encode[i] = 0u - ((kEncMinKeyExt + i) << kEncShift);  // code 0, no threshold, pre-biased
+      sm.encode[i] = 0u - ((kEncMinKeyExt + i) << kFastEncShift);  // code 0, no threshold, pre-biased
     copyTableWide<kFastWarps * 32>(reinterpret_cast<uint4*>(&sm.encode[kLow]),
-                                   reinterpret_cast<const uint4*>(t->encode), kEncEntriesPadded / 4);
+                                   reinterpret_cast<const uint4*>(t->encodeFast), kFastEncEntriesPadded / 4);
   }
   else
   {
-    uint4* e4 = reinterpret_cast<uint4*>(sm.encode);  // kEncWays == 4: one uint4 per entry
-    for(uint32_t i = threadIdx.x; i < kEncEntriesExt; i += blockDim.x)
+    // thread -> (entry, group of four copies): one 16-byte store
+    constexpr uint32_t kQuads = kEncWays >= 4 ? kEncWays / 4 : 1;
+    for(uint32_t i = threadIdx.x; i < kEncEntriesExt * kQuads; i += blockDim.x)
     {
-      const uint32_t v = i < kLow ? 0u - ((kEncMinKeyExt + i) << kEncShift) : __ldg(&t->encode[i - kLow]);
-      e4[i]            = make_uint4(v, v, v, v);
+      const uint32_t k = i / kQuads;
+      const uint32_t v = k < kLow ? 0u - ((kEncMinKeyExt + k) << kFastEncShift) : __ldg(&t->encodeFast[k - kLow]);
+      if(kEncWays >= 4)
+        reinterpret_cast<uint4*>(sm.encode)[i] = make_uint4(v, v, v, v);
+      else
+        reinterpret_cast<uint2*>(sm.encode)[i] = make_uint2(v, v);
     }
   }
   if(threadIdx.x == 0)
@@ -216,17 +273,19 @@ __device__ __forceinline__ V4 quadSumV(const unsigned char* dec, uint32_t laneOf
 }
 
 // Encode of one RGB channel carried as S' = 2^-100 * 4^K * x; the code lands in bits 16..23.
-// No clamp: every non-zero S' lies inside the (extended) table, zero reads its dedicated word.
+// Covered levels (encCovered): every non-zero S' lies inside the extended table, zero reads its dedicated word.
 // encWay = (lane & (kEncWays - 1)) * 4: which copy of the entry this lane reads.
 template <int K>
 __device__ __forceinline__ uint32_t encScaled(const unsigned char* encBytes, float s, uint32_t encWay = 0)
 {
+  if(EncConst<K>::kClamp)
+    s = fmaxf(s, __uint_as_float(EncConst<K>::kMinBits));  // below the first threshold everything encodes to 0
   const uint32_t b = __float_as_uint(s);
   uint32_t       off;
   if(kEncWays == 1)
-    off = (b >> (kEncShift - 2)) & 0x3FFFCu;
+    off = (b >> (kFastEncShift - 2)) & 0xFFFFFFFCu;
   else
-    off = ((b >> (kEncShift - 4)) & 0xFFFF0u) | encWay;  // key * 16 + copy * 4
+    off = ((b >> (kFastEncShift - kEncStrideLog2)) & ~(kEncStride - 1u)) | encWay;  // key * stride + copy * 4
   const uint32_t e = *reinterpret_cast<const uint32_t*>(encBytes + off - EncConst<K>::kBias);
   return e + b + EncConst<K>::kAdd;
 }
@@ -350,9 +409,11 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
   static_assert(M >= 2 && M <= 6, "2..6 levels");
   static_assert(!kSlabTasks || (M >= 4 && !kBatch), "slab tasks: single image, levels beyond +3");
   constexpr uint32_t kTileH = M >= 3 ? (1u << M) : 8u, kSlabs = kTileH / 8u;
+  constexpr int      kSlabUnroll = kPremul ? 1 : kFastSlabUnroll;
+  constexpr bool     kPinPrefetch = NVPYR_FAST_PIN_PREFETCH != 0 && kSlabUnroll > 1 && kSlabs > 1;
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  __shared__ uint32_t tileArrivals[kFastWarps];  // slab tasks: slabs of local tile j that have arrived
   Srgba8FastSmem& sm = *reinterpret_cast<Srgba8FastSmem*>(smemRaw);
+  uint32_t* const tileArrivals = sm.tileArrivals;
   if(kSlabTasks && threadIdx.x < kFastWarps)
     tileArrivals[threadIdx.x] = 0u;
   srgba8FastInit(sm, p.tables);
@@ -391,7 +452,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
   uint32_t       tile     = kSlabTasks ? blockIdx.x + gridDim.x * (task / kSlabs) : blockIdx.x + gridDim.x * warp;
   uint32_t       slab0    = kSlabTasks ? task % kSlabs : 0u;  // first slab of this warp's current unit of work
 
-  // Per-lane cursor of the slab being prefetched: source pointer + "inside the image".
+  // Per-lane cursor of the slab being prefetched: source pointer + "inside the image".  Edges are multiples of
+  // 2^M and a tile is 2^M rows tall, so a lane is inside or outside for a whole tile (outside: a narrow level
+  // whose last tile is cut in x, or no tile left).  Outside lanes read the first rows of the image instead
+  // -- the loads are unconditional, which spares the compiler a second copy of the 16 prefetch registers.
   struct Cursor
   {
     const unsigned char* src;
@@ -401,13 +465,14 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
     const uint32_t tt = kBatch ? t % batch.tilesPerImage : t;  // tile inside its image
     const uint32_t x0 = (tt % p.tilesX) * 64u + tx * 4u, y0 = (tt / p.tilesX) * kTileH + firstSlab * 8u + ty * 4u;
     Cursor         c;
-    c.active = t < numTiles && x0 < W && y0 < H;
-    c.src    = (kBatch && t >= numTiles ? nullptr : levelPtr(0, t)) + size_t(y0) * pitch0 + size_t(x0) * 4u;
+    c.active = t < numTiles && x0 < W && y0 < H;  // (y0 >= H: the 8-row tiles of a 2-level step on H % 8 == 4)
+    const unsigned char* base = levelPtr(0, kBatch && t >= numTiles ? 0u : t);
+    c.src    = c.active || !kFastUncondLoads ? base + size_t(y0) * pitch0 + size_t(x0) * 4u : base;
     return c;
   };
   uint4 row[4];
   auto  loadRows = [&](const Cursor& c) {
-    if(c.active)
+    if(kFastUncondLoads || c.active)
     {
 #pragma unroll
       for(int i = 0; i < 4; ++i)
@@ -436,7 +501,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
     unsigned char* d3 = M >= 3 ? levelPtr(3, tile) + size_t(y0 >> 3) * p.lv[3].pitch + size_t(x0 >> 3) * 4u : nullptr;
     const Cursor   nextTile = tileCursor(nextTileI, nextSlab0);
     const uint32_t slabEnd  = kSlabTasks ? slab0 + 1u : kSlabs;
-#pragma unroll kFastSlabUnroll
+#pragma unroll kSlabUnroll
     for(uint32_t slab = slab0; slab < slabEnd; ++slab, y0 += 8u, d1 += 4u * pitch1, d2 += 2u * pitch2)
     {
       // Edges are multiples of 2^M >= 4: a 4x4 block is entirely inside or outside.
@@ -447,14 +512,24 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
       unsigned char* const curSrc = const_cast<unsigned char*>(nxt.src);
       // the next slab (of this tile, or the first one of this warp's next tile)
       if(!kSlabTasks && slab + 1u < kSlabs)
-      {
-        nxt.src += 8u * pitch0;
-        nxt.active = x0 < W && y0 + 8u < H;
-      }
+        nxt.src += 8u * pitch0;  // (an outside lane walks down the first 2^M rows of the image)
       else
         nxt = nextTile;
       if(kFastPrefetch)
-        loadRows(nxt);
+      {
+        if(kPinPrefetch)
+        {
+          // ptxas tracks every LDG of this loop with ONE scoreboard.  In the unrolled loop the prefetch of slab s+2
+          // would be issued just before the first use of slab s+1's registers, and that use would then wait for
+          // both.  The address below depends (by a bit that is always 0: decoded values are never negative) on the
+          // first decode of this slab, so the new loads are issued after the wait for the previous ones.
+          Cursor pinned = nxt;
+          pinned.src += __float_as_uint(dec8<0>(dec, c0.x, laneOff)) >> 31;
+          loadRows(pinned);
+        }
+        else
+          loadRows(nxt);
+      }
 
       if(kPremul && active)
       {

@@ -53,10 +53,23 @@ constexpr uint32_t kEncEntries = kEncMaxKey - kEncMinKey + 1;  // 3329
 
 constexpr uint32_t kEncEntriesPadded = (kEncEntries + 3u) & ~3u;  // whole uint4s for the copy into shared memory
 
+// The tuned fast kernel (nvpyr_fast_srgba8.cuh) keys the same kind of table on 7 mantissa bits: with the pinned
+// thresholds a bucket of 2^16 float patterns still holds at most one (checked when the table is built), and the
+// table is half as long -- which pays for twice as many bank-partitioned copies of every entry.
+#ifndef NVPYR_FAST_ENC_SHIFT
+#define NVPYR_FAST_ENC_SHIFT 16
+#endif
+constexpr uint32_t kFastEncShift   = NVPYR_FAST_ENC_SHIFT;
+constexpr uint32_t kFastEncMinKey  = kEncMinBits >> kFastEncShift;
+constexpr uint32_t kFastEncMaxKey  = kEncMaxBits >> kFastEncShift;
+constexpr uint32_t kFastEncEntries = kFastEncMaxKey - kFastEncMinKey + 1;
+constexpr uint32_t kFastEncEntriesPadded = (kFastEncEntries + 3u) & ~3u;
+
 struct alignas(16) DeviceTables
 {
   float    decode[256];                // linearFromSrgb(c), shaders/srgb.h:18-28 (pinned bits)
   uint32_t encode[kEncEntriesPadded];  // bucket table described above
+  uint32_t encodeFast[kFastEncEntriesPadded];  // the same, keyed on bits >> kFastEncShift
 };
 
 // Programmatic dependent launch (sm_90+): every kernel of the library is launched with
