@@ -107,3 +107,30 @@ def test_product_package_does_not_touch_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle/" not in txt.replace("oracle/ ", "") or f in ("_lib.py", "__init__.py"), f
                 assert "nvpyr_oracle" not in txt and "libnvpyr_ref" not in txt, f
+
+
+def test_cxx_template_header_compiles_for_sm100a(tmp_path):
+    """include/nvpyr.cuh (user-defined functor sets, SURVEY 8b "Extensibility") is header-only: a user translation
+    unit with its own functor set must compile for sm_100a with nvcc alone."""
+    import shutil, subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    src = tmp_path / "user.cu"
+    src.write_text("""
+#include "nvpyr.cuh"
+struct LumaMin : nvpyr::PyramidFunctors<LumaMin>
+{
+  using Value = float2;
+  static constexpr int kTexelBytes = 8;
+  __device__ static Value load(const Params*, const void* t) { return *static_cast<const float2*>(t); }
+  __device__ static void store(const Params*, void* t, Value v) { *static_cast<float2*>(t) = v; }
+  __device__ static Value reduce(float a0, Value v0, float a1, Value v1, float a2, Value v2)
+  { return make_float2(a0 * v0.x + a1 * v1.x + a2 * v2.x, fminf(v0.y, fminf(v1.y, v2.y))); }
+};
+nvpyrStatus run(const nvpyrDispatchDesc& d) { return nvpyr::dispatch<LumaMin>(d); }
+""")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-c", "-I",
+                        os.path.join(ROOT, "include"), str(src), "-o", str(tmp_path / "user.o")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr

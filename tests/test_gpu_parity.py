@@ -481,6 +481,20 @@ def test_minimal_app_equivalent(nv, cuda, oracle, tmp_path):
     assert r.returncode != 0 and "Unknown argument" in r.stderr
 
 
+def test_user_defined_functor_sets(nv, cuda):
+    """include/nvpyr.cuh: the CUDA form of the reference's NVPRO_PYRAMID_* macro contract and dispatcher callbacks
+    (nvpro_pyramid.glsl:27-120, nvpro_pyramid_dispatch.hpp:99-116).  examples/custom_functors runs a hi-z (max)
+    pyramid over R32F images through every schedule variant -- bit-exact vs a CPU loop -- and a user-written copy
+    of the RGBA32F instance that must equal the library's own, bit for bit."""
+    import subprocess
+    exe = os.path.join(_oracle.ROOT, "examples", "custom_functors")
+    assert os.path.exists(exe), "examples/custom_functors has not been built (__graft_entry__.build())"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "custom functor sets ok" in r.stdout
+    assert r.stdout.count("0 of") == 36 + 1 + 4, r.stdout
+
+
 def test_other_stream(nv, cuda, oracle):
     w, h = 320, 192
     l0 = _oracle.random_level0(w, h, 13)

@@ -119,7 +119,6 @@ struct Srgba8FastSmem
   float    pad[32];                 // keeps the zero words in the spare halves (see encScaled)
   alignas(16) uint32_t encode[(kEncEntriesExt + 3) * kEncWays];  // bucket table, extended downwards, kEncWays copies per entry
   alignas(16) float l3[kFastWarps][8][8][4];  // per warp: level +3 sums of its 64x64 tile, [slab][x][channel]
-  uint32_t tileArrivals[kFastWarps];           // slab tasks: slabs of local tile j that have arrived
   unsigned char unused[NVPYR_FAST_PAD_BYTES];  // A/B experiments on the shared-memory carve-out
 };
 static_assert(offsetof(Srgba8FastSmem, decode) == 0 && offsetof(Srgba8FastSmem, encode) == 65536 + 128,
@@ -412,8 +411,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
   constexpr int      kSlabUnroll = kPremul ? 1 : kFastSlabUnroll;
   constexpr bool     kPinPrefetch = NVPYR_FAST_PIN_PREFETCH != 0 && kSlabUnroll > 1 && kSlabs > 1;
   extern __shared__ __align__(16) unsigned char smemRaw[];
+  __shared__ uint32_t tileArrivals[kFastWarps];  // slab tasks: slabs of local tile j that have arrived
   Srgba8FastSmem& sm = *reinterpret_cast<Srgba8FastSmem*>(smemRaw);
-  uint32_t* const tileArrivals = sm.tileArrivals;
   if(kSlabTasks && threadIdx.x < kFastWarps)
     tileArrivals[threadIdx.x] = 0u;
   srgba8FastInit(sm, p.tables);
@@ -512,7 +511,11 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm) fastSrgba8Ker
       unsigned char* const curSrc = const_cast<unsigned char*>(nxt.src);
       // the next slab (of this tile, or the first one of this warp's next tile)
       if(!kSlabTasks && slab + 1u < kSlabs)
-        nxt.src += 8u * pitch0;  // (an outside lane walks down the first 2^M rows of the image)
+      {
+        nxt.src += 8u * pitch0;  // (with unconditional loads an outside lane walks down the first 2^M rows of the image)
+        if(!kFastUncondLoads)
+          nxt.active = x0 < W && y0 + 8u < H;
+      }
       else
         nxt = nextTile;
       if(kFastPrefetch)

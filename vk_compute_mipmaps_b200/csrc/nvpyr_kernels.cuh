@@ -55,6 +55,22 @@ __device__ __forceinline__ float4 shflXor(float4 v, int mask)
   return make_float4(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask),
                      __shfl_xor_sync(0xffffffffu, v.z, mask), __shfl_xor_sync(0xffffffffu, v.w, mask));
 }
+// NVPRO_PYRAMID_SHUFFLE_XOR (glsl:191-193) for any value type made of 32-bit words (user functor sets).
+template <class V>
+__device__ __forceinline__ V shflXor(V v, int mask)
+{
+  static_assert(sizeof(V) % 4 == 0 && sizeof(V) <= 64, "value types are made of 1..16 32-bit words");
+  union
+  {
+    V        v;
+    uint32_t w[sizeof(V) / 4];
+  } a, b;
+  a.v = v;
+#pragma unroll
+  for(int i = 0; i < int(sizeof(V) / 4); ++i)
+    b.w[i] = __shfl_xor_sync(0xffffffffu, a.w[i], mask);
+  return b.v;
+}
 
 struct FastParams
 {
@@ -67,7 +83,7 @@ template <class F>
 struct FastSmem
 {
   typename F::Shared tables;
-  float4             l3[2][8][8];  // level +3 of the current tile, double buffered
+  typename F::Value  l3[2][8][8];  // level +3 of the current tile, double buffered
 };
 
 // Tile loop of an M-level fast step, executed by a whole 256-thread CTA: tiles firstTile,
@@ -78,7 +94,8 @@ struct FastSmem
 // 2-texel store.
 template <class F, int M, bool kVec>
 __device__ __forceinline__ void fastTileLoop(const FastParams& p, const typename F::Shared& tables,
-                                             float4 (*l3buf)[8][8], uint32_t firstTile, uint32_t tileStride)
+                                             typename F::Value (*l3buf)[8][8], uint32_t firstTile,
+                                             uint32_t tileStride)
 {
   static_assert(M >= 2 && M <= 6, "fastTileLoop handles 2..6 levels");
   using V = typename F::Value;
@@ -96,7 +113,7 @@ __device__ __forceinline__ void fastTileLoop(const FastParams& p, const typename
     const bool active = tid < 256u && x0 < W && y0 < H;
 
     V l1[2][2];
-    V l2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    V l2{};
     if(active)
     {
 #pragma unroll
@@ -163,7 +180,7 @@ __device__ __forceinline__ void fastTileLoop(const FastParams& p, const typename
         const uint32_t i = tid & 3u, j = (tid >> 2) & 3u;
         const uint32_t ox = tileX * 64u + i * 16u, oy = tileY * 64u + j * 16u;  // origin in level 0
         const bool     valid = tid < 16 && ox < W && oy < H;
-        V              l4    = make_float4(0.f, 0.f, 0.f, 0.f);
+        V              l4{};
         if(valid)
         {
           const V ul = l3buf[parity][2 * j][2 * i], ur = l3buf[parity][2 * j][2 * i + 1];
@@ -256,19 +273,19 @@ constexpr int kGenTile2 = 16;  // tile edge in level +2 of the stand-alone gener
 constexpr int kGenTile2Small = 8;  // ... of the tail kernel (more, smaller tiles: the levels are tiny)
 
 // Shared scratch of a T2 x T2 tile of level +2: (2 T2 + 1)^2 texels of level +1 (float32 carry).
-template <int T2>
+template <int T2, class V = float4>
 struct GenTile
 {
   static constexpr int kTile1 = 2 * T2 + 1;
   static constexpr int kPitch = kTile1 + 1;
-  float4               l1[kTile1][kPitch];  // [y][x]
+  V                    l1[kTile1][kPitch];  // [y][x]
 };
 
 template <class F>
 struct GeneralSmem
 {
-  typename F::Shared tables;
-  GenTile<kGenTile2> tile;
+  typename F::Shared                    tables;
+  GenTile<kGenTile2, typename F::Value> tile;
 };
 
 // kernelSizeFromInputSize_, glsl:557-561
@@ -328,10 +345,11 @@ __device__ __forceinline__ typename F::Value reduceSample(int kx, int ky, uint32
 // p.tilesX/Y must have been computed for T2 (generalTiles()).
 template <class F, int T2>
 __device__ __forceinline__ void generalTileLoop(const GeneralParams& p, const typename F::Shared& tables,
-                                                GenTile<T2>& scratch, uint32_t firstTile, uint32_t tileStride)
+                                                GenTile<T2, typename F::Value>& scratch, uint32_t firstTile,
+                                                uint32_t tileStride)
 {
-  float4(*l1buf)[GenTile<T2>::kPitch] = scratch.l1;
-  using V = typename F::Value;
+  using V                             = typename F::Value;
+  V(*l1buf)[GenTile<T2, V>::kPitch] = scratch.l1;
   const LevelView L0 = p.lv[0], L1 = p.lv[1], L2 = p.lv[2];
   const int       k1x = kernelTaps(L0.w), k1y = kernelTaps(L0.h);
   const uint32_t  numTiles = p.tilesX * p.tilesY;
@@ -444,8 +462,8 @@ struct TailSmem
   typename F::Shared tables;
   union
   {
-    float4                  l3[2][8][8];
-    GenTile<kGenTile2Small> tile;
+    typename F::Value                          l3[2][8][8];
+    GenTile<kGenTile2Small, typename F::Value> tile;
   };
   uint32_t isLast;
 };
