@@ -229,6 +229,27 @@ def fill_gradient(level0, w, h):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank's host threads to the CPUs next to its GPU (NVML's affinity mask) BEFORE any pinned host
+    memory is allocated, so that the staging buffers of the end-to-end leg live on the GPU's own NUMA node: with
+    one process per GPU the host side of the round trip otherwise crosses the socket interconnect for half of the
+    ranks.  Best effort: returns the number of CPUs bound to, or 0."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = [64 * i + b for i, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def run_gpu_arm(args):
     import numpy as np
     import torch
@@ -242,6 +263,7 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -399,7 +421,7 @@ def run_gpu_arm(args):
         t_separate = timed(lambda: nv.generate_host(a_in, W, H, out=a_out))
         e2e = {"value": world * chain_bytes / t_inplace / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": l0_bytes, "d2h_bytes_per_step": chain_bytes - l0_bytes, "steps": e_steps,
-               "ms_per_step": 1e3 * t_inplace,
+               "ms_per_step": 1e3 * t_inplace, "host_cpus_bound_to_gpu_numa_node": numa_cpus,
                "api": "nvpyrGenerateHost in place on one pinned host chain (level 0 filled -> levels 1..14 filled), "
                       "upload / kernels / download overlapped in 32 MB bands",
                "separate_buffers": {"value": world * chain_bytes / t_separate / 1e9, "unit": UNIT,

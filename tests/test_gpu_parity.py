@@ -495,6 +495,30 @@ def test_user_defined_functor_sets(nv, cuda):
     assert r.stdout.count("0 of") == 36 + 1 + 4, r.stdout
 
 
+@pytest.mark.parametrize("size", [(1024, 512), (333, 201), (1920, 1080)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_recorded_once_replayed_per_frame(nv, cuda, oracle, size):
+    """The reference RECORDS the pyramid into a command buffer and submits it every frame
+    (nvpro_pyramid_dispatch.hpp:42-53; demo_app/mipmaps_app.cpp:363-369).  The CUDA form: the dispatch is captured
+    into a CUDA graph once and the graph is replayed for new contents of level 0 -- programmatic dependent launches,
+    the tail kernel's ticket counter and the cached launch configuration must all survive capture and replay."""
+    w, h = size
+    buf = cuda.zeros(nv.chain_bytes(w, h), dtype=cuda.uint8, device="cuda")
+    pipes = nv.PyramidPipelines()
+    nv.cmd_pyramid_dispatch(None, pipes, w, h, image=buf)  # warm: per-device context and launch configs exist
+    cuda.cuda.synchronize()
+    g = cuda.cuda.CUDAGraph()
+    with cuda.cuda.graph(g):
+        nv.cmd_pyramid_dispatch(None, pipes, w, h, image=buf)
+    for frame in range(3):
+        l0 = _oracle.random_level0(w, h, 100 + frame)
+        buf.zero_()
+        buf[:4 * w * h] = cuda.from_numpy(l0).cuda()
+        g.replay()
+        cuda.cuda.synchronize()
+        want, _ = oracle.shader_chain(l0, w, h)
+        assert_same(buf.cpu().numpy(), want, w, h, oracle, f"graph replay {frame}")
+
+
 def test_other_stream(nv, cuda, oracle):
     w, h = 320, 192
     l0 = _oracle.random_level0(w, h, 13)

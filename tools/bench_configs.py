@@ -23,6 +23,8 @@ CONFIGS = [  # name, w, h, fmt, RTX 3090 min ns of the reference (README.md:166-
 def main():
     ap = argparse.ArgumentParser(); ap.add_argument("--batches", type=int, default=30); ap.add_argument("--out")
     ap.add_argument("--only", default="")
+    ap.add_argument("--graph", action="store_true", help="also time the chain captured once into a CUDA graph and "
+                    "replayed (the reference records a command buffer once and submits it per frame)")
     a = ap.parse_args()
     peak = 6541.8
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -57,13 +59,36 @@ def main():
             if bi: times.append(e0.elapsed_time(e1) * 1e6 / 8)
         times.sort()
         mn, med = times[0], times[len(times) // 2]
+        graph_med = None
+        if a.graph:
+            side = torch.cuda.Stream()
+            graphs = []
+            for k in range(nrot):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    nv.cmd_pyramid_dispatch(None, pipes, w, h, image=bufs[k])
+                graphs.append(g)
+            gt = []
+            for bi in range(a.batches + 1):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                for i in range(8):
+                    graphs[(bi * 8 + i) % nrot].replay()
+                e1.record(st)
+                torch.cuda.synchronize()
+                if bi: gt.append(e0.elapsed_time(e1) * 1e6 / 8)
+            gt.sort()
+            graph_med = gt[len(gt) // 2]
         r = {"config": name, "w": w, "h": h, "format": "srgba8" if fmt == 0 else "rgba32f", "launches": launches,
              "min_ns": round(mn), "median_ns": round(med), "algorithmic_bytes": nbytes,
              "GBps_at_median": round(nbytes / med, 1), "frac_of_hbm_peak": round(nbytes / med / peak, 3),
              "rtx3090_reference_min_ns": ref_ns, "rotating_buffers": nrot}
+        if graph_med is not None:
+            r["graph_replay_median_ns"] = round(graph_med)
         res.append(r)
         print(f"{name:20s} {w}x{h} {r['format']:8s} launches {launches:2d}  min {mn/1e3:9.1f} us  median {med/1e3:9.1f} us  "
               f"{r['GBps_at_median']:8.1f} GB/s  ({100*r['frac_of_hbm_peak']:.1f}% of HBM peak)"
+              + (f"  [graph replay {graph_med/1e3:.1f} us]" if graph_med is not None else "")
               + (f"  [RTX3090 ref {ref_ns/1e3:.1f} us]" if ref_ns else ""), flush=True)
         del bufs
         torch.cuda.empty_cache()
