@@ -1,6 +1,6 @@
 // custom_functors.cu -- the user-defined instance of the pyramid template (include/nvpyr.cuh), i.e. what a
 // user of the reference does by defining the NVPRO_PYRAMID_* macros before including nvpro_pyramid.glsl
-// (nvpro_pyramid/nvpro_pyramid.glsl:27-120) and by passing his own dispatcher callbacks to
+// (nvpro_pyramid/nvpro_pyramid.glsl:27-120) and by passing their own dispatcher callbacks to
 // nvproCmdPyramidDispatch (nvpro_pyramid_dispatch.hpp:99-116).
 //
 //   1. DepthMax   -- a hi-z pyramid over an R32F image: Value = float, reduce = max of the footprint, a
