@@ -33,17 +33,33 @@ namespace nvpyr {
 //   * decode table at window address 0x10000, [code][64 floats] (floats 0..31 = one copy per lane):
 //     address = 0x10000 | code << 8 | lane << 2 is produced by ONE PRMT from the packed texel and
 //     (0x10000 | lane << 2);
-//   * encode bucket table placed so that the entry of key k sits at window address (4 k) mod 2^16: the
-//     masked, shifted float bits ARE the address (keys 0x7200..0x7F00 -> 0xC800..0xFC00, no wrap inside).
+//   * encode bucket table placed so that the entry of key k sits at window address (stride * k) mod 2^16: the
+//     masked, shifted float bits ARE the address (no wrap inside the key range; see NVPYR_GEN_ENC_WAYS below).
 // 127 KB per CTA, one CTA per SM; ~100 KB stay free for the next kernel's CTAs (programmatic dependent launch).
 constexpr uint32_t kGenWindowBase = 0x400u;
 constexpr uint32_t kGenDecodeAddr = 0x10000u;
-constexpr uint32_t kGenEncodeMask = 0xFFFCu;
-constexpr uint32_t kGenEncodeAddr = (kEncMinKey * 4u) & kGenEncodeMask;  // window address of the first entry
-static_assert(((kEncMaxKey * 4u) & kGenEncodeMask) == kGenEncodeAddr + (kEncMaxKey - kEncMinKey) * 4u,
+// NVPYR_GEN_ENC_WAYS = 1 (default): 8 mantissa bits, one copy, the entry of key k at window address (4 k) mod 2^16.
+// NVPYR_GEN_ENC_WAYS = 8: the bucket table keyed on 7 mantissa bits (DeviceTables::encodeFast), every entry stored
+// 8 times (32 bytes), lane l reads copy l & 7 -- lanes with different l & 7 never collide on a bank (un-replicated,
+// 35 % of the shared-load wavefronts of the four-column kernel are bank conflicts on noisy input).  The entry of
+// key k sits at window address (32 k) mod 2^16 (keys 0x3900..0x3F80 -> 0x2000..0xF000, 52 KB, below the decode
+// table).  Bit-exact, but no faster (4095^2 52.4 -> 52.0 us, 4094^2 50.9 -> 51.7 us, the rest within noise): these
+// kernels are bound by load latency, not by the LSU pipe -- so the cheaper set-up stays the default.
+#ifndef NVPYR_GEN_ENC_WAYS
+#define NVPYR_GEN_ENC_WAYS 1
+#endif
+constexpr uint32_t kGenEncWays    = NVPYR_GEN_ENC_WAYS;
+static_assert(kGenEncWays == 1 || kGenEncWays == 8, "one copy (8-bit buckets) or eight (7-bit buckets)");
+constexpr uint32_t kGenEncShift   = kGenEncWays == 1 ? kEncShift : kFastEncShift;
+constexpr uint32_t kGenEncMinKey  = kEncMinBits >> kGenEncShift, kGenEncMaxKey = kEncMaxBits >> kGenEncShift;
+constexpr uint32_t kGenEncEntries = kGenEncWays == 1 ? kEncEntriesPadded : kFastEncEntriesPadded;
+constexpr uint32_t kGenEncStride  = 4u * kGenEncWays;  // bytes per entry
+constexpr uint32_t kGenEncodeMask = 0x10000u - kGenEncStride;
+constexpr uint32_t kGenEncodeAddr = (kGenEncMinKey * kGenEncStride) & kGenEncodeMask;  // window address of the first entry
+static_assert(((kGenEncMaxKey * kGenEncStride) & kGenEncodeMask) == kGenEncodeAddr + (kGenEncMaxKey - kGenEncMinKey) * kGenEncStride,
               "the key range must not wrap inside the 16-bit window");
 constexpr uint32_t kGenSmemBytes  = kGenDecodeAddr + 256u * 256u - kGenWindowBase;
-static_assert(kGenEncodeAddr >= kGenWindowBase && kGenEncodeAddr + kEncEntriesPadded * 4u <= kGenDecodeAddr,
+static_assert(kGenEncodeAddr >= kGenWindowBase && kGenEncodeAddr + kGenEncEntries * kGenEncStride <= kGenDecodeAddr,
               "encode table must fit below the decode table");
 static_assert(kGenEncodeAddr % 16u == 0, "encode table is copied as uint4");
 
@@ -74,8 +90,19 @@ __device__ __forceinline__ void genSrgba8Init(unsigned char* smemRaw, const Devi
     const float4   v4   = make_float4(v, v, v, v);
     d[0] = v4, d[1] = v4, d[2] = v4, d[3] = v4;
   }
-  copyTableWide<kThreads>(reinterpret_cast<uint4*>(encode), reinterpret_cast<const uint4*>(t->encode),
-                          kEncEntriesPadded / 4);
+  if(kGenEncWays == 1)
+    copyTableWide<kThreads>(reinterpret_cast<uint4*>(encode), reinterpret_cast<const uint4*>(t->encode),
+                            kEncEntriesPadded / 4);
+  else
+  {
+    // thread -> (entry, half): 4 of its 8 copies as one 16-byte store
+    uint4* e4 = reinterpret_cast<uint4*>(encode);
+    for(uint32_t i = threadIdx.x; i < kGenEncEntries * 2u; i += kThreads)
+    {
+      const uint32_t v = __ldg(&t->encodeFast[i >> 1]);
+      e4[i]            = make_uint4(v, v, v, v);
+    }
+  }
 }
 
 // linearFromSrgb of byte kByte (0..2) of a packed texel: PRMT builds the absolute shared address
@@ -134,7 +161,9 @@ __device__ __forceinline__ uint32_t genEncChannel(float x)
   // Weighted sums stay below 1 + 2^-8, i.e. inside the table's last bucket (key of 1.0f): only the lower
   // clamp is needed.
   const uint32_t b    = max(__float_as_uint(x), kEncMinBits);
-  const uint32_t addr = (b >> (kEncShift - 2)) & kGenEncodeMask;  // = (4 * key) mod 2^16 = the entry's shared address
+  uint32_t addr = (b >> (kGenEncShift - (kGenEncWays == 1 ? 2 : 5))) & kGenEncodeMask;  // (stride * key) mod 2^16 = the entry's shared address
+  if(kGenEncWays != 1)
+    addr |= (threadIdx.x & 7u) << 2;  // this lane's copy
   uint32_t       e;
   asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(addr));
   return e + b;
