@@ -143,7 +143,11 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     kind, make = _load_cpu_generator()
-    cores = max(1, min(os.cpu_count() or 1, 32))
+    try:
+        cores = len(os.sched_getaffinity(0))  # the host threads this process may actually use
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
+    cores = max(1, min(cores, 256))
     edge = 2048  # per-thread sample image; cores * steps of them stay within a few minutes
     rng = np.random.default_rng(0)
     jobs = [make(rng.integers(0, 256, 4 * edge * edge, dtype=np.uint8), edge, edge) for _ in range(cores)]

@@ -49,6 +49,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "nvpyr.h"
 #include "../vk_compute_mipmaps_b200/csrc/nvpyr_kernels.cuh"
 #include "../vk_compute_mipmaps_b200/csrc/nvpyr_plan.hpp"
@@ -125,14 +129,32 @@ struct UserSet
   __device__ __forceinline__ static Value sharedRound(Value v) { return S::sharedRound(v); }
 };
 
-template <class K>
-inline nvpyrStatus launchOn(K kernel, uint64_t work, int threads, size_t smem, cudaStream_t stream, int smCount,
-                            const void* params)
+// Blocks per SM of a kernel on the current device (and the opt-in to its dynamic shared memory), looked up once per
+// (kernel, device): the two runtime calls cost as much as a small launch.
+inline int blocksPerSm(const void* kernel, int threads, size_t smem, int device)
 {
-  if(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-    return NVPYR_ERROR_CUDA;
+  static std::mutex                                 m;
+  static std::map<std::pair<const void*, int>, int> cache;
+  std::lock_guard<std::mutex>                       lock(m);
+  const auto                                        it = cache.find({kernel, device});
+  if(it != cache.end())
+    return it->second;
   int perSm = 0;
-  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, smem) != cudaSuccess || perSm < 1)
+  if(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess
+     || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, smem) != cudaSuccess)
+    return -1;
+  cache[{kernel, device}] = perSm;
+  return perSm;
+}
+
+template <class K>
+inline nvpyrStatus launchOn(K kernel, uint64_t work, int threads, size_t smem, cudaStream_t stream, int device,
+                            int smCount, const void* params)
+{
+  const int perSm = blocksPerSm(reinterpret_cast<const void*>(kernel), threads, smem, device);
+  if(perSm < 0)
+    return NVPYR_ERROR_CUDA;
+  if(perSm < 1)
     return NVPYR_ERROR_UNSUPPORTED;
   uint64_t grid = uint64_t(perSm) * uint64_t(smCount);
   grid          = grid > work ? work : grid;
@@ -146,9 +168,10 @@ inline nvpyrStatus launchOn(K kernel, uint64_t work, int threads, size_t smem, c
 }
 
 template <class F, int M>
-inline nvpyrStatus launchFastStep(const FastParams& p, cudaStream_t stream, int smCount)
+inline nvpyrStatus launchFastStep(const FastParams& p, cudaStream_t stream, int device, int smCount)
 {
-  return launchOn(fastKernel<F, M, false>, uint64_t(p.tilesX) * p.tilesY, 256, sizeof(FastSmem<F>), stream, smCount, &p);
+  return launchOn(fastKernel<F, M, false>, uint64_t(p.tilesX) * p.tilesY, 256, sizeof(FastSmem<F>), stream, device, smCount,
+                  &p);
 }
 
 }  // namespace detail
@@ -237,13 +260,13 @@ inline nvpyrStatus dispatch(const nvpyrDispatchDesc& desc, const typename S::Par
       {
         case 1:
           st = detail::launchOn(fastKernel1<F>, (uint64_t(p.lv[1].w) * p.lv[1].h + 255u) / 256u, 256, sizeof(FastSmem<F>),
-                                stream, smCount, &p);
+                                stream, device, smCount, &p);
           break;
-        case 2: st = detail::launchFastStep<F, 2>(p, stream, smCount); break;
-        case 3: st = detail::launchFastStep<F, 3>(p, stream, smCount); break;
-        case 4: st = detail::launchFastStep<F, 4>(p, stream, smCount); break;
-        case 5: st = detail::launchFastStep<F, 5>(p, stream, smCount); break;
-        default: st = detail::launchFastStep<F, 6>(p, stream, smCount); break;
+        case 2: st = detail::launchFastStep<F, 2>(p, stream, device, smCount); break;
+        case 3: st = detail::launchFastStep<F, 3>(p, stream, device, smCount); break;
+        case 4: st = detail::launchFastStep<F, 4>(p, stream, device, smCount); break;
+        case 5: st = detail::launchFastStep<F, 5>(p, stream, device, smCount); break;
+        default: st = detail::launchFastStep<F, 6>(p, stream, device, smCount); break;
       }
     }
     else
@@ -259,7 +282,8 @@ inline nvpyrStatus dispatch(const nvpyrDispatchDesc& desc, const typename S::Par
       p.tilesX            = (o.w + t - 1u) / t;
       p.tilesY            = (o.h + t - 1u) / t;
       p.tables            = tables;
-      st = detail::launchOn(generalKernel<F>, uint64_t(p.tilesX) * p.tilesY, 256, sizeof(GeneralSmem<F>), stream, smCount, &p);
+      st = detail::launchOn(generalKernel<F>, uint64_t(p.tilesX) * p.tilesY, 256, sizeof(GeneralSmem<F>), stream, device,
+                            smCount, &p);
     }
     if(st != NVPYR_SUCCESS)
       return st;
