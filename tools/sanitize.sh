@@ -44,3 +44,5 @@ for tail in 262144 0; do
   echo "== $TOOL NVPYR_TAIL_MAX_TEXELS=$tail"
   NVPYR_HOST_BAND_BYTES=131072 NVPYR_TAIL_MAX_TEXELS=$tail compute-sanitizer --tool $TOOL --kernel-regex kns=nvpyr --print-limit 20 python /tmp/san_driver.py 2>&1 | tail -6
 done
+echo "== $TOOL examples/custom_functors (user-defined functor sets through include/nvpyr.cuh)"
+compute-sanitizer --tool $TOOL --print-limit 20 ./examples/custom_functors 2>&1 | tail -4
