@@ -153,6 +153,27 @@ typedef struct nvpyrDispatchDesc
 
 NVPYR_API nvpyrStatus nvpyrDispatchEx(const nvpyrDispatchDesc* desc);
 
+/* The 7-argument overload of nvproCmdPyramidDispatch (dispatch.hpp:109-116): the caller supplies the dispatcher
+ * callbacks that decide, dispatch by dispatch, which pipeline runs and how many levels it fills.
+ *   nvpyrPyramidState = NvproPyramidState (dispatch.hpp:63-75); remainingLevels is never 0 when a callback is called.
+ *   nvpyrDispatcher   = nvpro_pyramid_dispatcher_t (dispatch.hpp:99-104) without the Vulkan arguments: returns the
+ *                       number of levels filled from `state` (the fast dispatcher may return 0 = "not eligible",
+ *                       the general one never); it may fill step->workgroups / step->pushConstant (informational).
+ * general == NULL: nvproPyramidDefaultGeneralDispatcher.  fast == NULL: the default fast dispatcher selected by
+ * desc->fastDivisibility / fastMaxLevels, or none with NVPYR_FLAG_FORCE_GENERAL.  Limits of the kernels, checked
+ * before anything is enqueued (NVPYR_ERROR_INVALID_VALUE): a fast dispatch fills 1..6 levels and both edges of its
+ * input level are multiples of 2^levels; a general dispatch fills 1 or 2 levels; a dispatcher that fills 0 levels
+ * (general) or more than remain is the reference's assert (dispatch.hpp:169,172).  Callbacks run on the calling
+ * thread, inside this call, and may be called more than once per state (validation, then execution): like the
+ * reference's dispatchers they must be pure functions of the state. */
+typedef struct nvpyrPyramidState
+{
+  uint32_t currentLevel, remainingLevels, currentX, currentY;
+} nvpyrPyramidState;
+typedef uint32_t (*nvpyrDispatcher)(const nvpyrPyramidState* state, nvpyrPlanStep* step, void* userData);
+NVPYR_API nvpyrStatus nvpyrDispatchWithDispatchers(const nvpyrDispatchDesc* desc, nvpyrDispatcher general,
+                                                   nvpyrDispatcher fast, void* userData);
+
 /* Independent images (no data crosses images or GPUs); descs[i].stream is honoured. */
 NVPYR_API nvpyrStatus nvpyrDispatchBatch(const nvpyrDispatchDesc* descs, uint32_t count);
 

@@ -519,6 +519,65 @@ def test_recorded_once_replayed_per_frame(nv, cuda, oracle, size):
         assert_same(buf.cpu().numpy(), want, w, h, oracle, f"graph replay {frame}")
 
 
+def _fast_dispatcher(div, max_levels):
+    """nvproPyramidDefaultFastDispatcher<div, max_levels> (nvpro_pyramid_dispatch.hpp:195-242) written in Python."""
+    def f(state, step):
+        if state.currentX % div or state.currentY % div:
+            return 0
+        n = 0
+        while n < min(state.remainingLevels, max_levels) and not ((state.currentX >> n) & 1) and not ((state.currentY >> n) & 1):
+            n += 1
+        return n
+    return f
+
+
+def test_user_dispatcher_callbacks(nv, cuda, oracle):
+    """nvproCmdPyramidDispatch's 7-argument overload (nvpro_pyramid_dispatch.hpp:109-116) through
+    nvpyrDispatchWithDispatchers: user callbacks decide pipeline and level count per dispatch.  Callbacks that
+    restate the default dispatchers and the <2, 5> alternative must give the oracle's chains for those schedules; a
+    general dispatcher that fills one level per dispatch must equal level-by-level generation; bad dispatchers are
+    rejected before anything is enqueued."""
+    def run(w, h, l0, general=None, fast=None, flags=0):
+        buf = cuda.zeros(nv.chain_bytes(w, h), dtype=cuda.uint8, device="cuda")
+        buf[:4 * w * h] = cuda.from_numpy(l0).cuda()
+        nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(), w, h, 0, general, fast, image=buf, flags=flags)
+        cuda.cuda.synchronize()
+        return buf.cpu().numpy()
+
+    general2 = lambda state, step: min(2, state.remainingLevels)
+    for (w, h) in [(1024, 512), (260, 260), (333, 201), (1920, 1080)]:
+        l0 = _oracle.random_level0(w, h, 21)
+        want, _ = oracle.shader_chain(l0, w, h)
+        assert_same(run(w, h, l0, general2, _fast_dispatcher(4, 6)), want, w, h, oracle, "default dispatchers restated")
+        want25, _ = oracle.shader_chain(l0, w, h, div=2, max_levels=5)
+        assert_same(run(w, h, l0, None, _fast_dispatcher(2, 5)), want25, w, h, oracle, "fast <2, 5> callback")
+        wantg, _ = oracle.shader_chain(l0, w, h, force_general=True)
+        assert_same(run(w, h, l0, general2, lambda s, st: 0), wantg, w, h, oracle, "fast callback never eligible")
+
+    # one level per general dispatch == generating level k+1 from level k with separate two-level-count dispatches
+    w, h = 333, 201
+    l0 = _oracle.random_level0(w, h, 22)
+    got = run(w, h, l0, lambda s, st: 1, None, flags=nv.FLAG_FORCE_GENERAL)
+    buf = cuda.zeros(nv.chain_bytes(w, h), dtype=cuda.uint8, device="cuda")
+    buf[:4 * w * h] = cuda.from_numpy(l0).cuda()
+    n = nv.level_count(w, h)
+    for k in range(n - 1):
+        lw, lh = nv.level_extent(w, h, k)
+        ptrs = [buf.data_ptr() + 4 * nv.level_offset_texels(w, h, k + i) for i in range(2)]
+        nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(fast_pipeline=False), lw, lh, 2, image=None, level_ptrs=ptrs)
+    cuda.cuda.synchronize()
+    assert_same(got, buf.cpu().numpy(), w, h, oracle, "one level per dispatch")
+
+    # rejected plans: general fills nothing / too much, fast promises levels the size does not allow, 3-level general
+    before = nv.launch_count()
+    for general, fast in ((lambda s, st: 0, None), (lambda s, st: s.remainingLevels + 1, None),
+                          (None, lambda s, st: min(3, s.remainingLevels)), (lambda s, st: min(3, s.remainingLevels), lambda s, st: 0)):
+        with pytest.raises(nv.NvpyrError) as e:
+            run(333, 201, l0, general, fast)
+        assert e.value.status == 1  # NVPYR_ERROR_INVALID_VALUE
+    assert nv.launch_count() == before
+
+
 def test_other_stream(nv, cuda, oracle):
     w, h = 320, 192
     l0 = _oracle.random_level0(w, h, 13)

@@ -29,6 +29,11 @@ class PlanStep(C.Structure):
         "workgroups", "pushConstant", "bindPipeline", "barrierAfter")]
 
 
+class PyramidState(C.Structure):
+    """NvproPyramidState (nvpro_pyramid_dispatch.hpp:63-75)."""
+    _fields_ = [(n, C.c_uint32) for n in ("currentLevel", "remainingLevels", "currentX", "currentY")]
+
+
 class PlanOptions(C.Structure):
     _fields_ = [("flags", C.c_uint32), ("fastDivisibility", C.c_uint32), ("fastMaxLevels", C.c_uint32)]
 
@@ -49,6 +54,10 @@ class DispatchDesc(C.Structure):
     ]
 
 
+# nvpro_pyramid_dispatcher_t without the Vulkan arguments: levels filled = f(state*, step*, userData)
+Dispatcher = C.CFUNCTYPE(C.c_uint32, C.POINTER(PyramidState), C.POINTER(PlanStep), C.c_void_p)
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -64,6 +73,7 @@ def _load():
         "nvpyrGetPlan": (st, [Extent2D, u32, C.POINTER(PlanOptions), C.POINTER(PlanStep), u32, C.POINTER(u32)]),
         "nvpyrDispatch": (st, [vp, u32, Extent2D, vp]),
         "nvpyrDispatchEx": (st, [C.POINTER(DispatchDesc)]),
+        "nvpyrDispatchWithDispatchers": (st, [C.POINTER(DispatchDesc), Dispatcher, Dispatcher, vp]),
         "nvpyrDispatchBatch": (st, [C.POINTER(DispatchDesc), u32]),
         "nvpyrPremultiplyAlpha": (st, [vp, vp, u64, vp]),
         "nvpyrGenerateHost": (st, [vp, vp, Extent2D, u32, C.c_int, u32]),

@@ -560,8 +560,9 @@ struct ResolvedDesc
   nvpyrFormat  format;
   uint32_t     flags, w, h, levels, texelBytes;
   LevelView    lv[NVPYR_MAX_LEVELS];
-  dispatcher_t fast;
-  cudaStream_t stream;
+  DispatcherRef general = defaultGeneralDispatcher, fast;
+  bool          customDispatchers = false;  // nvpyrDispatchWithDispatchers: plan limits are checked, no fused paths
+  cudaStream_t  stream;
 };
 
 nvpyrStatus resolve(const nvpyrDispatchDesc* d, ResolvedDesc& r)
@@ -590,7 +591,7 @@ nvpyrStatus resolve(const nvpyrDispatchDesc* d, ResolvedDesc& r)
   if(!(d->flags & NVPYR_FLAG_FORCE_GENERAL))
   {
     r.fast = selectFastDispatcher(d->fastDivisibility, d->fastMaxLevels);
-    if(r.fast == nullptr)
+    if(!r.fast)
       return NVPYR_ERROR_UNSUPPORTED;
   }
   uint64_t off = 0;
@@ -691,7 +692,7 @@ template <class F>
 nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0, bool premulFirst = false)
 {
   nvpyrPlanStep steps[NVPYR_MAX_STEPS];
-  const int     n = buildPlan(r.w, r.h, r.levels, defaultGeneralDispatcher, r.fast, steps, NVPYR_MAX_STEPS);
+  const int     n = buildPlan(r.w, r.h, r.levels, r.general, r.fast, steps, NVPYR_MAX_STEPS);
   if(n < 0)
     return NVPYR_ERROR_INVALID_VALUE;
   auto texels = [&](int i) { return uint64_t(steps[i].srcWidth) * steps[i].srcHeight; };
@@ -738,10 +739,10 @@ nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0
 // (tiles never overlap, so rewriting level 0 in place is safe; the general pipeline re-reads halo columns).
 bool canFusePremultiply(const ResolvedDesc& r)
 {
-  if(r.format != NVPYR_FORMAT_SRGBA8 || r.levels < 2 || r.fast == nullptr || (r.flags & NVPYR_FLAG_F16_SHARED))
+  if(r.format != NVPYR_FORMAT_SRGBA8 || r.levels < 2 || !r.fast || (r.flags & NVPYR_FLAG_F16_SHARED))
     return false;
   nvpyrPlanStep steps[NVPYR_MAX_STEPS];
-  const int     n = buildPlan(r.w, r.h, r.levels, defaultGeneralDispatcher, r.fast, steps, NVPYR_MAX_STEPS);
+  const int     n = buildPlan(r.w, r.h, r.levels, r.general, r.fast, steps, NVPYR_MAX_STEPS);
   if(n < 1 || steps[0].pipeline != 1 || steps[0].levelCount < 2)
     return false;
   if(!g_noTailFusion && uint64_t(steps[0].srcWidth) * steps[0].srcHeight <= kTailMaxTexels)
@@ -799,7 +800,7 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
   const ResolvedDesc& a     = r[0];
   const uint32_t      count = uint32_t(r.size());
   if(count < 2 || count > kBatchRing / 4 || a.format != NVPYR_FORMAT_SRGBA8 || a.levels < 2 || g_forceGenericFast
-     || g_noTailFusion || a.fast == nullptr || (a.flags & NVPYR_FLAG_F16_SHARED))
+     || g_noTailFusion || !a.fast || a.customDispatchers || (a.flags & NVPYR_FLAG_F16_SHARED))
     return NVPYR_SUCCESS;
   for(const ResolvedDesc& d : r)
   {
@@ -812,7 +813,7 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
         return NVPYR_SUCCESS;
   }
   nvpyrPlanStep steps[NVPYR_MAX_STEPS];
-  const int     n = buildPlan(a.w, a.h, a.levels, defaultGeneralDispatcher, a.fast, steps, NVPYR_MAX_STEPS);
+  const int     n = buildPlan(a.w, a.h, a.levels, a.general, a.fast, steps, NVPYR_MAX_STEPS);
   if(n < 1)
     return NVPYR_SUCCESS;
   auto texels = [&](int i) { return uint64_t(steps[i].srcWidth) * steps[i].srcHeight; };
@@ -944,7 +945,7 @@ nvpyrStatus generateHostPipelined(DeviceContext& ctx, const ResolvedDesc& r, con
   const bool           level0Back = premul || hostChain != hostLevel0;
 
   nvpyrPlanStep steps[NVPYR_MAX_STEPS];
-  const int     n = r.levels > 1 ? buildPlan(r.w, r.h, r.levels, defaultGeneralDispatcher, r.fast, steps, NVPYR_MAX_STEPS) : 0;
+  const int     n = r.levels > 1 ? buildPlan(r.w, r.h, r.levels, r.general, r.fast, steps, NVPYR_MAX_STEPS) : 0;
   if(n < 0)
     return NVPYR_ERROR_INVALID_VALUE;
 
@@ -1095,6 +1096,47 @@ nvpyrStatus nvpyrDispatchEx(const nvpyrDispatchDesc* desc)
 {
   ResolvedDesc r;
   nvpyrStatus  st = resolve(desc, r);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  return dispatchResolved(r);
+}
+
+// Limits of the kernels for a plan made by user dispatchers (the defaults satisfy them by construction).
+nvpyrStatus checkCustomPlan(const ResolvedDesc& r)
+{
+  nvpyrPlanStep steps[NVPYR_MAX_STEPS];
+  const int     n = r.levels > 1 ? buildPlan(r.w, r.h, r.levels, r.general, r.fast, steps, NVPYR_MAX_STEPS) : 0;
+  if(n < 0)
+    return NVPYR_ERROR_INVALID_VALUE;  // 0 levels, more levels than remain, or too many dispatches
+  for(int i = 0; i < n; ++i)
+  {
+    const nvpyrPlanStep& s = steps[i];
+    if(s.pipeline == 1)
+    {
+      if(s.levelCount < 1 || s.levelCount > 6 || ((s.srcWidth | s.srcHeight) & ((1u << s.levelCount) - 1u)))
+        return NVPYR_ERROR_INVALID_VALUE;
+    }
+    else if(s.levelCount < 1 || s.levelCount > 2)
+      return NVPYR_ERROR_INVALID_VALUE;
+  }
+  return NVPYR_SUCCESS;
+}
+
+nvpyrStatus nvpyrDispatchWithDispatchers(const nvpyrDispatchDesc* desc, nvpyrDispatcher general, nvpyrDispatcher fast,
+                                         void* userData)
+{
+  ResolvedDesc r;
+  nvpyrStatus  st = resolve(desc, r);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  if(general != nullptr)
+    r.general = DispatcherRef(general, userData);
+  if(fast != nullptr && !(r.flags & NVPYR_FLAG_FORCE_GENERAL))
+    r.fast = DispatcherRef(fast, userData);
+  r.customDispatchers = general != nullptr || fast != nullptr;
+  // The callbacks are called once here (validation) and once more when the plan is executed: like the reference's,
+  // they must be pure functions of the state they are given.
+  st = checkCustomPlan(r);
   if(st != NVPYR_SUCCESS)
     return st;
   return dispatchResolved(r);

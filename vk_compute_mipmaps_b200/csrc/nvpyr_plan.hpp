@@ -87,10 +87,33 @@ inline uint32_t defaultGeneralDispatcher(const PyramidState& s, nvpyrPlanStep& s
 // with "record" replaced by "append to steps[]".  fast == nullptr means the fast
 // pipeline is unavailable.  Returns the number of steps, or -1 on overflow / bad
 // arguments / a dispatcher that violates its contract.
-inline int buildPlan(uint32_t baseWidth, uint32_t baseHeight, uint32_t mipLevels, dispatcher_t general,
-                     dispatcher_t fast, nvpyrPlanStep* steps, uint32_t maxSteps)
+// A dispatcher callback in either form: a C++ function (the defaults above, nvpyr.cuh users) or the C ABI's
+// nvpyrDispatcher + user data (nvpyrDispatchWithDispatchers).
+struct DispatcherRef
 {
-  if(baseWidth == 0 || baseHeight == 0 || general == nullptr)
+  dispatcher_t    fn   = nullptr;
+  nvpyrDispatcher cfn  = nullptr;
+  void*           user = nullptr;
+  DispatcherRef() = default;
+  DispatcherRef(dispatcher_t f) : fn(f) {}
+  DispatcherRef(decltype(nullptr)) {}
+  DispatcherRef(nvpyrDispatcher f, void* u) : cfn(f), user(u) {}
+  explicit operator bool() const { return fn != nullptr || cfn != nullptr; }
+  bool     operator==(const DispatcherRef& o) const { return fn == o.fn && cfn == o.cfn && user == o.user; }
+  bool     operator!=(const DispatcherRef& o) const { return !(*this == o); }
+  uint32_t operator()(const PyramidState& s, nvpyrPlanStep& step) const
+  {
+    if(fn != nullptr)
+      return fn(s, step);
+    const nvpyrPyramidState cs{s.currentLevel, s.remainingLevels, s.currentX, s.currentY};
+    return cfn(&cs, &step, user);
+  }
+};
+
+inline int buildPlan(uint32_t baseWidth, uint32_t baseHeight, uint32_t mipLevels, const DispatcherRef& general,
+                     const DispatcherRef& fast, nvpyrPlanStep* steps, uint32_t maxSteps)
+{
+  if(baseWidth == 0 || baseHeight == 0 || !general)
     return -1;
   if(mipLevels == 0)
     mipLevels = levelCountFor(baseWidth, baseHeight);

@@ -16,8 +16,8 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import (FLAG_F16_SHARED, FLAG_FORCE_GENERAL, FLAG_NONE, FLAG_PREMULTIPLY_ALPHA, FORMAT_RGBA32F, FORMAT_SRGBA8, DispatchDesc,
-                   Extent2D, NvpyrError, PlanOptions, PlanStep, check, lib)
+from ._lib import (FLAG_F16_SHARED, FLAG_FORCE_GENERAL, FLAG_NONE, FLAG_PREMULTIPLY_ALPHA, FORMAT_RGBA32F, FORMAT_SRGBA8, Dispatcher,
+                   DispatchDesc, Extent2D, NvpyrError, PlanOptions, PlanStep, check, lib)
 
 __all__ = [
     "PyramidPipelines", "cmd_pyramid_dispatch", "dispatch_batch", "level_count", "level_extent", "level_offset_texels",
@@ -120,12 +120,15 @@ def _make_desc(image, pipelines, base_width, base_height, mip_levels, flags, str
     return d
 
 
-def cmd_pyramid_dispatch(stream, pipelines, base_width, base_height, mip_levels=0, *, image, flags=FLAG_NONE,
-                         level_ptrs=None, pitches=None):
-    """nvproCmdPyramidDispatch(cmdBuf, pipelines, baseWidth, baseHeight, mipLevels).
+def cmd_pyramid_dispatch(stream, pipelines, base_width, base_height, mip_levels=0, general_dispatcher=None,
+                         fast_dispatcher=None, *, image, flags=FLAG_NONE, level_ptrs=None, pitches=None):
+    """nvproCmdPyramidDispatch(cmdBuf, pipelines, baseWidth, baseHeight, mipLevels[, generalDispatcher,
+    fastDispatcher]) -- both overloads (dispatch.hpp:54-59 and :109-116).
 
     Enqueues on ``stream`` (None = torch's current stream) the generation of mip
     levels 1..mip_levels-1 of ``image`` (packed chain, level 0 filled) from level 0.
+    general_dispatcher / fast_dispatcher: Python callables ``f(state, step) -> levels filled`` with the contract of
+    nvpro_pyramid_dispatcher_t (state: currentLevel, remainingLevels, currentX, currentY; fast may return 0).
     """
     if image is not None and hasattr(image, "numel"):
         need = chain_bytes(base_width, base_height, mip_levels, pipelines.format)
@@ -133,7 +136,16 @@ def cmd_pyramid_dispatch(stream, pipelines, base_width, base_height, mip_levels=
         if have < need:
             raise ValueError(f"image buffer holds {have} bytes, the chain needs {need}")
     d = _make_desc(image, pipelines, base_width, base_height, mip_levels, flags, stream, level_ptrs, pitches)
-    check(lib.nvpyrDispatchEx(C.byref(d)), "nvpyrDispatchEx")
+    if general_dispatcher is None and fast_dispatcher is None:
+        check(lib.nvpyrDispatchEx(C.byref(d)), "nvpyrDispatchEx")
+        return
+
+    def wrap(f):
+        if f is None:
+            return Dispatcher()  # NULL: the default
+        return Dispatcher(lambda state, step, _user: int(f(state.contents, step.contents)))
+    g, f = wrap(general_dispatcher), wrap(fast_dispatcher)  # kept alive until the call returns
+    check(lib.nvpyrDispatchWithDispatchers(C.byref(d), g, f, None), "nvpyrDispatchWithDispatchers")
 
 
 def dispatch_batch(stream, pipelines, images, base_width, base_height, mip_levels=0, flags=FLAG_NONE):
