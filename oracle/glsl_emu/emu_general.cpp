@@ -6,7 +6,18 @@
 namespace emu_general {
 #define float Float
 #define NVPRO_PYRAMID_IS_FAST_PIPELINE 0
+#if defined(SRGB_SHARED) && SRGB_SHARED
+#undef in
+#define in  // parameter qualifiers of srgbUnpack / srgbPack (preamble.glsl:81,91)
+#define out
+#endif
 #include "nvpro_pyramid/srgba8_mipmap_preamble.glsl"
+#if defined(SRGB_SHARED) && SRGB_SHARED
+#undef in
+#undef out
+#define in int emuLocalSizeDecl_
+#include "emu_srgb_shared_glue.inc"
+#endif
 #include "nvpro_pyramid/nvpro_pyramid.glsl"
 #undef float
 void mainEntry() { nvproPyramidMain(); }

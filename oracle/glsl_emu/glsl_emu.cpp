@@ -24,6 +24,11 @@ void emuFastMainF16();
 void emuGeneralMainF16();
 void emuFastSetImageF16(const uimage2D* levels);
 void emuGeneralSetImageF16(const uimage2D* levels);
+// ... and with SRGB_SHARED = 1 (emu_fast_srgb.cpp, emu_general_srgb.cpp)
+void emuFastMainSrgb();
+void emuGeneralMainSrgb();
+void emuFastSetImageSrgb(const uimage2D* levels);
+void emuGeneralSetImageSrgb(const uimage2D* levels);
 uint emuGlslSrgbFromLinear(float x);
 
 EmuInvocation* g_emuCur          = nullptr;
@@ -128,7 +133,7 @@ int            g_bound = -1;  // 0 general, 1 fast
 MockPipeline_T* kGeneral = reinterpret_cast<MockPipeline_T*>(0x1000);
 MockPipeline_T* kFast    = reinterpret_cast<MockPipeline_T*>(0x2000);
 uint           g_dispatches = 0;
-bool           g_f16Shared  = false;  // which build of the shaders the mock pipelines stand for
+int            g_sharedMode = 0;  // which build of the shaders the mock pipelines stand for: 0 default, 1 F16_SHARED, 2 SRGB_SHARED
 }  // namespace
 void vkCmdBindPipeline(VkCommandBuffer, VkPipelineBindPoint, VkPipeline p) { g_bound = p == kFast ? 1 : 0; }
 void vkCmdPushConstants(VkCommandBuffer, VkPipelineLayout, VkShaderStageFlags, uint32_t, uint32_t size, const void* v)
@@ -140,7 +145,8 @@ void vkCmdDispatch(VkCommandBuffer, uint32_t x, uint32_t, uint32_t)
   ++g_dispatches;
   for(uint32_t wg = 0; wg < x; ++wg)
     runWorkgroup(wg, g_bound == 1 ? 256u : 128u,
-                 g_bound == 1 ? (g_f16Shared ? emuFastMainF16 : emuFastMain) : (g_f16Shared ? emuGeneralMainF16 : emuGeneralMain));
+                 g_bound == 1 ? (g_sharedMode == 1 ? emuFastMainF16 : g_sharedMode == 2 ? emuFastMainSrgb : emuFastMain)
+                              : (g_sharedMode == 1 ? emuGeneralMainF16 : g_sharedMode == 2 ? emuGeneralMainSrgb : emuGeneralMain));
 }
 void vkCmdPipelineBarrier(VkCommandBuffer, VkPipelineStageFlags, VkPipelineStageFlags, VkDependencyFlags, uint32_t,
                           const VkMemoryBarrier*, uint32_t, const VkBufferMemoryBarrier*, uint32_t,
@@ -157,11 +163,11 @@ int emu_run_chain(uint8_t* chain, uint32_t w, uint32_t h, uint32_t mipLevels, ui
 {
   return emu_run_chain_ex(chain, w, h, mipLevels, haveFast, 0, stores);
 }
-// f16Shared != 0: the F16_SHARED build of both shaders.
+// f16Shared = 1: the F16_SHARED build of both shaders; 2: the SRGB_SHARED build.
 int emu_run_chain_ex(uint8_t* chain, uint32_t w, uint32_t h, uint32_t mipLevels, uint32_t haveFast, uint32_t f16Shared,
                      uint64_t* stores)
 {
-  g_f16Shared = f16Shared != 0;
+  g_sharedMode = int(f16Shared);
   uint32_t levels = mipLevels;
   if(levels == 0)
     for(uint32_t a = w, b = h; a != 0 || b != 0; a >>= 1, b >>= 1)
@@ -188,6 +194,8 @@ int emu_run_chain_ex(uint8_t* chain, uint32_t w, uint32_t h, uint32_t mipLevels,
   emuGeneralSetImage(imageMipLevels_shared);
   emuFastSetImageF16(imageMipLevels_shared);
   emuGeneralSetImageF16(imageMipLevels_shared);
+  emuFastSetImageSrgb(imageMipLevels_shared);
+  emuGeneralSetImageSrgb(imageMipLevels_shared);
   g_emuStores           = 0;
   g_dispatches          = 0;
   g_bound               = -1;

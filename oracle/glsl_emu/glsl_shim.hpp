@@ -107,6 +107,25 @@ inline vec4 operator+(const vec4& c, const Prod& p)
 }
 inline vec4 operator+(const Prod& p, const Prod& q) { return vec4(p) + q; }
 
+// packUnorm4x8 / unpackUnorm4x8 (used by the SRGB_SHARED build of the preamble): GLSL 4.60 section 8.4 --
+// pack: round(clamp(c, 0, +1) * 255.0), component x in the least significant byte; unpack: byte / 255.0.
+// The direction of round()'s ties is implementation-defined in GLSL; pinned here as round-half-even.
+inline uint packUnorm4x8(const vec4& v)
+{
+  auto q = [](Float c) {
+    float s = c.v < 0.f ? 0.f : (c.v > 1.f ? 1.f : c.v);
+    if(!(c.v == c.v))
+      s = 0.f;
+    return uint(rintf(s * 255.0f));
+  };
+  return q(v.x) | (q(v.y) << 8) | (q(v.z) << 16) | (q(v.w) << 24);
+}
+inline vec4 unpackUnorm4x8(uint p)
+{
+  return vec4(Float(p & 255u) / Float(255.0), Float((p >> 8) & 255u) / Float(255.0), Float((p >> 16) & 255u) / Float(255.0),
+              Float(p >> 24) / Float(255.0));
+}
+
 // ------------------------------------------------------------------ resources
 struct uimage2D
 {

@@ -306,13 +306,52 @@ typedef struct
   uint32_t lw[33], lh[33];
   uint64_t stores; /* number of NVPRO_PYRAMID_STORE executed */
   int      shared_f16; /* F16_SHARED build of the shaders (srgba8_mipmap_preamble.glsl:103-108) */
+  int      shared_srgb; /* SRGB_SHARED build (srgba8_mipmap_preamble.glsl:60-101) */
 } actx;
 
 /* NVPRO_PYRAMID_SHARED_STORE followed by NVPRO_PYRAMID_SHARED_LOAD.  Default: the shared type is the value
  * type (nvpro_pyramid.glsl:204-206).  F16_SHARED: f16vec4(in_) then vec4(smem_), i.e. every component is
  * rounded to IEEE binary16 (round to nearest even) and widened again. */
+/* SRGB_SHARED: srgbPack then srgbUnpack (srgba8_mipmap_preamble.glsl:81-99).  packUnorm4x8 of
+ * srgbComponentFromLinear(x) == number of pinned SHARED thresholds <= x (monotone, checked exhaustively by
+ * tools/gen_srgb_tables.c); unpackUnorm4x8 + linearFromSrgbComponent == the pinned SHARED decode table.  Alpha:
+ * round-half-even(clamp(a, 0, 1) * 255) and code / 255.0 (IEEE division). */
+uint32_t nvo_srgb_shared_pack(float x)
+{
+  uint32_t lo = 0, hi = 255;
+  if(!(x == x))
+    return 0;
+  while(lo < hi)
+  {
+    uint32_t mid = (lo + hi + 1) >> 1;
+    if(x >= bits_to_float(NVPYR_SRGB_SHARED_ENCODE_THRESHOLD_BITS[mid - 1]))
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+float nvo_srgb_shared_unpack(uint32_t code)
+{
+  return bits_to_float(NVPYR_SRGB_SHARED_DECODE_BITS[code > 255u ? 255u : code]);
+}
+static inline float a_unorm8_round_trip(float a)
+{
+  float s = a < 0.f ? 0.f : (a > 1.f ? 1.f : a);
+  if(!(a == a))
+    s = 0.f;
+  return rintf(s * 255.0f) / 255.0f;
+}
+
 static inline vec4 a_shared_round(const actx* c, vec4 v)
 {
+  if(c->shared_srgb)
+  {
+    v.x = nvo_srgb_shared_unpack(nvo_srgb_shared_pack(v.x));
+    v.y = nvo_srgb_shared_unpack(nvo_srgb_shared_pack(v.y));
+    v.z = nvo_srgb_shared_unpack(nvo_srgb_shared_pack(v.z));
+    v.w = a_unorm8_round_trip(v.w);
+  }
   if(c->shared_f16)
   {
     v.x = (float)(_Float16)v.x, v.y = (float)(_Float16)v.y;
@@ -841,7 +880,7 @@ static void a_general_workgroup(actx* c, uint32_t wg, uint32_t pc)
 }
 
 /* Whole chain in shader order.  fmt 0: chain = uint8 RGBA; fmt 1: float RGBA.
- * flags bit0: force general pipeline (no fast pipeline available); bit1: F16_SHARED build.
+ * flags bit0: force general pipeline (no fast pipeline available); bit1: F16_SHARED build; bit2: SRGB_SHARED build.
  * Returns number of dispatches, <0 on error.  stores_out (optional) receives
  * the number of texel stores executed (coverage accounting). */
 int nvo_shader_chain(int fmt, void* chain, uint32_t w, uint32_t h, uint32_t mip_levels, uint32_t flags,
@@ -859,7 +898,8 @@ int nvo_shader_chain(int fmt, void* chain, uint32_t w, uint32_t h, uint32_t mip_
     return n;
   actx c;
   actx_init(&c, fmt, chain, w, h, mip_levels);
-  c.shared_f16 = (flags & 2u) != 0;
+  c.shared_f16  = (flags & 2u) != 0;
+  c.shared_srgb = (flags & 4u) != 0;
   for(int i = 0; i < n; ++i)
   {
     for(uint32_t wg = 0; wg < steps[i].workgroups; ++wg)

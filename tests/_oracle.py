@@ -72,11 +72,14 @@ class Oracle:
         buf[:4 * w * h] = np.asarray(level0, dtype=dt).reshape(-1)
         return buf
 
-    def shader_chain(self, level0, w, h, fmt=0, levels=0, force_general=False, div=4, max_levels=6, f16_shared=False):
-        """Oracle A: chain in shader order. Returns (chain, stores).  f16_shared: the F16_SHARED build."""
+    def shader_chain(self, level0, w, h, fmt=0, levels=0, force_general=False, div=4, max_levels=6, f16_shared=False,
+                     srgb_shared=False):
+        """Oracle A: chain in shader order. Returns (chain, stores).  f16_shared / srgb_shared: the F16_SHARED /
+        SRGB_SHARED builds of the shaders."""
         buf = self.new_chain(level0, w, h, fmt, levels)
         st = C.c_uint64()
-        n = self.lib.nvo_shader_chain(fmt, buf.ctypes.data, w, h, levels, (1 if force_general else 0) | (2 if f16_shared else 0),
+        n = self.lib.nvo_shader_chain(fmt, buf.ctypes.data, w, h, levels,
+                                      (1 if force_general else 0) | (2 if f16_shared else 0) | (4 if srgb_shared else 0),
                                       div, max_levels, C.byref(st))
         assert n >= 0
         return buf, st.value
@@ -167,10 +170,12 @@ class GlslEmu:
         lib.emu_run_chain_ex.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
         lib.emu_glsl_srgb_from_linear.argtypes = [C.c_float]
 
-    def run_chain(self, chain, w, h, levels=0, have_fast=1, f16_shared=0):
+    def run_chain(self, chain, w, h, levels=0, have_fast=1, f16_shared=0, srgb_shared=0):
+        """f16_shared / srgb_shared: run the F16_SHARED / SRGB_SHARED build of the shaders."""
         buf = np.array(chain, dtype=np.uint8, copy=True)
         st = C.c_uint64()
-        n = self.lib.emu_run_chain_ex(buf.ctypes.data, w, h, levels, have_fast, f16_shared, C.byref(st))
+        n = self.lib.emu_run_chain_ex(buf.ctypes.data, w, h, levels, have_fast, 2 if srgb_shared else (1 if f16_shared else 0),
+                                      C.byref(st))
         assert n >= 0, n
         return buf, n, st.value
 

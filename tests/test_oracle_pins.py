@@ -1,6 +1,7 @@
 """Pins the CPU oracle (oracle/nvpyr_oracle.c) to the reference: its own code compiled in
 place (oracle/_ref), its recorded known answers (demo_app/rtx3090.json), and the golden
 fixtures generated from its test images (tools/make_golden.py)."""
+import ctypes as C
 import glob
 import hashlib
 import os
@@ -33,7 +34,7 @@ def test_transfer_thresholds_are_tight(oracle):
     """Each pinned threshold is the FIRST float of its code (formula on both sides of it)."""
     import re
     src = open(os.path.join(_oracle.ROOT, "vk_compute_mipmaps_b200", "csrc", "srgb_tables.inc")).read()
-    body = src.split("NVPYR_SRGB_ENCODE_THRESHOLD_BITS[255]")[1]
+    body = src.split("NVPYR_SRGB_ENCODE_THRESHOLD_BITS[255]")[1].split("};")[0]
     thr = [int(t, 16) for t in re.findall(r"0x([0-9a-f]{8})u", body)]
     assert len(thr) == 255 and thr == sorted(thr)
     f = oracle.lib.nvo_srgb_from_linear_formula
@@ -214,6 +215,48 @@ def test_oracle_a_f16_shared_equals_executed_reference_shaders(oracle, emu, size
         assert differs
 
 
+@pytest.mark.parametrize("size", F16_SIZES, ids=lambda s: f"{s[0]}x{s[1]}")
+def test_oracle_a_srgb_shared_equals_executed_reference_shaders(oracle, emu, size):
+    """The SRGB_SHARED build (srgba8_mipmap_preamble.glsl:60-101, the demo's "srgbShared" alternative): values that
+    pass through shared memory are packed to 8-bit sRGB (packUnorm4x8 of srgbComponentFromLinear) and unpacked again.
+    The reference's shaders compiled with the macro set and executed, against Oracle A's restatement through the
+    pinned SHARED tables (tools/gen_srgb_tables.c).  Must differ from the default build somewhere."""
+    w, h = size
+    differs = False
+    for seed, make in ((1, _oracle.random_level0), (2, lambda w, h, s: _oracle.smooth_level0(w, h, s))):
+        l0 = make(w, h, seed)
+        for have_fast in (1, 0):
+            want, stores = oracle.shader_chain(l0, w, h, force_general=not have_fast, srgb_shared=True)
+            got, _, emu_stores = emu.run_chain(oracle.new_chain(l0, w, h), w, h, 0, have_fast, srgb_shared=1)
+            assert (got == want).all(), (size, have_fast)
+            assert emu_stores == stores
+            differs |= bool((want != oracle.shader_chain(l0, w, h, force_general=not have_fast)[0]).any())
+    if max(w, h) >= 64:
+        assert differs
+
+
+def test_srgb_shared_tables_equal_the_glsl_functions(oracle, emu):
+    """Every code's unpack value and every pack threshold (and its predecessor) of the pinned SHARED tables against the
+    preamble's own linearFromSrgbComponent / srgbComponentFromLinear + packUnorm4x8 / unpackUnorm4x8 as executed."""
+    lib = oracle.lib
+    lib.nvo_srgb_shared_unpack.restype = C.c_float
+    lib.nvo_srgb_shared_unpack.argtypes = [C.c_uint32]
+    lib.nvo_srgb_shared_pack.argtypes = [C.c_float]
+    emu.lib.emu_srgb_shared_round_trip.restype = C.c_float
+    emu.lib.emu_srgb_shared_round_trip.argtypes = [C.c_float, C.POINTER(C.c_uint32)]
+    import re
+    src = open(os.path.join(_oracle.ROOT, "vk_compute_mipmaps_b200", "csrc", "srgb_tables.inc")).read()
+    thr = [int(t, 16) for t in re.findall(r"0x([0-9a-f]{8})u", src.split("NVPYR_SRGB_SHARED_ENCODE_THRESHOLD_BITS[255]")[1].split("};")[0])]
+    assert len(thr) == 255
+    code = C.c_uint32()
+    for c, bits in enumerate(thr, start=1):
+        for b, want in ((bits, c), (bits - 1, c - 1)):
+            x = float(np.array([b], dtype=np.uint32).view(np.float32)[0])
+            back = emu.lib.emu_srgb_shared_round_trip(x, C.byref(code))
+            assert code.value == want == lib.nvo_srgb_shared_pack(x)
+            assert np.float32(back).tobytes() == np.float32(lib.nvo_srgb_shared_unpack(want)).tobytes()
+
+
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_golden_fixtures_through_executed_shaders(oracle, emu, path):
     g = np.load(path)
@@ -228,7 +271,8 @@ def test_glsl_encode_equals_pinned_thresholds(emu):
     thresholds (so the GLSL twin and the C++ twin in shaders/srgb.h agree on every float)."""
     import re
     src = open(os.path.join(_oracle.ROOT, "vk_compute_mipmaps_b200", "csrc", "srgb_tables.inc")).read()
-    thr = [int(t, 16) for t in re.findall(r"0x([0-9a-f]{8})u", src.split("NVPYR_SRGB_ENCODE_THRESHOLD_BITS[255]")[1])]
+    thr = [int(t, 16) for t in re.findall(r"0x([0-9a-f]{8})u", src.split("NVPYR_SRGB_ENCODE_THRESHOLD_BITS[255]")[1].split("};")[0])]
+    assert len(thr) == 255
     f = emu.lib.emu_glsl_srgb_from_linear
     for c, bits in enumerate(thr, start=1):
         at = np.array([bits], dtype=np.uint32).view(np.float32)[0]
