@@ -77,7 +77,11 @@ typedef enum nvpyrFlags
   /* The reference's optional F16_SHARED build of the sRGBA8 shaders (srgba8_mipmap_preamble.glsl:103-108,
    * demo_app alternative "f16Shared"): values that pass through shared memory inside a dispatch are rounded
    * to IEEE binary16.  Non-default and lossy; sRGBA8 only; runs on the functor-template kernels. */
-  NVPYR_FLAG_F16_SHARED = 1u << 2
+  NVPYR_FLAG_F16_SHARED = 1u << 2,
+  /* The reference's optional SRGB_SHARED build (srgba8_mipmap_preamble.glsl:60-101, demo_app alternative
+   * "srgbShared"): values that pass through shared memory inside a dispatch are packed to 8-bit sRGB and unpacked
+   * again.  Non-default and lossy; sRGBA8 only; mutually exclusive with F16_SHARED; functor-template kernels. */
+  NVPYR_FLAG_SRGB_SHARED = 1u << 3
 } nvpyrFlags;
 
 typedef struct CUstream_st* nvpyrStream; /* == cudaStream_t == CUstream */

@@ -294,6 +294,30 @@ def test_f16_shared_variant_bit_exact(nv, cuda, oracle, size):
             gpu_chain(nv, cuda, _oracle.random_level0(64, 64, 1, fmt=1), 64, 64, fmt=1, flags=nv.FLAG_F16_SHARED)
 
 
+@pytest.mark.parametrize("size", [(256, 256), (1024, 512), (96, 160), (32, 32), (260, 260), (255, 255), (511, 300),
+                                  (136, 512), (1920, 1080), (100, 37), (64, 4096)])
+def test_srgb_shared_variant_bit_exact(nv, cuda, oracle, size):
+    """NVPYR_FLAG_SRGB_SHARED = the reference's SRGB_SHARED build of the sRGBA8 shaders (values passing through
+    shared memory inside a dispatch are packed to 8-bit sRGB and unpacked again): bit-exact against Oracle A's
+    restatement, which is pinned by executing the reference's shaders with the macro set
+    (tests/test_oracle_pins.py).  Also with the fast pipeline disabled, through the host round trip, on a smooth
+    image, and rejected for rgba32f and together with F16_SHARED."""
+    w, h = size
+    for l0 in (_oracle.random_level0(w, h, 23), _oracle.smooth_level0(w, h, 5)):
+        for fg in (False, True):
+            want, _ = oracle.shader_chain(l0, w, h, force_general=fg, srgb_shared=True)
+            got = gpu_chain(nv, cuda, l0, w, h, pipelines=nv.PyramidPipelines(fast_pipeline=not fg), flags=nv.FLAG_SRGB_SHARED)
+            assert_same(got, want, w, h, oracle, f"srgb shared, force_general={fg}")
+    want, _ = oracle.shader_chain(l0, w, h, srgb_shared=True)
+    assert (nv.generate_host(l0, w, h, flags=nv.FLAG_SRGB_SHARED) == want).all()
+    if size == (256, 256):
+        assert (want != oracle.shader_chain(l0, w, h)[0]).any()
+        with pytest.raises(nv.NvpyrError):
+            gpu_chain(nv, cuda, _oracle.random_level0(64, 64, 1, fmt=1), 64, 64, fmt=1, flags=nv.FLAG_SRGB_SHARED)
+        with pytest.raises(nv.NvpyrError):
+            gpu_chain(nv, cuda, l0, w, h, flags=nv.FLAG_SRGB_SHARED | nv.FLAG_F16_SHARED)
+
+
 def test_partial_level_count(nv, cuda, oracle):
     w, h = 256, 256
     l0 = _oracle.random_level0(w, h, 6)

@@ -13,9 +13,9 @@ Images: the reference's 13 test images are not redistributable with this repo an
 each is replaced by a synthetic image of the same size and alpha class (smooth colour fields plus noise; alpha images
 get a varying alpha channel and are premultiplied like mipmaps_app.cpp:606 does).  With --images DIR the real files
 are used (needs PIL).  Alternatives: those of demo_app/pipeline_alternative.cpp that this library offers --
-default, generalonly (no fast pipeline), levels_1_5 / levels_1_6 (fast dispatcher <2,5> / <2,6>), f16Shared,
+default, generalonly (no fast pipeline), levels_1_5 / levels_1_6 (fast dispatcher <2,5> / <2,6>), f16Shared, srgbShared,
 noBilinear (= default here: the software 4-tap first reduction is the only one).  blit / generalblit / onelevel /
-levels_1_3 / levels_3_3 / workgroup1024 / srgbShared are not offered and are left out.
+levels_1_3 / levels_3_3 / workgroup1024 are not offered and are left out.
 This tool is bench/test infrastructure: it is the one place outside tests/ and bench.py that calls oracle/.
 """
 import argparse, json, os, sys
@@ -36,7 +36,8 @@ IMAGES = [  # name, w, h, has alpha   (test_images/, docs/test_images.txt)
 ]
 ALTERNATIVES = [  # label, flags, fast divisibility, fast max levels
     ("default", nv.FLAG_NONE, 0, 0), ("generalonly", nv.FLAG_FORCE_GENERAL, 0, 0), ("levels_1_5", nv.FLAG_NONE, 2, 5),
-    ("levels_1_6", nv.FLAG_NONE, 2, 6), ("f16Shared", nv.FLAG_F16_SHARED, 0, 0), ("noBilinear", nv.FLAG_NONE, 0, 0),
+    ("levels_1_6", nv.FLAG_NONE, 2, 6), ("srgbShared", nv.FLAG_SRGB_SHARED, 0, 0), ("f16Shared", nv.FLAG_F16_SHARED, 0, 0),
+    ("noBilinear", nv.FLAG_NONE, 0, 0),
 ]
 
 

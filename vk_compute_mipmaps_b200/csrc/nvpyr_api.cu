@@ -573,10 +573,13 @@ nvpyrStatus resolve(const nvpyrDispatchDesc* d, ResolvedDesc& r)
     return NVPYR_ERROR_INVALID_VALUE;
   if(d->format != NVPYR_FORMAT_SRGBA8 && d->format != NVPYR_FORMAT_RGBA32F)
     return NVPYR_ERROR_UNSUPPORTED;
-  if(d->flags & ~uint32_t(NVPYR_FLAG_FORCE_GENERAL | NVPYR_FLAG_PREMULTIPLY_ALPHA | NVPYR_FLAG_F16_SHARED))
+  constexpr uint32_t kSharedFlags = NVPYR_FLAG_F16_SHARED | NVPYR_FLAG_SRGB_SHARED;
+  if(d->flags & ~uint32_t(NVPYR_FLAG_FORCE_GENERAL | NVPYR_FLAG_PREMULTIPLY_ALPHA | kSharedFlags))
     return NVPYR_ERROR_UNSUPPORTED;
-  if((d->flags & (NVPYR_FLAG_PREMULTIPLY_ALPHA | NVPYR_FLAG_F16_SHARED)) && d->format != NVPYR_FORMAT_SRGBA8)
+  if((d->flags & (NVPYR_FLAG_PREMULTIPLY_ALPHA | kSharedFlags)) && d->format != NVPYR_FORMAT_SRGBA8)
     return NVPYR_ERROR_UNSUPPORTED;
+  if((d->flags & kSharedFlags) == kSharedFlags)
+    return NVPYR_ERROR_INVALID_VALUE;  // the two shared types are alternative builds of the shaders
   r.format         = d->format;
   r.flags          = d->flags;
   r.w              = d->extent.width;
@@ -739,7 +742,7 @@ nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0
 // (tiles never overlap, so rewriting level 0 in place is safe; the general pipeline re-reads halo columns).
 bool canFusePremultiply(const ResolvedDesc& r)
 {
-  if(r.format != NVPYR_FORMAT_SRGBA8 || r.levels < 2 || !r.fast || (r.flags & NVPYR_FLAG_F16_SHARED))
+  if(r.format != NVPYR_FORMAT_SRGBA8 || r.levels < 2 || !r.fast || (r.flags & (NVPYR_FLAG_F16_SHARED | NVPYR_FLAG_SRGB_SHARED)))
     return false;
   nvpyrPlanStep steps[NVPYR_MAX_STEPS];
   const int     n = buildPlan(r.w, r.h, r.levels, r.general, r.fast, steps, NVPYR_MAX_STEPS);
@@ -776,6 +779,8 @@ nvpyrStatus dispatchResolved(const ResolvedDesc& r)
     return NVPYR_SUCCESS;
   if(r.flags & NVPYR_FLAG_F16_SHARED)
     return runPlan<Srgba8F16Shared>(*ctx, r);
+  if(r.flags & NVPYR_FLAG_SRGB_SHARED)
+    return runPlan<Srgba8SrgbShared>(*ctx, r);
   return r.format == NVPYR_FORMAT_SRGBA8 ? runPlan<Srgba8>(*ctx, r, 0, fusePremul) : runPlan<Rgba32f>(*ctx, r);
 }
 
@@ -800,7 +805,7 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
   const ResolvedDesc& a     = r[0];
   const uint32_t      count = uint32_t(r.size());
   if(count < 2 || count > kBatchRing / 4 || a.format != NVPYR_FORMAT_SRGBA8 || a.levels < 2 || g_forceGenericFast
-     || g_noTailFusion || !a.fast || a.customDispatchers || (a.flags & NVPYR_FLAG_F16_SHARED))
+     || g_noTailFusion || !a.fast || a.customDispatchers || (a.flags & (NVPYR_FLAG_F16_SHARED | NVPYR_FLAG_SRGB_SHARED)))
     return NVPYR_SUCCESS;
   for(const ResolvedDesc& d : r)
   {
@@ -1242,6 +1247,8 @@ nvpyrStatus nvpyrGenerateHost(const void* hostLevel0, void* hostChain, nvpyrExte
     return st;
   if(r.flags & NVPYR_FLAG_F16_SHARED)
     st = generateHostPipelined<Srgba8F16Shared>(*ctx, r, hostLevel0, hostChain, bytes);
+  else if(r.flags & NVPYR_FLAG_SRGB_SHARED)
+    st = generateHostPipelined<Srgba8SrgbShared>(*ctx, r, hostLevel0, hostChain, bytes);
   else
     st = r.format == NVPYR_FORMAT_SRGBA8 ? generateHostPipelined<Srgba8>(*ctx, r, hostLevel0, hostChain, bytes)
                                          : generateHostPipelined<Rgba32f>(*ctx, r, hostLevel0, hostChain, bytes);

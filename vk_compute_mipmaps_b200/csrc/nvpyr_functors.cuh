@@ -266,6 +266,44 @@ struct Srgba8F16Shared : Srgba8T<1>
   }
 };
 
+// SRGB_SHARED variant of the sRGBA8 instance (srgba8_mipmap_preamble.glsl:60-101, the demo's "srgbShared"
+// alternative): the shared type is a packed 8-bit sRGB texel -- SHARED_STORE = packUnorm4x8 of
+// srgbComponentFromLinear, SHARED_LOAD = linearFromSrgbComponent of unpackUnorm4x8.  Numerics as pinned by
+// tools/gen_srgb_tables.c (and checked by the test suite against the executed shaders): the pack is monotone, so it equals the number of pinned
+// SHARED thresholds <= x (binary search in constant memory); the unpack is a 256-entry table; alpha is
+// round-half-even(clamp(a, 0, 1) * 255) / 255 (IEEE division).  Non-default, lossy and slow in the reference too;
+// runs on the functor-template kernels only.
+namespace devtables {
+#define NVPYR_TABLES_SHARED_ONLY
+#define NVPYR_SHARED_TABLE_DECL static __constant__ unsigned int
+#include "srgb_tables.inc"
+#undef NVPYR_SHARED_TABLE_DECL
+#undef NVPYR_TABLES_SHARED_ONLY
+}  // namespace devtables
+
+struct Srgba8SrgbShared : Srgba8T<1>
+{
+  __device__ __forceinline__ static float roundTrip(float x)
+  {
+    uint32_t lo = 0u, hi = 255u;  // the code is in [lo, hi]
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+    {
+      const uint32_t mid = (lo + hi + 1u) >> 1;
+      if(mid > lo && x >= __uint_as_float(devtables::NVPYR_SRGB_SHARED_ENCODE_THRESHOLD_BITS[mid - 1u]))
+        lo = mid;
+      else
+        hi = mid > lo ? mid - 1u : hi;
+    }
+    return __uint_as_float(devtables::NVPYR_SRGB_SHARED_DECODE_BITS[lo]);
+  }
+  __device__ __forceinline__ static Value sharedRound(Value v)
+  {
+    const float a = fminf(fmaxf(v.w, 0.0f), 1.0f);
+    return make_float4(roundTrip(v.x), roundTrip(v.y), roundTrip(v.z), __fdiv_rn(rintf(__fmul_rn(a, 255.0f)), 255.0f));
+  }
+};
+
 // ---------------------------------------------------------------------------
 // RGBA32F: the template of nvpro_pyramid.glsl:27-49 instantiated with identity
 // load/store (the reference ships no such shader).
