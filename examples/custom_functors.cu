@@ -63,6 +63,11 @@ struct MyRgba32f : nvpyr::PyramidFunctors<MyRgba32f>
   }
 };
 
+// Dispatchers the library must reject (the reference asserts, dispatch.hpp:169,172): nothing may be enqueued.
+static uint32_t fillsNothing(const nvpyr::PyramidState&, nvpyrPlanStep&) { return 0; }
+static uint32_t fillsTooMuch(const nvpyr::PyramidState& s, nvpyrPlanStep&) { return s.remainingLevels + 1; }
+static uint32_t fastOnOddSizes(const nvpyr::PyramidState& s, nvpyrPlanStep&) { return s.remainingLevels < 3 ? s.remainingLevels : 3; }
+
 // A user dispatcher (nvpro_pyramid_dispatcher_t): general pipeline, one level per dispatch.
 static uint32_t oneLevelGeneral(const nvpyr::PyramidState& s, nvpyrPlanStep& step)
 {
@@ -217,6 +222,29 @@ int main()
     checkDepth(sz[0], sz[1], "fast <2, 5> + one-level general", 0, 2, 5, oneLevelGeneral);
   }
   checkDepth(1024, 1024, "levelCount 4 (partial chain)", 0, 0, 0, nullptr, 4);
+  {
+    float* dev = nullptr;
+    CK(cudaMalloc(&dev, 4 * 333 * 201 * 2));
+    CK(cudaMemset(dev, 0, 4 * 333 * 201 * 2));
+    nvpyrDispatchDesc d;
+    memset(&d, 0, sizeof(d));
+    d.structSize = sizeof(d);
+    d.extent     = {333, 201};
+    d.base       = dev;
+    const nvpyrStatus a = nvpyr::dispatch<DepthMax>(d, nullptr, fillsNothing);
+    const nvpyrStatus b = nvpyr::dispatch<DepthMax>(d, nullptr, fillsTooMuch);
+    const nvpyrStatus c = nvpyr::dispatch<DepthMax>(d, nullptr, nullptr, fastOnOddSizes);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> got(333 * 201 * 2);
+    CK(cudaMemcpy(got.data(), dev, got.size() * 4, cudaMemcpyDeviceToHost));
+    size_t written = 0;
+    for(float v : got)
+      written += v != 0.0f;
+    const bool ok = a == NVPYR_ERROR_INVALID_VALUE && b == NVPYR_ERROR_INVALID_VALUE && c == NVPYR_ERROR_INVALID_VALUE && written == 0;
+    printf("bad dispatchers: status %d %d %d, %zu texels written -> %s\n", int(a), int(b), int(c), written, ok ? "rejected" : "NOT rejected");
+    failures += !ok;
+    cudaFree(dev);
+  }
   const uint32_t fsizes[][2] = {{512, 256}, {255, 129}, {260, 260}, {96, 1000}};
   for(const auto& sz : fsizes)
     checkRgba32f(sz[0], sz[1]);

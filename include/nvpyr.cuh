@@ -235,6 +235,14 @@ inline nvpyrStatus dispatch(const nvpyrDispatchDesc& desc, const typename S::Par
   const int     n = buildPlan(w, h, levels, general, fast, steps, NVPYR_MAX_STEPS);
   if(n < 0)
     return NVPYR_ERROR_INVALID_VALUE;  // a dispatcher filled 0 levels or too many (the reference asserts)
+  // Limits of the kernels, checked for the whole plan before anything is enqueued.
+  for(int i = 0; i < n; ++i)
+  {
+    const nvpyrPlanStep& s = steps[i];
+    if(s.pipeline == 1 ? (s.levelCount < 1 || s.levelCount > 6 || ((s.srcWidth | s.srcHeight) & ((1u << s.levelCount) - 1u)))
+                       : (s.levelCount < 1 || s.levelCount > 2))
+      return NVPYR_ERROR_INVALID_VALUE;  // a custom dispatcher promised levels its pipeline cannot fill
+  }
   int device = 0, smCount = 0;
   if(cudaGetDevice(&device) != cudaSuccess
      || cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
@@ -248,8 +256,6 @@ inline nvpyrStatus dispatch(const nvpyrDispatchDesc& desc, const typename S::Par
     nvpyrStatus          st = NVPYR_SUCCESS;
     if(s.pipeline == 1)
     {
-      if(s.levelCount > 6 || ((lv[s.inputLevel].w | lv[s.inputLevel].h) & ((1u << s.levelCount) - 1u)))
-        return NVPYR_ERROR_INVALID_VALUE;  // a custom fast dispatcher promised levels the size does not allow
       FastParams p{};
       for(uint32_t k = 0; k <= s.levelCount; ++k)
         p.lv[k] = lv[s.inputLevel + k];
@@ -271,8 +277,6 @@ inline nvpyrStatus dispatch(const nvpyrDispatchDesc& desc, const typename S::Par
     }
     else
     {
-      if(s.levelCount > 2)
-        return NVPYR_ERROR_INVALID_VALUE;
       GeneralParams p{};
       for(uint32_t k = 0; k <= s.levelCount; ++k)
         p.lv[k] = lv[s.inputLevel + k];

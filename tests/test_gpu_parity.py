@@ -517,6 +517,7 @@ def test_user_defined_functor_sets(nv, cuda):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "custom functor sets ok" in r.stdout
     assert r.stdout.count("0 of") == 36 + 1 + 4, r.stdout
+    assert "-> rejected" in r.stdout
 
 
 @pytest.mark.parametrize("size", [(1024, 512), (333, 201), (1920, 1080)], ids=lambda s: f"{s[0]}x{s[1]}")
