@@ -286,12 +286,39 @@ template <int M, bool kBatch, bool kPremul, bool kSlabTasks>
 nvpyrStatus launchFastSrgba8K(const DeviceContext& ctx, const FastParams& p, const FastBatch& b, uint64_t work,
                               cudaStream_t stream)
 {
-  const size_t smem = sizeof(Srgba8FastSmem);
+  const size_t smem = fastSmemBytes(kFastTma && !kBatch && !kPremul && !kSlabTasks);
   int          grid = 1;
   nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M, kBatch, kPremul, kSlabTasks>, smem, ctx, work, &grid, kFastWarps * 32);
   if(st != NVPYR_SUCCESS)
     return st;
-  NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, kBatch, kPremul, kSlabTasks>, grid, kFastWarps * 32, smem, stream, p, b));
+  FastTensorMap tmap{};
+#if NVPYR_FAST_TMA == 2
+  if(!kBatch && !kPremul && !kSlabTasks)
+  {
+    // 2-D tensor map of the step's input level: W x H texels of 4 bytes, row pitch in bytes, box 64 x 8
+    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const EncodeFn encode = [] {
+      void*                           f = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess)
+        f = nullptr;
+      return reinterpret_cast<EncodeFn>(f);
+    }();
+    if(encode == nullptr)
+      return NVPYR_ERROR_UNSUPPORTED;
+    const cuuint64_t dims[2]    = {p.lv[0].w, p.lv[0].h};
+    const cuuint64_t strides[1] = {p.lv[0].pitch};
+    const cuuint32_t box[2]     = {64u, 8u};
+    const cuuint32_t estr[2]    = {1u, 1u};
+    if(encode(&tmap.map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, p.lv[0].ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+       != CUDA_SUCCESS)
+      return NVPYR_ERROR_CUDA;
+  }
+#endif
+  NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, kBatch, kPremul, kSlabTasks>, grid, kFastWarps * 32, smem, stream, p, b, tmap));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
@@ -530,7 +557,7 @@ nvpyrStatus launchPremultiply(const DeviceContext& ctx, const void* in, void* ou
      && !g_forceGenericFast)
   {
     const uint64_t n4   = texels / 4u;
-    const size_t   smem = sizeof(Srgba8FastSmem);
+    const size_t   smem = fastSmemBytes(false);
     int            grid = 1;
     nvpyrStatus    st   = persistentGrid(premultiplySrgba8Kernel, smem, ctx, (n4 + kFastWarps * 32 - 1) / (kFastWarps * 32), &grid,
                                          kFastWarps * 32);
