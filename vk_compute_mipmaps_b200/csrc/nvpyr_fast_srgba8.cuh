@@ -28,17 +28,20 @@
 //    tall as the step needs, so steps with M < 6 expose 2-8x more independent warp tasks.
 //  * packed adds: FADD2 (add.rn.f32x2) performs two IEEE float32 additions per issue slot;
 //    the sums run on (R, G) and (B, A) pairs.
-//  * the next slab's four 16-byte rows are prefetched into registers before the current
-//    slab is processed.
+//  * the level-0 slab of a warp is staged in shared memory by the TMA unit (one 2-D tensor-map
+//    copy per slab on the warp's own mbarrier, NVPYR_FAST_TMA below) while the previous slab is
+//    processed; the batch / fused-premultiply / slab-task kernels prefetch the next slab's four
+//    16-byte rows into registers instead.
 //
 //  * the encode bucket table (bucket = exponent + 7 mantissa bits) is stored 8-way bank-partitioned
 //    (entry k occupies 32 bytes, lane l reads copy l & 7): lanes with different l & 7 can never
 //    collide on a bank.  Measured on 16384^2, uniform-random input: 328 us un-replicated, 284 us
 //    4-way (8 mantissa bits), 273 us 8-way.
 //
-// CTA = 1024 threads = 32 warps sharing the tables (163 KB of shared memory); one CTA per SM.
-// Shared memory beyond ~200 KB leaves the SM too little L1 for the loads in flight (a 213 KB
-// variant of the same code ran 19 % slower).
+// CTA = 1024 threads = 32 warps sharing the tables; one CTA per SM.  160 KB of tables and stashes
+// + 64 KB of TMA ring for the kernels that use it.  With LDG loads, shared memory beyond ~200 KB
+// leaves the SM too little L1 for the loads in flight (a 213 KB variant of the register path ran
+// 19 % slower); loads staged by the TMA unit do not pass through L1.
 #pragma once
 #include <stddef.h>
 
