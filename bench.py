@@ -475,7 +475,7 @@ def run_gpu_arm(args):
                              "opaque smooth gradient"}[args.input],
                    "other_inputs": other_inputs, "batch_of_4096": batch},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "fastKernel<Srgba8,6> (level 0 -> levels 1..6)",
+                     "traffic": traffic, "kernel": "fastSrgba8Kernel<6> (TMA-staged level-0 slabs; level 0 -> levels 1..6)",
                      "algorithmic_bytes_per_launch": k_bytes, "us_per_launch": 1e3 * k_ms, "peak_source": peak_src},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
