@@ -44,6 +44,19 @@ def test_transfer_thresholds_are_tight(oracle):
         assert f(float(at)) == c and f(float(below)) == c - 1
 
 
+def test_committed_tables_are_the_generator_output(tmp_path):
+    """vk_compute_mipmaps_b200/csrc/srgb_tables.inc is exactly what tools/gen_srgb_tables.c prints on this platform
+    (the pinned bit patterns were not edited by hand; the exhaustive monotonicity pass is the generator's
+    --exhaustive option, ~10 s, not run here)."""
+    import shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "gen")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", os.path.join(_oracle.ROOT, "tools", "gen_srgb_tables.c"), "-lm", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    assert out == open(os.path.join(_oracle.ROOT, "vk_compute_mipmaps_b200", "csrc", "srgb_tables.inc")).read()
+
+
 def test_transfer_matches_reference_header(oracle, ref):
     for c in range(256):
         assert oracle.lib.nvo_linear_from_srgb(c) == ref.lib.ref_linear_from_srgb(c)
