@@ -760,3 +760,112 @@ def test_headline_16384_properties(nv, cuda, oracle):
     nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(), w, h, image=buf)
     torch.cuda.synchronize()
     assert bool((buf.view(-1, 4) == torch.tensor([10, 128, 250, 77], dtype=torch.uint8, device="cuda")).all())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Round 2: the configurations the numbers are quoted on, checked in full.
+
+def _crop_chains(oracle, level0_hw4, edge, levels, workers=None):
+    """Oracle A on every edge x edge crop of level 0 (numpy [H, W, 4]), `levels` levels each, across host threads
+    (the C oracle releases the GIL).  A fast-pipeline step of M levels never looks outside its 2^M-aligned tile, so
+    for edge % 64 == 0 the crops of a 6-level step are exact.  Returns {(cy, cx): chain bytes}."""
+    import concurrent.futures as cf
+    h, w = level0_hw4.shape[:2]
+    jobs = [(cy, cx) for cy in range(0, h, edge) for cx in range(0, w, edge)]
+
+    def run(job):
+        cy, cx = job
+        crop = np.ascontiguousarray(level0_hw4[cy:cy + edge, cx:cx + edge]).reshape(-1)
+        return job, oracle.shader_chain(crop, edge, edge, levels=levels)[0]
+    with cf.ThreadPoolExecutor(workers or max(1, len(os.sched_getaffinity(0)))) as ex:
+        return dict(ex.map(run, jobs))
+
+
+@pytest.mark.parametrize("content", ["julia", "random", "gradient"])
+def test_headline_16384_every_tile(nv, cuda, oracle, content):
+    """BASELINE config 3 in full, on the three inputs bench.py times (the Julia set of the reference demo, uniform
+    random bytes, the smooth gradient): levels 1..6 of EVERY 64x64 tile against Oracle A (64 crops of 2048^2, each
+    a 7-level chain), then levels 7..14 against the oracle chain of the GPU's own level 6 (same carry groups:
+    fast 6 | fast 6 | fast 2)."""
+    import bench
+    torch = cuda
+    w = h = 16384
+    n = nv.chain_bytes(w, h)
+    buf = torch.empty(n, dtype=torch.uint8, device="cuda")
+    buf.view(-1, 4)[w * h:] = torch.from_numpy(MAGENTA).cuda()
+    l0 = buf[:4 * w * h].view(h, w, 4)
+    if content == "random":
+        g = torch.Generator(device="cuda").manual_seed(7)
+        buf[:4 * w * h] = torch.randint(0, 256, (4 * w * h,), dtype=torch.uint8, device="cuda", generator=g)
+    else:
+        {"julia": bench.fill_julia, "gradient": bench.fill_gradient}[content](l0, w, h)
+    host_l0 = l0.cpu().numpy()
+    nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(), w, h, image=buf)
+    torch.cuda.synchronize()
+    assert bool((buf[:4 * w * h].view(h, w, 4).cpu() == torch.from_numpy(host_l0)).all()), "level 0 was modified"
+    edge = 2048
+    chains = _crop_chains(oracle, host_l0, edge, 7)
+    views = [v.cpu().numpy() for v in nv.level_views(buf, w, h)[:7]]
+    for (cy, cx), want in chains.items():
+        off = edge * edge
+        for lvl in range(1, 7):
+            e = edge >> lvl
+            got = views[lvl][cy >> lvl:(cy >> lvl) + e, cx >> lvl:(cx >> lvl) + e].reshape(-1)
+            assert (got == want[4 * off:4 * (off + e * e)]).all(), (content, cx, cy, lvl)
+            off += e * e
+    want_tail, _ = oracle.shader_chain(views[6].reshape(-1), 256, 256)
+    off6 = nv.level_offset_texels(w, h, 6)
+    assert (buf[4 * off6:].cpu().numpy() == want_tail).all(), content
+
+
+IMAGES_DIR = os.path.join(os.path.dirname(__file__), "golden", "test_images")
+# file, recorded worst delta of the reference's GPU "default" pipeline vs its CPU generator (demo_app/rtx3090.json),
+# worst delta of Oracle A vs the real CPU generator on the PIL-decoded, premultiplied image (computed in the build
+# container: the alpha images reproduce the recorded 5 / 4 / 4, the opaque ones stay at or below the recorded 2)
+REFERENCE_IMAGES = [("1080p.jpg", 2, 1), ("1440p.jpg", 2, 1), ("4094.jpg", 2, 2), ("4095.jpg", 2, 2), ("4096.jpg", 2, 2),
+                    ("4k.jpg", 2, 1), ("alpha1080p.png", 5, 5), ("alpha2048.png", 4, 4), ("alpha2052.png", 4, 4),
+                    ("lunch_2047.jpg", 2, 2), ("lunch_with_friend.jpg", 2, 2), ("mandelbrots.png", 2, 2), ("tall.jpg", 2, 1)]
+
+
+@pytest.mark.parametrize("name,recorded,expected", REFERENCE_IMAGES, ids=[r[0] for r in REFERENCE_IMAGES])
+def test_reference_test_images_full_size(nv, cuda, oracle, name, recorded, expected):
+    """BASELINE configs 1, 2 and 4 on the reference's own test images at FULL size (test_images/*, shipped under
+    tests/golden/test_images): level 0 = the decoded image, premultiplied by the library as the reference's loader
+    does (scoped_image.hpp:233-255, mipmaps_app.cpp:606).  Bit-exact against Oracle A, and the worst delta against
+    the reference's own CPU generator (oracle/_ref when present, else Oracle B, its pinned restatement) equals the
+    known answer."""
+    from PIL import Image
+    im = Image.open(os.path.join(IMAGES_DIR, name)).convert("RGBA")
+    w, h = im.size
+    raw = np.asarray(im, dtype=np.uint8).reshape(-1).copy()
+    l0 = oracle.premultiply(raw)
+    want, _ = oracle.shader_chain(l0, w, h)
+    got = gpu_chain(nv, cuda, raw, w, h, flags=2)  # NVPYR_FLAG_PREMULTIPLY_ALPHA: the pre-pass runs on the GPU
+    assert_same(got, want, w, h, oracle, name)
+    ref = _oracle.load_ref()
+    cpu = ref.cpu_chain(oracle.new_chain(l0, w, h), w, h) if ref is not None else oracle.cpu_chain(l0, w, h)
+    worst = oracle.compare(got, cpu, w, h).worst
+    assert worst == expected and worst <= recorded, (name, worst, expected, recorded)
+
+
+def test_fused_batch_at_the_benchmarked_size(nv, cuda, oracle):
+    """BASELINE config 5's unit: 4096^2 textures through nvpyrDispatchBatch (fastSrgba8Kernel<6, batch> +
+    tailBatchKernel, two launches), every texture bit-exact against Oracle A."""
+    import concurrent.futures as cf
+    w = h = 4096
+    count = 8
+    l0s = [_oracle.random_level0(w, h, 900 + k) if k % 2 == 0 else _oracle.smooth_level0(w, h, 900 + k) for k in range(count)]
+    with cf.ThreadPoolExecutor(max(1, len(os.sched_getaffinity(0)))) as ex:
+        wants = list(ex.map(lambda l0: oracle.shader_chain(l0, w, h)[0], l0s))
+    imgs = []
+    for l0 in l0s:
+        buf = cuda.empty(nv.chain_bytes(w, h), dtype=cuda.uint8, device="cuda")
+        buf.view(-1, 4)[:] = cuda.from_numpy(MAGENTA).cuda()
+        buf[:4 * w * h] = cuda.from_numpy(l0).cuda()
+        imgs.append(buf)
+    before = nv.launch_count()
+    nv.dispatch_batch(None, nv.PyramidPipelines(), imgs, w, h)
+    cuda.cuda.synchronize()
+    assert nv.launch_count() - before == 2
+    for k, (b, want) in enumerate(zip(imgs, wants)):
+        assert_same(b.cpu().numpy(), want, w, h, oracle, f"texture {k}")
