@@ -5,15 +5,19 @@
 
 Workload (BASELINE.json configs[2], the configuration the metric is quoted on): full mip chain of a synthetic
 16384x16384 sRGBA8 image, 15 levels, 1 431 655 764 algorithmic bytes (level 0 read once + every other level
-written once).  Level 0 is the Julia-set texture the reference demo mip-maps every frame at this very size
-(--input julia, default); uniform random bytes (the worst case for shared-memory bank conflicts) and a smooth
-gradient are timed in the same run and reported under config.other_inputs.  A "step" is one full-chain generation.  Two distinct 1.43 GB chains are alternated, each far
-larger than the 126 MB L2, so level 0 is never cache resident.  At N > 1 every rank runs the same step on its own
+written once).  A "step" is one full-chain generation.  The three level-0 contents of SURVEY 8d are each timed for
+exactly K steps -- the Julia-set texture the reference demo mip-maps every frame at this very size, uniform random
+bytes (worst case for shared-memory bank conflicts), a smooth gradient -- and reported under `inputs`; the headline
+`value` / `ms_per_step` / `roofline` are those of the SLOWEST input.  Two distinct 1.43 GB chains are alternated, each
+far larger than the 126 MB L2, so level 0 is never cache resident.  At N > 1 every rank runs the same step on its own
 image (independent units, no data-path collective): weak scaling, value = N * bytes / max-over-ranks time.
+`config.batch_of_4096` is BASELINE configs[4] as written: 512 textures of 4096^2 partitioned over the N ranks
+(strong scaling), per-texture checksums gathered and compared with the single-GPU run.
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own CPU generator
 (cpuGenerateMipmaps_sRGBA compiled in place from /root/reference into oracle/_ref, else our C port of it) on
-the host cores; that leg and the `cpu_baseline` object are the only places this file touches oracle/.
+the host cores, on the same 16384^2 configuration; that leg and the `cpu_baseline` object are the only places this
+file touches oracle/.
 """
 import argparse
 import ctypes as C
@@ -116,13 +120,48 @@ def _load_cpu_generator():
     return "port", make
 
 
+def _stats(ms_list):
+    """min / median / max per step (the reference's benchmark reports the same three, mipmaps_app.cpp:812-821)."""
+    v = sorted(ms_list)
+    return {"min_us": 1e3 * v[0], "median_us": 1e3 * v[len(v) // 2], "max_us": 1e3 * v[-1]}
+
+
+def _host_threads():
+    try:
+        cores = len(os.sched_getaffinity(0))  # the host threads this process may actually use
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
+    return max(1, min(cores, 256))
+
+
+def _julia_level0_host(w, h, threads):
+    """Level 0 of the headline workload on the host: the Julia-set texture of the reference demo
+    (shaders/julia.comp:27-63, demo_app/julia.cpp:65-81), filled by `threads` host threads."""
+    import numpy as np
+    so = os.path.join(ROOT, "oracle", "libnvpyr_oracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    lib = C.CDLL(so)
+    lib.nvo_julia_srgba8_rows.argtypes = [C.c_void_p] + [C.c_uint32] * 5 + [C.c_int]
+    out = np.empty(4 * w * h, dtype=np.uint8)
+    rows = (h + threads - 1) // threads
+    ts = [threading.Thread(target=lib.nvo_julia_srgba8_rows,
+                           args=(out.ctypes.data, w, h, y, min(h, y + rows), 2109710467, 64))
+          for y in range(0, h, rows)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return out
+
+
+WORKLOAD = ("synthetic 16384x16384 sRGBA8 full mip chain, 15 levels, 1 431 655 764 algorithmic bytes "
+            "(BASELINE configs[2])")
+
+
 def cpu_baseline_single(sample_edge=16384):
     """The reference's CPU generator on ONE host thread (how the reference itself runs it, one std::thread
-    per image, demo_app/mipmaps_app.cpp:651-652) over a bounded sample of the workload."""
-    import numpy as np
+    per image, demo_app/mipmaps_app.cpp:651-652) over the whole workload of one step."""
     kind, make = _load_cpu_generator()
-    rng = np.random.default_rng(0)
-    l0 = rng.integers(0, 256, 4 * sample_edge * sample_edge, dtype=np.uint8)
+    l0 = _julia_level0_host(sample_edge, sample_edge, _host_threads())
     run, free = make(l0, sample_edge, sample_edge)
     t = time.perf_counter()
     run()
@@ -130,27 +169,30 @@ def cpu_baseline_single(sample_edge=16384):
     free()
     by = algorithmic_bytes(sample_edge, sample_edge)
     return {"value": by / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": f"one {sample_edge}x{sample_edge} sRGBA8 full chain ("
-                      + ("the whole workload of one step" if sample_edge == W else
-                         f"1/{(W // sample_edge) ** 2} of the 16384^2 workload's texels")
-                      + f"), {dt:.2f} s on one host thread"}
+            "sample": f"one {sample_edge}x{sample_edge} sRGBA8 full chain (Julia-set level 0; the whole workload of one "
+                      f"step), {dt:.2f} s on one host thread"}
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference CPU generator, one image per host thread, all host cores."""
-    import numpy as np
+    """--impl reference: the reference's own CPU generator (cpuGenerateMipmaps_sRGBA, compiled in place into
+    oracle/_ref) on the SAME configuration as the GPU arm: every step generates the full mip chain of the 16384^2
+    Julia-set image, one chain per host thread on all host threads -- the reference's own parallelism (one
+    std::thread per image, demo_app/mipmaps_app.cpp:651-652; generateLevel itself is single-threaded).
+    value = threads * 1 431 655 764 B / step time.  About 11-15 s per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     kind, make = _load_cpu_generator()
+    cores = _host_threads()
     try:
-        cores = len(os.sched_getaffinity(0))  # the host threads this process may actually use
-    except (AttributeError, OSError):
-        cores = os.cpu_count() or 1
-    cores = max(1, min(cores, 256))
-    edge = 2048  # per-thread sample image; cores * steps of them stay within a few minutes
-    rng = np.random.default_rng(0)
-    jobs = [make(rng.integers(0, 256, 4 * edge * edge, dtype=np.uint8), edge, edge) for _ in range(cores)]
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 64 << 30
+    chain = algorithmic_bytes(W, H)
+    threads = int(max(1, min(cores, (avail // 2) // chain)))
+    l0 = _julia_level0_host(W, H, cores)
+    jobs = [make(l0, W, H) for _ in range(threads)]
+    del l0
 
     def step():
         ts = [threading.Thread(target=j[0]) for j in jobs]
@@ -158,22 +200,24 @@ def run_reference_arm(args):
         [t.join() for t in ts]
     for _ in range(args.warmup):
         step()
+    per_step = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        t = time.perf_counter()
         step()
+        per_step.append(1e3 * (time.perf_counter() - t))
     dt = time.perf_counter() - t0
     [j[1]() for j in jobs]
-    by = algorithmic_bytes(edge, edge) * cores * args.steps
-    value = by / dt / 1e9
-    sample = (f"each step = {cores} independent {edge}x{edge} sRGBA8 full chains, one per host thread "
-              f"(the reference's own thread-per-image parallelism); same bytes-per-texel metric as the 16384^2 workload")
+    value = chain * threads * args.steps / dt / 1e9
+    sample = (f"each step = {threads} full 16384x16384 chains (the whole workload, Julia-set level 0), one per host "
+              f"thread on {threads} of {cores} host threads: the reference's own thread-per-image parallelism")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic 16384x16384 sRGBA8 full mip chain (BASELINE configs[2]); CPU arm runs a "
-                               "bounded sample", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": WORKLOAD, "algorithmic_bytes_per_step": chain, "chains_per_step": threads,
+                   "input": "Julia set of the reference demo", "per_step": _stats(per_step)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -254,11 +298,18 @@ def bind_to_gpu_numa_node(torch, local):
         return 0
 
 
+# Checksum of the 512 per-texture checksums of BASELINE configs[4] (texture k = uniform random bytes from seed
+# BATCH_SEED + k), recorded from the single-GPU run: every sharded run must reproduce it (batch.fold_checksums).
+BATCH_SEED = 100000
+BATCH_EXPECTED = {512: 0x1ceab29ae8b61d5e}
+
+
 def run_gpu_arm(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     import vk_compute_mipmaps_b200 as nv
+    from vk_compute_mipmaps_b200 import batch as nvbatch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -276,15 +327,18 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     pipes = nv.PyramidPipelines()
     chain_bytes = nv.chain_bytes(W, H)
     assert chain_bytes == algorithmic_bytes(W, H) == 1431655764
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    bufs = []
-    for _ in range(2):  # two distinct chains, alternated (each >> L2)
-        b = torch.empty(chain_bytes, dtype=torch.uint8, device=dev)
-        b[:4 * W * H] = torch.randint(0, 256, (4 * W * H,), dtype=torch.uint8, device=dev, generator=gen)
-        bufs.append(b)
+    bufs = [torch.empty(chain_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]  # two chains, alternated (each >> L2)
+
     def fill_input(name):
         if name == "random":
             for b in bufs:
@@ -292,113 +346,130 @@ def run_gpu_arm(args):
         else:
             {"julia": fill_julia, "gradient": fill_gradient}[name](bufs[0][:4 * W * H].view(H, W, 4), W, H)
             bufs[1][:4 * W * H].copy_(bufs[0][:4 * W * H])
-    if args.input != "random":
-        fill_input(args.input)
     stream = torch.cuda.current_stream()
-
-    def step(i):
-        nv.cmd_pyramid_dispatch(stream, pipes, W, H, image=bufs[i & 1])
-
-    # ---- whole-chain timing (value) ----
-    sampler = ClockSampler(local) if rank == 0 else None
-    for i in range(max(3, args.warmup)):
-        step(i)
-    barrier()
-    launches0 = nv.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
-    ev0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    ev1.record(stream)
-    barrier()
-    t_wall1 = time.time()
-    launches = nv.launch_count() - launches0
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    ms_per_step = ms_total / args.steps
-    value = world * chain_bytes / (ms_per_step * 1e-3) / 1e9
-
-    # ---- dominant kernel alone: the 6-level fast kernel on level 0 (levelCount = 7 -> exactly one launch) ----
+    warm = max(3, args.warmup)
     k_bytes = algorithmic_bytes(W, H, 0, 6)
-    for i in range(3):
-        nv.cmd_pyramid_dispatch(stream, pipes, W, H, 7, image=bufs[i & 1])
-    torch.cuda.synchronize()
-    l0 = nv.launch_count()
-    kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev0.record(stream)
-    for i in range(args.steps):
-        nv.cmd_pyramid_dispatch(stream, pipes, W, H, 7, image=bufs[i & 1])
-    kev1.record(stream)
-    torch.cuda.synchronize()
-    assert nv.launch_count() - l0 == args.steps
-    k_ms = kev0.elapsed_time(kev1) / args.steps
 
-    # ---- same chain on the other synthetic inputs of SURVEY 8d (bytes moved are identical) ----
-    other_inputs = {}
-    if rank == 0 and not args.no_other_inputs:
-        for name in [n for n in ("julia", "random", "gradient") if n != args.input]:
-            fill_input(name)
-            for i in range(3):
-                step(i)
-            torch.cuda.synchronize()
-            oev0, oev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n_o = max(4, min(args.steps, 10))
-            oev0.record(stream)
-            for i in range(n_o):
-                step(i)
-            oev1.record(stream)
-            torch.cuda.synchronize()
-            o_ms = oev0.elapsed_time(oev1) / n_o
-            other_inputs[name] = {"us_per_chain": 1e3 * o_ms, "GBps": chain_bytes / (o_ms * 1e-3) / 1e9,
-                                  "frac_of_hbm_peak": None}
-        if other_inputs:  # back to the headline input for the end-to-end leg
-            fill_input(args.input)
-            step(0), step(1)
-            torch.cuda.synchronize()
+    def timed_steps(fn, n_warm, n):
+        """n_warm untimed + exactly n timed calls of fn(i), one event between consecutive steps; barrier +
+        synchronize on both sides; returns (max-over-ranks total ms, this rank's per-step ms, launches)."""
+        for i in range(n_warm):
+            fn(i)
+        barrier()
+        l0 = nv.launch_count()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        evs[0].record(stream)
+        for i in range(n):
+            fn(i)
+            evs[i + 1].record(stream)
+        barrier()
+        launches = nv.launch_count() - l0
+        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(n)]
+        return max_over_ranks(evs[0].elapsed_time(evs[n])), per, launches
+
+    # ---- the three synthetic level-0 contents of SURVEY 8d: whole chain, and the dominant kernel alone
+    # (levelCount = 7 -> exactly the 6-level fast launch on level 0) ----
+    names = [args.input] if args.no_other_inputs else ["julia", "random", "gradient"]
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
+    per_input = {}
+    for name in names:
+        fill_input(name)
+        total_ms, per, launches = timed_steps(lambda i: nv.cmd_pyramid_dispatch(stream, pipes, W, H, image=bufs[i & 1]),
+                                              warm, args.steps)
+        k_total_ms, k_per, k_launches = timed_steps(
+            lambda i: nv.cmd_pyramid_dispatch(stream, pipes, W, H, 7, image=bufs[i & 1]), 3, args.steps)
+        assert k_launches == args.steps
+        ms = total_ms / args.steps
+        k_ms = k_total_ms / args.steps
+        per_input[name] = {"ms_per_step": ms, "us_per_chain": 1e3 * ms, "GBps": world * chain_bytes / (ms * 1e-3) / 1e9,
+                           "launches_per_chain": launches / args.steps, "launches": int(launches),
+                           "per_step": _stats(per), "kernel_us": 1e3 * k_ms, "kernel_per_launch": _stats(k_per),
+                           "kernel_GBps": k_bytes / (k_ms * 1e-3) / 1e9}
     t_wall2 = time.time()
+    # headline = the WORST of the inputs (the bytes moved are identical; the encode table's bank conflicts are not)
+    worst = min(per_input, key=lambda n: per_input[n]["GBps"])
+    ms_per_step = per_input[worst]["ms_per_step"]
+    value = per_input[worst]["GBps"]
+    launches = per_input[worst]["launches"]
+    if names[-1] != "julia":  # the end-to-end leg runs on the reference demo's texture
+        fill_input("julia" if "julia" in names else args.input)
+    nv.cmd_pyramid_dispatch(stream, pipes, W, H, image=bufs[0])
+    torch.cuda.synchronize()
 
-    # ---- BASELINE configs[4]: a batch of independent 4096^2 textures per rank (texture k -> rank k mod G, no
-    # collective), nvpyrDispatchBatch = two launches for the whole batch ----
+    # ---- BASELINE configs[4] as written: a batch of 512 independent 4096^2 textures PARTITIONED over the ranks
+    # (texture k -> rank k % world, vk_compute_mipmaps_b200.batch.shard_indices; no data crosses GPUs), one
+    # nvpyrDispatchBatch per rank and pass (two launches), per-texture checksums gathered and compared ----
     batch = None
     if not args.no_batch:
         bw = bh = 4096
-        per_rank = 32
+        total_tex = args.batch_textures
+        mine = nvbatch.shard_indices(total_tex, rank, world)
         b_bytes = nv.chain_bytes(bw, bh)
+        stride = (b_bytes + 255) // 256 * 256
+        pool = torch.empty(max(1, len(mine)) * stride, dtype=torch.uint8, device=dev)
+
+        def texture_level0(k, out):
+            g = torch.Generator(device=dev).manual_seed(BATCH_SEED + k)
+            out[:4 * bw * bh] = torch.randint(0, 256, (4 * bw * bh,), dtype=torch.uint8, device=dev, generator=g)
         imgs = []
-        for k in range(per_rank):
-            t = torch.empty(b_bytes, dtype=torch.uint8, device=dev)
-            t[:4 * bw * bh] = torch.randint(0, 256, (4 * bw * bh,), dtype=torch.uint8, device=dev, generator=gen)
+        for j, k in enumerate(mine):
+            t = pool[j * stride:j * stride + b_bytes]
+            texture_level0(k, t)
             imgs.append(t)
-        for _ in range(2):
-            nv.dispatch_batch(stream, pipes, imgs, bw, bh)
-        barrier()
-        b_reps = 5
-        bev0, bev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        bev0.record(stream)
-        for _ in range(b_reps):
-            nv.dispatch_batch(stream, pipes, imgs, bw, bh)
-        bev1.record(stream)
-        barrier()
-        b_ms = torch.tensor([bev0.elapsed_time(bev1) / b_reps], dtype=torch.float64, device=dev)
+        b_reps = 3
+        b_total_ms, b_per, b_launches = timed_steps(lambda i: nv.dispatch_batch(stream, pipes, imgs, bw, bh), 1, b_reps)
+        b_ms = b_total_ms / b_reps
+        # checksums: every rank fills its own slots, a SUM all_reduce assembles the table (no texture moves)
+        sums = torch.zeros(total_tex, dtype=torch.int64, device=dev)
+        for j, k in enumerate(mine):
+            c = nvbatch.device_checksum(imgs[j])
+            sums[k] = c - (1 << 64) if c >= (1 << 63) else c
+        # cross-rank check on hardware: this rank also generates two textures OWNED BY THE NEXT RANK, alone
+        # (one nvpyrDispatch each, not the fused batch), and their checksums must equal the owner's
+        probe = nvbatch.shard_indices(total_tex, (rank + 1) % world, world)[:2] if total_tex else []
+        probe_sums = torch.zeros(total_tex, dtype=torch.int64, device=dev)
+        scratch = torch.empty(b_bytes, dtype=torch.uint8, device=dev)
+        for k in probe:
+            texture_level0(k, scratch)
+            nv.cmd_pyramid_dispatch(stream, pipes, bw, bh, image=scratch)
+            torch.cuda.synchronize()
+            c = nvbatch.device_checksum(scratch)
+            probe_sums[k] = c - (1 << 64) if c >= (1 << 63) else c
+        probed = torch.zeros(total_tex, dtype=torch.int64, device=dev)
+        if probe:
+            probed[probe] = 1
         if world > 1:
-            dist.all_reduce(b_ms, op=dist.ReduceOp.MAX)
-        b_ms = float(b_ms.item())
-        batch = {"workload": f"{per_rank} independent 4096x4096 sRGBA8 textures per rank (uniform random bytes), one "
-                             "nvpyrDispatchBatch per pass; 2.9 GB per rank per pass (> L2)",
-                 "textures_per_s": world * per_rank / (b_ms * 1e-3), "us_per_texture_per_gpu": 1e3 * b_ms / per_rank,
-                 "GBps": world * per_rank * b_bytes / (b_ms * 1e-3) / 1e9, "launches_per_batch": 2}
-        del imgs
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            dist.all_reduce(probe_sums, op=dist.ReduceOp.SUM)
+            dist.all_reduce(probed, op=dist.ReduceOp.SUM)
+        sel = probed > 0
+        cross_ok = bool((sums[sel] == probe_sums[sel]).all().item()) and int(probed.max().item()) <= 1
+        folded = nvbatch.fold_checksums([int(v) & 0xFFFFFFFFFFFFFFFF for v in sums.tolist()])
+        expected = BATCH_EXPECTED.get(total_tex)
+        batch = {"workload": f"{total_tex} independent 4096x4096 sRGBA8 textures (uniform random bytes, seed "
+                             f"{BATCH_SEED}+k) partitioned over {world} rank(s) with batch.shard_indices, one "
+                             "nvpyrDispatchBatch per rank and pass (> L2 per rank)",
+                 "total_textures": total_tex, "textures_per_rank": len(mine), "scaling": "strong",
+                 "textures_per_s": total_tex / (b_ms * 1e-3), "us_per_texture_per_gpu": 1e3 * b_ms / max(1, len(mine)),
+                 "ms_per_pass": b_ms, "per_pass": _stats(b_per),
+                 "GBps": total_tex * b_bytes / (b_ms * 1e-3) / 1e9, "launches_per_pass_per_rank": b_launches / b_reps,
+                 "checksum_of_checksums": f"{folded:016x}",
+                 "expected_from_single_gpu_run": None if expected is None else f"{expected:016x}",
+                 "matches_single_gpu_run": None if expected is None else folded == expected,
+                 "cross_rank_probes": int(sel.sum().item()), "cross_rank_probes_equal": cross_ok}
+        assert cross_ok, "a texture generated alone on another rank differs from its owner's batch result"
+        assert expected is None or folded == expected, "sharded batch differs from the single-GPU run"
+        del imgs, pool, scratch
 
     # ---- end to end through the host-buffer entry point (nvpyrGenerateHost) ----
     # Headline: the reference's staging-buffer model (one host chain whose level 0 is filled, all other
     # levels filled on return -- scoped_image.hpp:436-453, and what cpuGenerateMipmaps_sRGBA does to a
-    # MipmapStorage): H2D level 0, D2H levels 1..N-1.  Also timed: separate input/output buffers, where
-    # level 0 travels back as well.  Upload, kernels and download are overlapped band by band inside the call.
+    # MipmapStorage): H2D level 0, D2H levels 1..N-1.  Also timed: separate input/output buffers (level 0 travels
+    # back as well), a caller with PAGEABLE memory (what examples/minimal_mipmaps.cpp passes: a std::vector), and
+    # the bare H2D copy of level 0 (the floor of the round trip: it is PCIe-bound).
     e2e = None
-    if rank == 0 or world > 1:
+    if not args.no_e2e:
         e_steps = max(2, min(args.steps, 5))
         l0_bytes = 4 * W * H
         h_in = torch.empty(l0_bytes, dtype=torch.uint8).pin_memory()
@@ -408,6 +479,8 @@ def run_gpu_arm(args):
         h_chain[:l0_bytes].copy_(bufs[0][:l0_bytes])
         torch.cuda.synchronize()
         a_in, a_out, a_chain = h_in.numpy(), h_out.numpy(), h_chain.numpy()
+        p_chain = np.empty(chain_bytes, dtype=np.uint8)  # pageable
+        p_chain[:l0_bytes] = a_in
 
         def timed(fn):
             fn()  # warm-up (allocates the library's device scratch)
@@ -416,13 +489,16 @@ def run_gpu_arm(args):
             for _ in range(e_steps):
                 fn()
             barrier()
-            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            return float(dt.item()) / e_steps
+            return max_over_ranks(time.perf_counter() - t0) / e_steps
 
         t_inplace = timed(lambda: nv.generate_host(a_chain[:l0_bytes], W, H, out=a_chain))
         t_separate = timed(lambda: nv.generate_host(a_in, W, H, out=a_out))
+        t_pageable = timed(lambda: nv.generate_host(p_chain[:l0_bytes], W, H, out=p_chain))
+
+        def h2d_only():
+            bufs[1][:l0_bytes].copy_(h_in, non_blocking=True)
+            torch.cuda.synchronize()
+        t_h2d = timed(h2d_only)
         e2e = {"value": world * chain_bytes / t_inplace / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": l0_bytes, "d2h_bytes_per_step": chain_bytes - l0_bytes, "steps": e_steps,
                "ms_per_step": 1e3 * t_inplace, "host_cpus_bound_to_gpu_numa_node": numa_cpus,
@@ -432,10 +508,18 @@ def run_gpu_arm(args):
                                     "ms_per_step": 1e3 * t_separate, "h2d_bytes_per_step": l0_bytes,
                                     "d2h_bytes_per_step": chain_bytes,
                                     "api": "nvpyrGenerateHost, pinned level 0 in, separate pinned packed chain out "
-                                           "(level 0 downloaded too)"}}
-        # sanity: both downloaded chains are what the device path produced, every byte
+                                           "(level 0 downloaded too)"},
+               "pageable_caller": {"value": world * chain_bytes / t_pageable / 1e9, "unit": UNIT,
+                                   "ms_per_step": 1e3 * t_pageable,
+                                   "api": "nvpyrGenerateHost in place on a PAGEABLE host chain (malloc'd memory, what "
+                                          "examples/minimal_mipmaps.cpp passes)"},
+               "h2d_only": {"GBps_per_rank": l0_bytes / t_h2d / 1e9, "GBps_all_ranks": world * l0_bytes / t_h2d / 1e9,
+                            "ms": 1e3 * t_h2d, "what": "cudaMemcpyAsync of level 0 alone, pinned -> device, all ranks at "
+                                                       "once: the floor of the round trip"}}
+        # sanity: the downloaded chains are what the device path produced, every byte
         want = bufs[0].cpu()
-        assert torch.equal(h_out, want) and torch.equal(h_chain, want), "e2e chain differs from the device path"
+        assert torch.equal(h_out, want) and torch.equal(h_chain, want) and bool((torch.from_numpy(p_chain) == want).all()), \
+            "e2e chain differs from the device path"
         del want
 
     if rank != 0:
@@ -450,9 +534,10 @@ def run_gpu_arm(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    achieved = k_bytes / (k_ms * 1e-3) / 1e9
-    for v in other_inputs.values():
-        v["frac_of_hbm_peak"] = v["GBps"] / peak
+    for v in per_input.values():
+        v["frac_of_hbm_peak"] = v["GBps"] / world / peak
+        v["kernel_frac_of_hbm_peak"] = v["kernel_GBps"] / peak
+    achieved = per_input[worst]["kernel_GBps"]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath):
@@ -460,23 +545,26 @@ def run_gpu_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_single()
+    described = {"random": "uniform random bytes, all four channels (worst case for the encode table's bank conflicts)",
+                 "julia": "Julia set of the reference demo (the texture it mip-maps every frame at this size)",
+                 "gradient": "opaque smooth gradient"}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "synthetic 16384x16384 sRGBA8 full mip chain, 15 levels (BASELINE configs[2]); level 0 = "
-                               + {"julia": "the reference demo's Julia-set texture", "random": "uniform random bytes",
-                                  "gradient": "smooth opaque gradient"}[args.input],
-                   "algorithmic_bytes_per_step": chain_bytes, "us_per_chain": 1e3 * ms_per_step,
+        "config": {"workload": WORKLOAD, "algorithmic_bytes_per_step": chain_bytes, "us_per_chain": 1e3 * ms_per_step,
+                   "input": described[worst] + " -- the SLOWEST of the inputs timed; all of them under `inputs`",
                    "l2_policy": "inputs larger than L2: two distinct 1.43 GB chains alternated",
-                   "per_rank": "one chain per step per rank, no collective", "launches_per_chain": launches / args.steps,
-                   "input": {"random": "uniform random bytes, all four channels (worst case for the encode table's bank "
-                                       "conflicts)", "julia": "Julia set of the reference demo", "gradient":
-                             "opaque smooth gradient"}[args.input],
-                   "other_inputs": other_inputs, "batch_of_4096": batch},
+                   "per_rank": "one chain per step per rank, no collective",
+                   "launches_per_chain": per_input[worst]["launches_per_chain"], "per_step": per_input[worst]["per_step"],
+                   "batch_of_4096": batch},
+        "inputs": {n: dict(v, description=described[n]) for n, v in per_input.items()},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "fastSrgba8Kernel<6> (TMA-staged level-0 slabs; level 0 -> levels 1..6)",
-                     "algorithmic_bytes_per_launch": k_bytes, "us_per_launch": 1e3 * k_ms, "peak_source": peak_src},
+                     "input": worst, "algorithmic_bytes_per_launch": k_bytes, "us_per_launch": per_input[worst]["kernel_us"],
+                     "per_launch": per_input[worst]["kernel_per_launch"], "peak_source": peak_src,
+                     "per_input": {n: {"us_per_launch": v["kernel_us"], "frac": v["kernel_frac_of_hbm_peak"]}
+                                   for n, v in per_input.items()}},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line))
@@ -494,11 +582,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-inputs", action="store_true")
     ap.add_argument("--no-batch", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--batch-textures", type=int, default=512,
+                    help="BASELINE configs[4]: total textures of the 4096^2 batch, partitioned over the ranks")
     ap.add_argument("--input", default="julia", choices=["random", "julia", "gradient"],
-                    help="level-0 content of the headline loop. Default: the Julia-set texture the reference demo "
-                         "regenerates and mip-maps every frame at its default size 16384x16384 "
-                         "(demo_app/app_args.hpp:25, demo_app/julia.cpp:65-81). 'random' = uniform random bytes, the "
-                         "worst case for the encode table's bank conflicts; every input is timed and reported.")
+                    help="with --no-other-inputs: the only level-0 content timed (default: the Julia-set texture of "
+                         "the reference demo, demo_app/app_args.hpp:25, demo_app/julia.cpp:65-81). Without it all "
+                         "three contents are timed and the slowest one is the headline.")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

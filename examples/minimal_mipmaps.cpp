@@ -7,6 +7,7 @@
 //
 // Differences: inputs are TGA or binary PPM/PGM (no JPEG/PNG decoder is bundled, the reference uses
 // stb_image); there is no device-capability probe -- the fast pipeline needs nothing optional on sm_100.
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -16,61 +17,76 @@
 
 #include "nvpyr.h"
 
-struct Config
+// Command line: the option NAMES are the reference tool's (so that scripts written for it keep working); the parser
+// is a plain table walk.
+struct Options
 {
-  bool        forceDisableFastPipeline = false;  // minimal_mipmaps.cpp:42-43
-  bool        doPremultiplyAlpha       = false;  // :45-47
-  std::string rawInputFilename         = "4096.tga";
-  std::string outputFilenameTemplate   = "./vk_compute_mipmaps_minimal.tga";  // :53
-  Config(int argc, char** argv);
+  std::string input  = "4096.tga";
+  std::string output = "./vk_compute_mipmaps_minimal.tga";
+  uint32_t    flags  = NVPYR_FLAG_NONE;
 };
 
-static const char helpString[] =
-    "%s:\n    Generates mipmaps for an input image and exports as TGA.\n"
-    "\n"
-    "    ** Arguments **\n"
-    "-i [input filename] (TGA or binary PPM/PGM)\n"
-    "-o [output filename] (will be annotated with mip level numbers)\n"
-    "-force-no-fast-pipeline: debug tool, never use the fast pipeline.\n"
-    "-premultiplied-alpha: indicate input image has premultiplied alpha.\n"
-    "-do-premultiply-alpha: indicate input image does not have premultiplied\n"
-    "    alpha, so the program must do this itself.\n"
-    "Note that output images have premultiplied alpha in either case.\n";
-
-Config::Config(int argc, char** argv)
+static void usage(const char* program, FILE* to)
 {
-  for(int i = 1; i < argc; ++i)
+  fprintf(to,
+          "usage: %s [-i image] [-o level-file-template] [-force-no-fast-pipeline]\n"
+          "          [-premultiplied-alpha | -do-premultiply-alpha]\n\n"
+          "Builds the full mip chain of one sRGBA8 image on the GPU and writes one TGA per level.\n"
+          "  -i FILE    level 0: TGA, or binary PPM / PGM (default 4096.tga)\n"
+          "  -o FILE    output name; the level number is inserted before the extension\n"
+          "  -force-no-fast-pipeline   general (NPOT) pipeline for every level\n"
+          "  -do-premultiply-alpha     level 0 has straight alpha: premultiply it first\n"
+          "  -premultiplied-alpha      level 0 is premultiplied already (default)\n"
+          "Either way the files written hold premultiplied alpha.\n",
+          program);
+}
+
+static Options parseOptions(int argc, char** argv)
+{
+  struct Switch
   {
-    const char* arg    = argv[i];
-    const char* param0 = argv[i + 1];  // argv[argc] is NULL
-    auto        needed = [&] {
-      if(param0 == nullptr)
-      {
-        fprintf(stderr, "%s: %s missing parameter\n", argv[0], arg);
-        exit(EXIT_FAILURE);
-      }
-    };
-    if(strcmp(arg, "-h") == 0 || strcmp(arg, "/?") == 0)
+    const char* name;
+    uint32_t    set, clear;
+  };
+  static const Switch switches[] = {{"-force-no-fast-pipeline", NVPYR_FLAG_FORCE_GENERAL, 0u},
+                                    {"-do-premultiply-alpha", NVPYR_FLAG_PREMULTIPLY_ALPHA, 0u},
+                                    {"-premultiplied-alpha", 0u, NVPYR_FLAG_PREMULTIPLY_ALPHA}};
+  Options opt;
+  int     at = 1;
+  while(at < argc)
+  {
+    const std::string word = argv[at++];
+    if(word == "-h" || word == "--help" || word == "/?")
     {
-      printf(helpString, argv[0]);
+      usage(argv[0], stdout);
       exit(EXIT_SUCCESS);
     }
-    else if(strcmp(arg, "-i") == 0)
-      needed(), rawInputFilename = param0, ++i;
-    else if(strcmp(arg, "-o") == 0)
-      needed(), outputFilenameTemplate = param0, ++i;
-    else if(strcmp(arg, "-force-no-fast-pipeline") == 0)
-      forceDisableFastPipeline = true;
-    else if(strcmp(arg, "-premultiplied-alpha") == 0)
-      doPremultiplyAlpha = false;
-    else if(strcmp(arg, "-do-premultiply-alpha") == 0)
-      doPremultiplyAlpha = true;
-    else
+    std::string* value = word == "-i" ? &opt.input : word == "-o" ? &opt.output : nullptr;
+    if(value != nullptr)
     {
-      fprintf(stderr, "%s: Unknown argument '%s'\n", argv[0], arg);
+      if(at == argc)
+      {
+        fprintf(stderr, "%s: option %s needs a file name\n", argv[0], word.c_str());
+        exit(EXIT_FAILURE);
+      }
+      *value = argv[at++];
+      continue;
+    }
+    bool known = false;
+    for(const Switch& sw : switches)
+      if(word == sw.name)
+      {
+        opt.flags = (opt.flags | sw.set) & ~sw.clear;
+        known     = true;
+      }
+    if(!known)
+    {
+      fprintf(stderr, "%s: unrecognised option '%s'\n\n", argv[0], word.c_str());
+      usage(argv[0], stderr);
       exit(EXIT_FAILURE);
     }
   }
+  return opt;
 }
 
 static void check(nvpyrStatus st, const char* what)
@@ -83,13 +99,13 @@ static void check(nvpyrStatus st, const char* what)
 
 int main(int argc, char** argv)
 {
-  const Config config(argc, argv);
+  const Options opt = parseOptions(argc, argv);
 
   // Load image from file (ScopedImage::stageImage, scoped_image.hpp:210-262).
   void*         pixels = nullptr;
   nvpyrExtent2D extent{};
-  fprintf(stderr, "Loading: '%s'...", config.rawInputFilename.c_str());
-  check(nvpyrReadImage(config.rawInputFilename.c_str(), &pixels, &extent), "nvpyrReadImage");
+  fprintf(stderr, "Loading: '%s'...", opt.input.c_str());
+  check(nvpyrReadImage(opt.input.c_str(), &pixels, &extent), "nvpyrReadImage");
   fprintf(stderr, " done (%u x %u)\n", extent.width, extent.height);
 
   // One staging chain, level 0 in place -- the reference's staging buffer (scoped_image.hpp:436-453).
@@ -101,18 +117,14 @@ int main(int argc, char** argv)
 
   // Upload, premultiply (optional), generate every level, download: replaces
   // cmdReallocUploadImage + nvproCmdPyramidDispatch + cmdDownloadImage (minimal_mipmaps.cpp:134-217).
-  uint32_t flags = NVPYR_FLAG_NONE;
-  if(config.forceDisableFastPipeline)
-    flags |= NVPYR_FLAG_FORCE_GENERAL;  // pipelines.fastPipeline = VK_NULL_HANDLE (:192-196)
-  if(config.doPremultiplyAlpha)
-    flags |= NVPYR_FLAG_PREMULTIPLY_ALPHA;
-  check(nvpyrGenerateHost(chain.data(), chain.data(), extent, 0, NVPYR_FORMAT_SRGBA8, flags), "nvpyrGenerateHost");
+  // NVPYR_FLAG_FORCE_GENERAL stands for pipelines.fastPipeline = VK_NULL_HANDLE (:192-196).
+  check(nvpyrGenerateHost(chain.data(), chain.data(), extent, 0, NVPYR_FORMAT_SRGBA8, opt.flags), "nvpyrGenerateHost");
 
   // Write to disk (writeMipmapsTga, mipmap_storage.hpp:441-479).
-  check(nvpyrWriteChainTga(chain.data(), extent, 0, config.outputFilenameTemplate.c_str()), "nvpyrWriteChainTga");
+  check(nvpyrWriteChainTga(chain.data(), extent, 0, opt.output.c_str()), "nvpyrWriteChainTga");
   char name[4096];
   for(uint32_t level = 0; level < nvpyrGetLevelCount(extent); ++level)
-    if(nvpyrGetLevelFilename(config.outputFilenameTemplate.c_str(), level, name, sizeof name) == NVPYR_SUCCESS)
+    if(nvpyrGetLevelFilename(opt.output.c_str(), level, name, sizeof name) == NVPYR_SUCCESS)
       fprintf(stderr, "Wrote %s\n", name);
   nvpyrShutdown();
   return EXIT_SUCCESS;

@@ -206,7 +206,11 @@ inline nvpyrStatus dispatch(const nvpyrDispatchDesc& desc, const typename S::Par
   if(desc.flags & NVPYR_FLAG_FORCE_GENERAL)
     fast = nullptr;
   else if(fast == nullptr)
+  {
     fast = selectFastDispatcher(desc.fastDivisibility, desc.fastMaxLevels);
+    if(fast == nullptr)
+      return NVPYR_ERROR_UNSUPPORTED;  // like the C ABI: an unknown <Div, Max> pair is an error, never a silent general-only plan
+  }
 
   LevelView lv[NVPYR_MAX_LEVELS];
   uint64_t  off = 0;

@@ -224,6 +224,10 @@ NVPYR_API const char* nvpyrGetErrorString(nvpyrStatus status);
 NVPYR_API int nvpyrGetLastCudaError(void);
 /* Number of kernels the library has launched in this process (for launch accounting). */
 NVPYR_API uint64_t nvpyrGetLaunchCount(void);
+/* Creates the library's per-device state (tables, counters) for the CURRENT device now instead of inside the first
+ * dispatch.  Call it before capturing nvpyrDispatch* into a CUDA graph: the first call on a device allocates and
+ * copies, which a stream capture forbids.  NVPYR_ERROR_UNSUPPORTED on anything but an sm_100 device. */
+NVPYR_API nvpyrStatus nvpyrInit(void);
 /* Frees per-device cached tables. */
 NVPYR_API nvpyrStatus nvpyrShutdown(void);
 NVPYR_API uint32_t    nvpyrGetVersion(void);

@@ -1190,7 +1190,16 @@ void nvo_premultiply_srgba8(const uint8_t* in, uint8_t* out, uint64_t texels)
 
 /* Restatement of shaders/julia.comp:27-63 with the push constants of
  * demo_app/julia.cpp:65-81 (alphaNormalized as given, maxIterations 64). */
+void nvo_julia_srgba8_rows(uint8_t* out, uint32_t w, uint32_t h, uint32_t y_begin, uint32_t y_end,
+                           uint32_t alpha_normalized, int max_iterations);
 void nvo_julia_srgba8(uint8_t* out, uint32_t w, uint32_t h, uint32_t alpha_normalized, int max_iterations)
+{
+  nvo_julia_srgba8_rows(out, w, h, 0, h, alpha_normalized, max_iterations);
+}
+/* Rows [y_begin, y_end) of the same image (out = base of the whole image): lets callers fill a large level 0 from
+ * several host threads. */
+void nvo_julia_srgba8_rows(uint8_t* out, uint32_t w, uint32_t h, uint32_t y_begin, uint32_t y_end,
+                           uint32_t alpha_normalized, int max_iterations)
 {
   const double alphaRadians = alpha_normalized * 1.4629180792671596e-09;
   const float  c_real       = (float)(0.7885 * sin(alphaRadians));
@@ -1198,7 +1207,7 @@ void nvo_julia_srgba8(uint8_t* out, uint32_t w, uint32_t h, uint32_t alpha_norma
   const float  offset_real  = -2.0f;
   const float  scale        = 4.0f / (float)w;
   const float  offset_imag  = 2.0f * (float)h / (float)w;
-  for(uint32_t y = 0; y < h; ++y)
+  for(uint32_t y = y_begin; y < y_end && y < h; ++y)
     for(uint32_t x = 0; x < w; ++x)
     {
       float zr = (float)x * scale + offset_real;

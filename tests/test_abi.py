@@ -134,3 +134,19 @@ nvpyrStatus run(const nvpyrDispatchDesc& d) { return nvpyr::dispatch<LumaMin>(d)
                         os.path.join(ROOT, "include"), str(src), "-o", str(tmp_path / "user.o")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
+
+
+def test_generate_host_rejects_bad_out_buffers(nv):
+    """generate_host(out=...) must not hand an undersized / mistyped / strided buffer to the C ABI (the download
+    would overflow it).  Checked before the library is called: no GPU needed."""
+    import numpy as np
+    l0 = np.zeros((8, 8, 4), dtype=np.uint8)
+    n = nv.chain_bytes(8, 8)
+    for bad in (np.zeros(n - 1, dtype=np.uint8), np.zeros(n, dtype=np.float32), np.zeros(2 * n, dtype=np.uint8)[::2],
+                bytearray(n)):
+        with pytest.raises(ValueError):
+            nv.generate_host(l0, 8, 8, out=bad)
+    ro = np.zeros(n, dtype=np.uint8)
+    ro.flags.writeable = False
+    with pytest.raises(ValueError):
+        nv.generate_host(l0, 8, 8, out=ro)

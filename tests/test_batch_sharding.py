@@ -86,3 +86,25 @@ def test_two_rank_gloo_sharded_batch_matches_single_process():
     for k in range(n_tex):
         chain, _ = o.shader_chain(_oracle.random_level0(32, 32, 1000 + k), 32, 32)
         assert sums[k] == int(np.uint64(batch.fnv1a64(chain)).view(np.int64))
+
+
+def test_device_checksum_equals_numpy_evaluation_and_is_order_sensitive():
+    """The checksum bench.py uses to compare sharded batch runs with the single-GPU run (torch int64 arithmetic,
+    wraps mod 2^64) against an independent numpy uint64 evaluation."""
+    import torch
+    from vk_compute_mipmaps_b200 import batch
+    rng = np.random.default_rng(3)
+    for n in (4, 4 * 1000, 4 * ((1 << 22) + 17)):
+        a = rng.integers(0, 256, n, dtype=np.uint8)
+        w = a.view("<u4").astype(np.uint64)
+        idx = np.arange(w.size, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            mult = (idx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x2545F4914F6CDD1D)) | np.uint64(1)
+            want = int(((w + np.uint64(1)) * mult).sum(dtype=np.uint64))
+        assert batch.device_checksum(torch.from_numpy(a)) == want
+    b = a.copy()
+    b[[5, 70000]] = b[[70000, 5]]
+    assert batch.device_checksum(torch.from_numpy(b)) != want
+    assert batch.fold_checksums([1, 2, 3]) != batch.fold_checksums([3, 2, 1])
+    with pytest.raises(ValueError):
+        batch.device_checksum(torch.zeros(5, dtype=torch.uint8))

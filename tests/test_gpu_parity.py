@@ -502,7 +502,9 @@ def test_minimal_app_equivalent(nv, cuda, oracle, tmp_path):
             assert (gh, gw) == v.shape[:2] and (got == v).all(), (args, level)
         assert ("Wrote " + nv.level_filename(base, 8)) in r.stderr
     r = subprocess.run([exe, "-bogus"], capture_output=True, text=True)
-    assert r.returncode != 0 and "Unknown argument" in r.stderr
+    assert r.returncode != 0 and "unrecognised option '-bogus'" in r.stderr
+    r = subprocess.run([exe, "-i"], capture_output=True, text=True)
+    assert r.returncode != 0 and "needs a file name" in r.stderr
 
 
 def test_user_defined_functor_sets(nv, cuda):
@@ -684,10 +686,13 @@ def test_slab_tasks_of_the_fast_kernel(nv, cuda, oracle, size):
         assert_same(got, want, w, h, oracle, "slab tasks")
 
 
-def test_four_column_strip_kernel_on_every_size(nv, cuda, oracle):
+@pytest.mark.parametrize("staged", ["1", "0"], ids=["cp.async-staged-rows", "per-lane-loads"])
+def test_four_column_strip_kernel_on_every_size(nv, cuda, oracle, staged):
     """generalStrip4Kernel normally takes only large levels; NVPYR_GEN_STRIP4_MIN_TEXELS=0 (with the tail fusion
     off so that small levels reach the stand-alone kernels) runs all its variants -- 1 / 2 levels, 2 or 3 taps
-    per axis on either level, ragged strips and segments -- on sizes the oracle handles quickly."""
+    per axis on either level, ragged strips and segments -- on sizes the oracle handles quickly.  Both ways of
+    fetching the source rows: staged in shared memory by 4-byte cp.async copies (rows whose pitch is not a multiple
+    of 16 bytes are realigned on the way; the default) and with per-lane 4-byte loads (NVPYR_GEN_STAGED=0)."""
     import subprocess
     import sys
     code = (
@@ -706,7 +711,7 @@ def test_four_column_strip_kernel_on_every_size(nv, cuda, oracle):
         "        torch.cuda.synchronize()\n"
         "        assert (buf.cpu().numpy() == o.shader_chain(l0, w, h, force_general=fg)[0]).all(), (w, h, fg)\n"
         "print('strip4 ok')\n") % (_oracle.ROOT, os.path.join(_oracle.ROOT, "tests"))
-    env = dict(os.environ, NVPYR_GEN_STRIP4_MIN_TEXELS="0", NVPYR_TAIL_MAX_TEXELS="0")
+    env = dict(os.environ, NVPYR_GEN_STRIP4_MIN_TEXELS="0", NVPYR_TAIL_MAX_TEXELS="0", NVPYR_GEN_STAGED=staged)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "strip4 ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
@@ -869,3 +874,136 @@ def test_fused_batch_at_the_benchmarked_size(nv, cuda, oracle):
     assert nv.launch_count() - before == 2
     for k, (b, want) in enumerate(zip(imgs, wants)):
         assert_same(b.cpu().numpy(), want, w, h, oracle, f"texture {k}")
+
+
+def test_batch_recorded_into_a_graph(nv, cuda, oracle):
+    """nvpyrDispatchBatch under stream capture must not record its base-pointer upload (a copy from a
+    host vector that is gone at replay time): it falls back to one dispatch per image while capturing, and the
+    replayed graph produces the oracle's bits for new level-0 contents, also while live batches keep running."""
+    w, h = 1024, 512
+    count = 4
+    nv.init()
+    bufs = [cuda.zeros(nv.chain_bytes(w, h), dtype=cuda.uint8, device="cuda") for _ in range(count)]
+    live = [cuda.zeros(nv.chain_bytes(w, h), dtype=cuda.uint8, device="cuda") for _ in range(count)]
+    pipes = nv.PyramidPipelines()
+    nv.dispatch_batch(None, pipes, bufs, w, h)  # warm: launch configurations cached
+    cuda.cuda.synchronize()
+    g = cuda.cuda.CUDAGraph()
+    with cuda.cuda.graph(g):
+        nv.dispatch_batch(None, pipes, bufs, w, h)
+    side = cuda.cuda.Stream()
+    for frame in range(3):
+        l0s = [_oracle.random_level0(w, h, 40 + 10 * frame + k) for k in range(count)]
+        for b, lb, l0 in zip(bufs, live, l0s):
+            b.zero_()
+            lb.zero_()
+            b[:4 * w * h] = cuda.from_numpy(l0).cuda()
+            lb[:4 * w * h] = b[:4 * w * h]
+        cuda.cuda.synchronize()
+        g.replay()
+        nv.dispatch_batch(side, pipes, live, w, h)  # a live fused batch on another stream at the same time
+        cuda.cuda.synchronize()
+        for k, l0 in enumerate(l0s):
+            want, _ = oracle.shader_chain(l0, w, h)
+            assert_same(bufs[k].cpu().numpy(), want, w, h, oracle, f"replayed batch, frame {frame}, image {k}")
+            assert_same(live[k].cpu().numpy(), want, w, h, oracle, f"live batch, frame {frame}, image {k}")
+
+
+def test_ticket_counters_are_never_shared_between_unordered_launches(nv, cuda, oracle):
+    """the tail kernel's 'last CTA' counter belongs to ONE stream (or to one captured launch).  Many
+    streams, two graphs replayed concurrently with live dispatches: every chain must still be complete."""
+    w, h = 1920, 1080  # fast 3, then a tail launch with a grid step and solo steps
+    l0 = _oracle.random_level0(w, h, 77)
+    want, _ = oracle.shader_chain(l0, w, h)
+    pipes = nv.PyramidPipelines()
+    nv.init()
+    streams = [cuda.cuda.Stream() for _ in range(24)]
+    bufs = [cuda.zeros(nv.chain_bytes(w, h), dtype=cuda.uint8, device="cuda") for _ in range(len(streams) + 2)]
+    nv.cmd_pyramid_dispatch(None, pipes, w, h, image=bufs[0])
+    cuda.cuda.synchronize()
+    graphs = []
+    for b in bufs[-2:]:
+        g = cuda.cuda.CUDAGraph()
+        with cuda.cuda.graph(g):
+            nv.cmd_pyramid_dispatch(None, pipes, w, h, image=b)
+        graphs.append(g)
+    for rnd in range(5):
+        for b in bufs:
+            b.zero_()
+            b[:4 * w * h] = cuda.from_numpy(l0).cuda()
+        cuda.cuda.synchronize()
+        for g in graphs:
+            g.replay()
+        for s, b in zip(streams, bufs):
+            nv.cmd_pyramid_dispatch(s, pipes, w, h, image=b)
+        for g in graphs:
+            g.replay()
+        cuda.cuda.synchronize()
+        for k, b in enumerate(bufs):
+            assert_same(b.cpu().numpy(), want, w, h, oracle, f"round {rnd}, buffer {k}")
+
+
+def test_slab_task_hand_off_stress(nv, cuda, oracle):
+    """The slab-task mode hands a tile's level +3 sums from the warps that made them to the warp that arrives last
+    (store -> fence -> shared atomic -> fence -> load, no barrier).  compute-sanitizer's racecheck models barriers
+    only, so the evidence is volume: thousands of launches over sizes with different tile / slab interleavings,
+    every result compared ON THE DEVICE with the oracle's chain."""
+    torch = cuda
+    sizes = [(1024, 1024), (2048, 1024), (512, 2048), (1040, 528), (1056, 1056), (1024, 64), (64, 1024), (1984, 1088)]
+    pipes = nv.PyramidPipelines()
+    for (w, h) in sizes:
+        l0 = _oracle.random_level0(w, h, w ^ h)
+        want = torch.from_numpy(oracle.shader_chain(l0, w, h)[0]).cuda()
+        n = nv.chain_bytes(w, h)
+        bufs = [torch.zeros(n, dtype=torch.uint8, device="cuda") for _ in range(4)]
+        for b in bufs:
+            b[:4 * w * h] = want[:4 * w * h]
+        bad = torch.zeros((), dtype=torch.int64, device="cuda")
+        for it in range(400):
+            b = bufs[it & 3]
+            b[4 * w * h:].zero_()
+            nv.cmd_pyramid_dispatch(None, pipes, w, h, image=b)
+            bad += (b != want).sum()
+        assert int(bad.item()) == 0, (w, h, int(bad.item()))
+
+
+def test_concurrent_host_round_trips_and_pageable_callers(nv, cuda, oracle):
+    """nvpyrGenerateHost takes a pipeline (scratch chain, streams, staging) from a per-device pool instead of
+    holding one lock for the whole call: four host threads at once, pinned and PAGEABLE buffers (the latter pass
+    through the pinned staging chain band by band), in place and with separate buffers, at a size that is banded
+    with the default 32 MB bands (4096^2: 64 MB of level 0)."""
+    import threading
+    torch = cuda
+    w = h = 4096
+    n = nv.chain_bytes(w, h)
+    l0 = _oracle.random_level0(w, h, 31)
+    want, _ = oracle.shader_chain(l0, w, h)
+    errors = []
+
+    def worker(t):
+        try:
+            for rnd in range(2):
+                if t % 2 == 0:  # pageable, in place
+                    chain = np.zeros(n, dtype=np.uint8)
+                    chain[:4 * w * h] = l0
+                    nv.generate_host(chain[:4 * w * h], w, h, out=chain)
+                    got = chain
+                else:  # pinned in, pageable out
+                    pin = torch.from_numpy(l0.copy()).pin_memory()
+                    got = nv.generate_host(pin.numpy(), w, h)
+                if not (got == want).all():
+                    errors.append((t, rnd))
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    # pageable premultiplied in place: level 0 comes back changed
+    raw = _oracle.random_level0(2048, 8192, 5)
+    pm = oracle.premultiply(raw)
+    want2, _ = oracle.shader_chain(pm, 2048, 8192)
+    chain = np.zeros(nv.chain_bytes(2048, 8192), dtype=np.uint8)
+    chain[:raw.size] = raw
+    nv.generate_host(chain[:raw.size], 2048, 8192, flags=nv.FLAG_PREMULTIPLY_ALPHA, out=chain)
+    assert (chain == want2).all()

@@ -45,3 +45,37 @@ def fnv1a64(data):
             else:
                 h = h * (P ** np.uint64(k)) + np.sum(c * pw[block - k:], dtype=np.uint64)
     return int(h)
+
+
+_MIX_A = 0x9E3779B97F4A7C15 - (1 << 64)   # as signed 64-bit constants (torch int64 arithmetic wraps mod 2^64)
+_MIX_B = 0x2545F4914F6CDD1D
+
+
+def device_checksum(chain):
+    """Order-sensitive 64-bit checksum of a packed chain that stays on the device it lives on.
+
+    ``chain``: 1-D torch uint8 tensor whose length is a multiple of 4 (CPU or CUDA).  Word i (little-endian
+    uint32) contributes (word + 1) * (i * A + B | 1) mod 2^64.  Used by the batch bench to compare the outputs of
+    sharded runs (texture k on rank k % world) with the single-GPU run without moving 45 GB through the host.
+    Returns a Python int in [0, 2^64).
+    """
+    import torch
+    if chain.dtype != torch.uint8 or chain.dim() != 1 or chain.numel() % 4:
+        raise ValueError("device_checksum expects a flat uint8 tensor of whole texels")
+    words = chain.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    total = 0
+    block = 1 << 22
+    for s in range(0, words.numel(), block):  # blocks bound the temporaries (32 MB each)
+        w = words[s:s + block]
+        idx = torch.arange(s, s + w.numel(), dtype=torch.int64, device=chain.device)
+        mult = (idx * _MIX_A + _MIX_B) | 1
+        total = (total + int(((w + 1) * mult).sum().item())) & 0xFFFFFFFFFFFFFFFF
+    return total
+
+
+def fold_checksums(values):
+    """Checksum of checksums, order-sensitive (values: iterable of ints in texture-index order)."""
+    h = 14695981039346656037
+    for v in values:
+        h = ((h ^ (int(v) & 0xFFFFFFFFFFFFFFFF)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h

@@ -6,11 +6,13 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <deque>
 #include <map>
 #include <type_traits>
 #include <utility>
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/nvpyr.h"
@@ -119,11 +121,19 @@ bool buildHostTables(DeviceTables& t)
 }
 
 // ------------------------------------------------------------ device context
-// Tail launches in flight at the same time each need their own ticket counter.
+// Ticket counters of tailKernel ("which CTA finished the grid step last").  A counter may only be shared by
+// launches that are ordered one after the other, so: every STREAM owns one slot (launches of a stream are ordered;
+// each kernel executes griddepcontrol.wait before it touches anything, so with programmatic dependent launch the
+// counter is still used by one launch at a time), and every launch recorded into a CUDA GRAPH gets a dedicated slot
+// that is never recycled (a graph may be replayed on any stream while live launches go on; launches of one
+// executable graph are ordered among themselves by CUDA).  Exhaustion is an error (NVPYR_ERROR_OUT_OF_MEMORY),
+// never a silently shared counter: at most kTicketPool streams + captured tail launches per device and process.
 constexpr uint32_t kTicketPool = 4096;
 
 constexpr uint32_t kMaxHostBands = 64;
 constexpr uint32_t kBatchRing    = 1u << 17;  // base pointers (1 MB); a batch takes a contiguous slice
+
+struct HostPipeline;
 
 struct DeviceContext
 {
@@ -131,17 +141,26 @@ struct DeviceContext
   int           smCount  = 0;
   DeviceTables* tables   = nullptr;
   uint32_t*     tickets  = nullptr;  // kTicketPool zero-initialised counters for tailKernel
-  std::atomic<uint32_t> nextTicket{0};
-  // nvpyrDispatchBatch: ring of device words holding the chain base pointers of batched launches
+  std::mutex                       ticketMutex;
+  std::map<cudaStream_t, uint32_t> ticketOfStream;
+  uint32_t                         ticketsUsed = 0;
+  // nvpyrDispatchBatch: ring of device words holding the chain base pointers of batched launches.  A slice stays
+  // reserved until the event recorded behind the batch's last kernel has completed.
   const unsigned char** batchBases = nullptr;
-  std::atomic<uint64_t> batchCursor{0};
-  void*         scratch  = nullptr;  // nvpyrGenerateHost staging chain
-  size_t        scratchBytes = 0;
-  std::mutex    scratchMutex;
-  // nvpyrGenerateHost pipeline: upload, compute and download run on three streams so that the two
-  // PCIe directions and the kernels overlap band by band (created on first use, under scratchMutex).
-  cudaStream_t  hostUp = nullptr, hostRun = nullptr, hostDown = nullptr;
-  cudaEvent_t   hostEvUp[kMaxHostBands] = {}, hostEvRun[kMaxHostBands + 1] = {};
+  struct BatchSlice
+  {
+    uint64_t    begin, end;  // positions in the unwrapped ring
+    cudaEvent_t done;
+  };
+  std::mutex                    batchMutex;
+  std::deque<BatchSlice>        batchInFlight;
+  std::vector<cudaEvent_t>      batchEventPool;
+  uint64_t                      batchHead = 0;     // next free position (unwrapped)
+  bool          genWindowOk = false;  // the strip kernels' absolute shared-memory addresses are valid on this device
+  // nvpyrGenerateHost: a small pool of independent pipelines (device scratch chain + three streams + events), so
+  // that concurrent round trips on one device do not serialise on one scratch buffer.
+  std::mutex                 hostMutex;
+  std::vector<HostPipeline*> hostIdle;
 };
 
 std::mutex                  g_ctxMutex;
@@ -160,39 +179,44 @@ nvpyrStatus getContext(DeviceContext** out)
     }
   cudaDeviceProp prop;
   NVPYR_CUDA(cudaGetDeviceProperties(&prop, dev));
-  if(prop.major != 10)
-    return NVPYR_ERROR_UNSUPPORTED;  // kernels are built for sm_100a only
+  if(prop.major != 10 || prop.minor != 0)
+    return NVPYR_ERROR_UNSUPPORTED;  // the kernels are built for sm_100a only (arch-specific: no other 10.x part runs them)
   static DeviceTables host;
-  if(!buildHostTables(host))
+  static const bool   hostOk = buildHostTables(host);
+  if(!hostOk)
     return NVPYR_ERROR_UNSUPPORTED;
-  DeviceTables* d = nullptr;
-  NVPYR_CUDA(cudaMalloc(&d, sizeof(DeviceTables)));
-  cudaError_t e = cudaMemcpy(d, &host, sizeof(DeviceTables), cudaMemcpyHostToDevice);
-  if(e != cudaSuccess)
-  {
-    cudaFree(d);
-    g_lastCudaError = int(e);
-    return NVPYR_ERROR_CUDA;
-  }
-  uint32_t* tickets = nullptr;
-  e                 = cudaMalloc(&tickets, kTicketPool * sizeof(uint32_t));
+  DeviceTables*         d       = nullptr;
+  uint32_t*             tickets = nullptr;
+  const unsigned char** ring    = nullptr;
+  uint32_t*             probe   = nullptr;
+  cudaError_t           e       = cudaMalloc(&d, sizeof(DeviceTables));
+  if(e == cudaSuccess)
+    e = cudaMemcpy(d, &host, sizeof(DeviceTables), cudaMemcpyHostToDevice);
+  if(e == cudaSuccess)
+    e = cudaMalloc(&tickets, kTicketPool * sizeof(uint32_t));
   if(e == cudaSuccess)
     e = cudaMemset(tickets, 0, kTicketPool * sizeof(uint32_t));
-  if(e != cudaSuccess)
+  if(e == cudaSuccess)
+    e = cudaMalloc(&ring, size_t(kBatchRing) * sizeof(void*));
+  // Where does the dynamic shared-memory window of a kernel without static shared memory start on this
+  // device / driver?  The strip kernels address their tables absolutely (nvpyr_general_srgba8.cuh); if the answer
+  // is not what they were built for, sRGBA8 general steps take the functor-template kernel instead.
+  uint32_t windowBase = 0;
+  if(e == cudaSuccess)
+    e = cudaMalloc(&probe, sizeof(uint32_t));
+  if(e == cudaSuccess)
   {
-    cudaFree(d);
-    cudaFree(tickets);
-    g_lastCudaError = int(e);
-    return NVPYR_ERROR_CUDA;
+    genWindowProbeKernel<<<1, 32, 1024>>>(probe);
+    e = cudaMemcpy(&windowBase, probe, sizeof(uint32_t), cudaMemcpyDeviceToHost);
   }
-  const unsigned char** ring = nullptr;
-  e                          = cudaMalloc(&ring, size_t(kBatchRing) * sizeof(void*));
+  cudaFree(probe);
   if(e != cudaSuccess)
   {
     cudaFree(d);
     cudaFree(tickets);
+    cudaFree(ring);
     g_lastCudaError = int(e);
-    return NVPYR_ERROR_CUDA;
+    return e == cudaErrorMemoryAllocation ? NVPYR_ERROR_OUT_OF_MEMORY : NVPYR_ERROR_CUDA;
   }
   DeviceContext* c = new DeviceContext;
   c->batchBases    = ring;
@@ -200,8 +224,45 @@ nvpyrStatus getContext(DeviceContext** out)
   c->smCount       = prop.multiProcessorCount;
   c->tables        = d;
   c->tickets       = tickets;
+  c->genWindowOk   = windowBase == kGenWindowBase;
   g_ctx.push_back(c);
   *out = c;
+  return NVPYR_SUCCESS;
+}
+
+// Is `stream` being captured into a CUDA graph?  (Legacy-stream queries fail while another stream captures in
+// global mode; that counts as "capturing": the caller must not do anything a capture forbids.)
+bool streamIsCapturing(cudaStream_t stream)
+{
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if(cudaStreamIsCapturing(stream, &st) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return true;
+  }
+  return st != cudaStreamCaptureStatusNone;
+}
+
+// The ticket counter a tail launch on `stream` may use (see kTicketPool).
+nvpyrStatus acquireTicket(DeviceContext& ctx, cudaStream_t stream, uint32_t** ticket)
+{
+  const bool                  capturing = streamIsCapturing(stream);
+  std::lock_guard<std::mutex> lock(ctx.ticketMutex);
+  if(!capturing)
+  {
+    auto it = ctx.ticketOfStream.find(stream);
+    if(it != ctx.ticketOfStream.end())
+    {
+      *ticket = ctx.tickets + it->second;
+      return NVPYR_SUCCESS;
+    }
+  }
+  if(ctx.ticketsUsed >= kTicketPool)
+    return NVPYR_ERROR_OUT_OF_MEMORY;  // documented limit; never share a counter between unordered launches
+  const uint32_t slot = ctx.ticketsUsed++;
+  if(!capturing)
+    ctx.ticketOfStream[stream] = slot;
+  *ticket = ctx.tickets + slot;
   return NVPYR_SUCCESS;
 }
 
@@ -276,6 +337,22 @@ bool tunedFastOk(const LevelView* lv)
   return std::is_same<F, Srgba8>::value && !g_forceGenericFast && fastVectorOk<F>(lv);
 }
 
+// cuTensorMapEncodeTiled, looked up at run time (libcuda is not linked).
+using TensorMapEncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensorMapEncoder()
+{
+  static const TensorMapEncodeFn encode = [] {
+    void*                           f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess)
+      f = nullptr;
+    return reinterpret_cast<TensorMapEncodeFn>(f);
+  }();
+  return encode;
+}
+
 // NVPYR_NO_SLAB_TASKS=1: always one warp per tile in the tuned fast kernel (A/B timing).
 const bool g_noSlabTasks = [] {
   const char* e = getenv("NVPYR_NO_SLAB_TASKS");
@@ -296,16 +373,7 @@ nvpyrStatus launchFastSrgba8K(const DeviceContext& ctx, const FastParams& p, con
   if(!kBatch && !kPremul && !kSlabTasks)
   {
     // 2-D tensor map of the step's input level: W x H texels of 4 bytes, row pitch in bytes, box 64 x 8
-    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static const EncodeFn encode = [] {
-      void*                           f = nullptr;
-      cudaDriverEntryPointQueryResult q;
-      if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess)
-        f = nullptr;
-      return reinterpret_cast<EncodeFn>(f);
-    }();
+    const TensorMapEncodeFn encode = tensorMapEncoder();
     if(encode == nullptr)
       return NVPYR_ERROR_UNSUPPORTED;
     const cuuint64_t dims[2]    = {p.lv[0].w, p.lv[0].h};
@@ -446,17 +514,24 @@ const uint64_t g_genStrip4MinTexels = [] {
   return e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : 4000000ull;
 }();
 
+// NVPYR_GEN_STAGED=0: the four-column strip kernel loads its rows with per-lane 4-byte loads into registers instead
+// of staging them in shared memory with cp.async (A/B timing).
+const bool g_genStaged = [] {
+  const char* e = getenv("NVPYR_GEN_STAGED");
+  return e == nullptr || e[0] != '0';
+}();
+
 // The four-columns-per-lane sRGBA8 strip kernel (generalStrip4Kernel): strips of 62 (+1 halo) level +1 columns.
-template <int kLevels, bool kX3, bool kY3>
-nvpyrStatus launchGeneralStrip4T(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
+template <int kLevels, bool kX3, bool kY3, bool kStaged>
+nvpyrStatus launchGeneralStrip4K(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
 {
   GenStripParams p{};
   p.lv[0] = gp.lv[0], p.lv[1] = gp.lv[1], p.lv[2] = gp.lv[2];
   p.tables            = ctx.tables;
   p.stripsX           = std::max(1u, (gp.lv[1].w - 1u + 61u) / 62u);
-  const size_t smem   = kGenSmemBytes;
+  const size_t smem   = kStaged ? kGenStagedSmemBytes : kGenSmemBytes;
   int          perSm  = 0;
-  nvpyrStatus  st     = blocksPerSm(reinterpret_cast<const void*>(generalStrip4Kernel<kLevels, kX3, kY3>), smem,
+  nvpyrStatus  st     = blocksPerSm(reinterpret_cast<const void*>(generalStrip4Kernel<kLevels, kX3, kY3, kStaged>), smem,
                                     kGen4Warps * 32, ctx.device, &perSm);
   if(st != NVPYR_SUCCESS)
     return st;
@@ -468,10 +543,19 @@ nvpyrStatus launchGeneralStrip4T(const DeviceContext& ctx, const GeneralParams& 
   p.segsY                = (rows + p.segRows - 1) / p.segRows;
   const uint64_t tasks   = uint64_t(p.stripsX) * p.segsY;
   const uint64_t ctas    = std::min<uint64_t>(uint64_t(perSm) * ctx.smCount, (tasks + kGen4Warps - 1) / kGen4Warps);
-  NVPYR_CUDA(launchKernel(generalStrip4Kernel<kLevels, kX3, kY3>, int(std::max<uint64_t>(1, ctas)), kGen4Warps * 32, smem,
+  NVPYR_CUDA(launchKernel(generalStrip4Kernel<kLevels, kX3, kY3, kStaged>, int(std::max<uint64_t>(1, ctas)), kGen4Warps * 32, smem,
                           stream, p));
   ++g_launchCount;
   return NVPYR_SUCCESS;
+}
+
+template <int kLevels, bool kX3, bool kY3>
+nvpyrStatus launchGeneralStrip4T(const DeviceContext& ctx, const GeneralParams& gp, cudaStream_t stream)
+{
+  // (4-byte copies: the level base and pitch are multiples of the texel size by contract)
+  if(g_genStaged)
+    return launchGeneralStrip4K<kLevels, kX3, kY3, true>(ctx, gp, stream);
+  return launchGeneralStrip4K<kLevels, kX3, kY3, false>(ctx, gp, stream);
 }
 
 template <int kLevels>
@@ -533,7 +617,9 @@ nvpyrStatus launchGeneral(const DeviceContext& ctx, GeneralParams p, cudaStream_
   p.tables = ctx.tables;
   // Tuned path (sRGBA8, rgba32f): no 1-texel-wide/high level involved (those use kernel size 1).
   using Codec = typename StripCodec<F>::type;
-  if(!std::is_same<Codec, void>::value && !g_forceGenericFast && p.lv[0].w >= 2 && p.lv[0].h >= 2
+  constexpr bool kAbsoluteTables = std::is_same<Codec, GenCodecSrgba8>::value;  // needs the expected window base
+  if(!std::is_same<Codec, void>::value && !g_forceGenericFast && (ctx.genWindowOk || !kAbsoluteTables) && p.lv[0].w >= 2
+     && p.lv[0].h >= 2
      && (p.levels == 1 || (p.lv[1].w >= 2 && p.lv[1].h >= 2)))
     return launchGeneralTuned<Codec>(ctx, p, stream);
   generalTiles(p.lv, p.levels, kGenTile2, &p.tilesX, &p.tilesY);
@@ -684,7 +770,9 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
   TailParams tp{};
   tp.numSteps = uint32_t(count);
   tp.tables   = ctx.tables;
-  tp.ticket   = ctx.tickets + (ctx.nextTicket.fetch_add(1) % kTicketPool);
+  nvpyrStatus tst = acquireTicket(ctx, r.stream, &tp.ticket);
+  if(tst != NVPYR_SUCCESS)
+    return tst;
   for(int i = 0; i < count; ++i)
   {
     const nvpyrPlanStep& s  = steps[i];
@@ -857,18 +945,69 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
   if(!fastVectorOk<Srgba8>(a.lv))
     return NVPYR_SUCCESS;
 
-  // chain base pointers -> a slice of the device ring
+  // Under stream capture the fused path is not taken: its base-pointer upload would be recorded as a copy from
+  // host memory that is gone at replay time, and the ring slice would be baked into the graph.
+  if(streamIsCapturing(a.stream))
+    return NVPYR_SUCCESS;
+
+  // chain base pointers -> a slice of the device ring, reserved until this batch's last kernel has completed
+  const unsigned char** devBases = nullptr;
+  cudaEvent_t           doneEvent = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(ctx.batchMutex);
+    auto reclaim = [&](bool wait) {
+      while(!ctx.batchInFlight.empty())
+      {
+        DeviceContext::BatchSlice& f = ctx.batchInFlight.front();
+        const cudaError_t q = wait ? cudaEventSynchronize(f.done) : cudaEventQuery(f.done);
+        if(q != cudaSuccess)
+        {
+          cudaGetLastError();  // cudaErrorNotReady is not an error
+          return;
+        }
+        ctx.batchEventPool.push_back(f.done);
+        ctx.batchInFlight.pop_front();
+        if(wait)
+          return;
+      }
+    };
+    reclaim(false);
+    for(;;)
+    {
+      uint64_t begin = ctx.batchHead;
+      if(begin % kBatchRing + count > kBatchRing)
+        begin += kBatchRing - begin % kBatchRing;  // a slice never wraps: skip to the start of the ring
+      const uint64_t tail = ctx.batchInFlight.empty() ? begin : ctx.batchInFlight.front().begin;
+      if(begin + count - tail <= kBatchRing)
+      {
+        ctx.batchHead = begin + count;
+        devBases      = ctx.batchBases + begin % kBatchRing;
+        if(ctx.batchEventPool.empty())
+          NVPYR_CUDA(cudaEventCreateWithFlags(&doneEvent, cudaEventDisableTiming));
+        else
+        {
+          doneEvent = ctx.batchEventPool.back();
+          ctx.batchEventPool.pop_back();
+        }
+        ctx.batchInFlight.push_back({begin, begin + count, doneEvent});
+        break;
+      }
+      reclaim(true);  // ring full of batches still in flight: wait for the oldest one instead of overwriting it
+    }
+  }
+  // From here on every exit records doneEvent on the stream (a slice whose event was never recorded would be
+  // reclaimed at once, which is right if nothing was enqueued, and the stream order covers what was).
+  struct RecordDone
+  {
+    cudaEvent_t  e;
+    cudaStream_t s;
+    ~RecordDone() { cudaEventRecord(e, s); }
+  } recordDone{doneEvent, a.stream};
+  // The pointers travel as kernel-launch-sized chunks of a memcpy node fed from a std::vector: cudaMemcpyAsync from
+  // pageable memory returns once the source has been staged, so the vector may die when this function returns.
   std::vector<const unsigned char*> hostBases(count);
   for(uint32_t i = 0; i < count; ++i)
     hostBases[i] = r[i].lv[0].ptr;
-  uint64_t start;
-  for(;;)
-  {
-    start = ctx.batchCursor.fetch_add(count) % kBatchRing;
-    if(start + count <= kBatchRing)
-      break;  // (a slice that would wrap is skipped)
-  }
-  const unsigned char** devBases = ctx.batchBases + start;
   NVPYR_CUDA(cudaMemcpyAsync(devBases, hostBases.data(), size_t(count) * sizeof(void*), cudaMemcpyHostToDevice, a.stream));
   *handled = true;  // from here on errors are real errors
 
@@ -933,20 +1072,117 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
 }
 
 // ------------------------------------------------- host round trip, pipelined
-nvpyrStatus hostPipelineInit(DeviceContext& ctx)
+// One independent round-trip pipeline: device scratch chain, three streams (upload, compute, download), the events
+// that chain them band by band, and -- for callers with pageable memory -- a pinned staging chain.  A call takes an
+// idle pipeline from the device's pool (or makes a new one) and gives it back when it returns, so concurrent
+// nvpyrGenerateHost calls on one device run side by side.
+struct HostPipeline
 {
-  if(ctx.hostUp != nullptr)
-    return NVPYR_SUCCESS;
-  cudaStream_t s[3] = {};
-  for(int i = 0; i < 3; ++i)
-    NVPYR_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+  void*          scratch = nullptr;
+  size_t         scratchBytes = 0;
+  cudaStream_t   up = nullptr, run = nullptr, down = nullptr;
+  cudaEvent_t    evUp[kMaxHostBands] = {}, evRun[kMaxHostBands + 1] = {}, evDown[kMaxHostBands + 1] = {};
+  unsigned char* stage = nullptr;  // pinned, stageBytes
+  size_t         stageBytes = 0;
+};
+
+void destroyHostPipeline(HostPipeline* hp)
+{
+  if(hp == nullptr)
+    return;
+  if(hp->scratch)
+    cudaFree(hp->scratch);
+  if(hp->stage)
+    cudaFreeHost(hp->stage);
+  for(cudaStream_t st : {hp->up, hp->run, hp->down})
+    if(st)
+      cudaStreamDestroy(st);
+  for(cudaEvent_t e : hp->evUp)
+    if(e)
+      cudaEventDestroy(e);
+  for(cudaEvent_t e : hp->evRun)
+    if(e)
+      cudaEventDestroy(e);
+  for(cudaEvent_t e : hp->evDown)
+    if(e)
+      cudaEventDestroy(e);
+  delete hp;
+}
+
+nvpyrStatus createHostPipeline(HostPipeline** out)
+{
+  HostPipeline* hp = new HostPipeline;
+  auto          fail = [&](cudaError_t e) {
+    g_lastCudaError = int(e);
+    destroyHostPipeline(hp);
+    return NVPYR_ERROR_CUDA;
+  };
+  cudaError_t e;
+  for(cudaStream_t* st : {&hp->up, &hp->run, &hp->down})
+    if((e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking)) != cudaSuccess)
+      return fail(e);
   for(uint32_t i = 0; i < kMaxHostBands; ++i)
-    NVPYR_CUDA(cudaEventCreateWithFlags(&ctx.hostEvUp[i], cudaEventDisableTiming));
+    if((e = cudaEventCreateWithFlags(&hp->evUp[i], cudaEventDisableTiming)) != cudaSuccess)
+      return fail(e);
   for(uint32_t i = 0; i <= kMaxHostBands; ++i)
-    NVPYR_CUDA(cudaEventCreateWithFlags(&ctx.hostEvRun[i], cudaEventDisableTiming));
-  ctx.hostRun = s[1], ctx.hostDown = s[2];
-  ctx.hostUp  = s[0];  // last: marks the pipeline as complete
+  {
+    if((e = cudaEventCreateWithFlags(&hp->evRun[i], cudaEventDisableTiming)) != cudaSuccess)
+      return fail(e);
+    if((e = cudaEventCreateWithFlags(&hp->evDown[i], cudaEventDisableTiming)) != cudaSuccess)
+      return fail(e);
+  }
+  *out = hp;
   return NVPYR_SUCCESS;
+}
+
+// Takes an idle pipeline whose scratch chain holds `bytes` (growing it if need be).
+nvpyrStatus acquireHostPipeline(DeviceContext& ctx, uint64_t bytes, HostPipeline** out)
+{
+  HostPipeline* hp = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(ctx.hostMutex);
+    for(size_t i = 0; i < ctx.hostIdle.size(); ++i)  // prefer one that is already large enough
+      if(ctx.hostIdle[i]->scratchBytes >= bytes)
+      {
+        hp = ctx.hostIdle[i];
+        ctx.hostIdle.erase(ctx.hostIdle.begin() + i);
+        break;
+      }
+    if(hp == nullptr && !ctx.hostIdle.empty())
+    {
+      hp = ctx.hostIdle.back();
+      ctx.hostIdle.pop_back();
+    }
+  }
+  if(hp == nullptr)
+  {
+    nvpyrStatus st = createHostPipeline(&hp);
+    if(st != NVPYR_SUCCESS)
+      return st;
+  }
+  if(hp->scratchBytes < bytes)
+  {
+    if(hp->scratch)
+      cudaFree(hp->scratch);
+    hp->scratch      = nullptr;
+    hp->scratchBytes = 0;
+    const cudaError_t e = cudaMalloc(&hp->scratch, bytes);
+    if(e != cudaSuccess)
+    {
+      g_lastCudaError = int(e);
+      destroyHostPipeline(hp);
+      return e == cudaErrorMemoryAllocation ? NVPYR_ERROR_OUT_OF_MEMORY : NVPYR_ERROR_CUDA;
+    }
+    hp->scratchBytes = bytes;
+  }
+  *out = hp;
+  return NVPYR_SUCCESS;
+}
+
+void releaseHostPipeline(DeviceContext& ctx, HostPipeline* hp)
+{
+  std::lock_guard<std::mutex> lock(ctx.hostMutex);
+  ctx.hostIdle.push_back(hp);
 }
 
 // Band height (rows of level 0) of the pipelined round trip; 0 = do not band.  NVPYR_HOST_BAND_BYTES
@@ -955,19 +1191,66 @@ const uint64_t kHostBandBytes = [] {
   const char* e = getenv("NVPYR_HOST_BAND_BYTES");
   return e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : 32ull << 20;
 }();
+// Host threads that move a pageable caller's bands into / out of the pinned staging chain (NVPYR_HOST_COPY_THREADS).
+const unsigned kHostCopyThreads = [] {
+  const char* e = getenv("NVPYR_HOST_COPY_THREADS");
+  if(e != nullptr)
+    return unsigned(std::max(1, atoi(e)));
+  const unsigned hw = std::thread::hardware_concurrency();
+  return std::max(1u, std::min(8u, hw ? hw : 4u));
+}();
+
+// memcpy split over host threads (one thread cannot saturate the host memory system: ~10 GB/s against a PCIe 5 link
+// that takes 50+).
+void parallelCopy(void* dst, const void* src, size_t bytes)
+{
+  const size_t   kMinChunk = 4u << 20;
+  const unsigned n = unsigned(std::min<size_t>(kHostCopyThreads, std::max<size_t>(1, bytes / kMinChunk)));
+  if(n <= 1)
+  {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t             chunk = ((bytes + n - 1) / n + 4095) & ~size_t(4095);
+  std::vector<std::thread> ts;
+  for(unsigned i = 1; i < n; ++i)
+  {
+    const size_t off = size_t(i) * chunk;
+    if(off < bytes)
+      ts.emplace_back([=] { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, std::min(chunk, bytes - off)); });
+  }
+  memcpy(dst, src, std::min(chunk, bytes));
+  for(std::thread& t : ts)
+    t.join();
+}
+
+// Is this host pointer pageable (neither cudaHostAlloc'ed nor cudaHostRegister'ed)?  Copies from / to such memory are
+// staged by the driver and block the calling thread, which would serialise the three streams of the pipeline.
+bool isPageable(const void* p)
+{
+  cudaPointerAttributes a;
+  if(cudaPointerGetAttributes(&a, p) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
 
 // Upload, generate, download -- the shape of minimal_app (minimal_mipmaps.cpp:134-217) -- with the three
 // stages overlapped.  When the chain starts with a fast-pipeline step of M >= 2 levels, level 0 is cut
 // into bands of whole tile rows (a multiple of 2^M rows: no texel of levels 1..M depends on two bands,
-// and the float32 expression trees are untouched).  Band b is uploaded on stream `hostUp`; the step runs on it on
-// `hostRun` as soon as it has arrived; its rows of levels 1 and 2 (and 0, unless the caller's chain
-// already holds it) go back on `hostDown` while band b+1 is still arriving: both PCIe directions and the
+// and the float32 expression trees are untouched).  Band b is uploaded on stream `up`; the step runs on it on
+// `run` as soon as it has arrived; its rows of levels 1 and 2 (and 0, unless the caller's chain
+// already holds it) go back on `down` while band b+1 is still arriving: both PCIe directions and the
 // SMs are busy at once.  The rest of the plan and the small levels follow in one piece.
 // In place (hostChain == hostLevel0, the reference's single staging buffer, scoped_image.hpp:436-453)
 // level 0 is not downloaded again unless the premultiply pre-pass changed it.
+// Pageable callers (a std::vector, malloc): the bands pass through the pipeline's pinned staging chain, moved by a
+// few host threads while the previous band is on the wire, so the device-side overlap is the same.
 template <class F>
-nvpyrStatus generateHostPipelined(DeviceContext& ctx, const ResolvedDesc& r, const void* hostLevel0, void* hostChain,
-                                  uint64_t chainBytes)
+nvpyrStatus generateHostPipelined(DeviceContext& ctx, HostPipeline& hp, const ResolvedDesc& r, const void* hostLevel0,
+                                  void* hostChain, uint64_t chainBytes)
 {
   const unsigned char* hin      = static_cast<const unsigned char*>(hostLevel0);
   unsigned char*       hout     = static_cast<unsigned char*>(hostChain);
@@ -996,25 +1279,88 @@ nvpyrStatus generateHostPipelined(DeviceContext& ctx, const ResolvedDesc& r, con
 
   if(bandRows == 0 || bandRows >= r.h)
   {
-    // One piece: upload, whole plan, download.
-    NVPYR_CUDA(cudaMemcpyAsync(dev, hin, level0Bytes, cudaMemcpyHostToDevice, ctx.hostRun));
+    // One piece: upload, whole plan, download (pageable memory: the driver stages these few megabytes).
+    NVPYR_CUDA(cudaMemcpyAsync(dev, hin, level0Bytes, cudaMemcpyHostToDevice, hp.run));
     nvpyrStatus st = dispatchResolved(r);
     if(st != NVPYR_SUCCESS)
       return st;
     const uint64_t from = level0Back ? 0 : level0Bytes;
     if(chainBytes > from)
-      NVPYR_CUDA(cudaMemcpyAsync(hout + from, dev + from, chainBytes - from, cudaMemcpyDeviceToHost, ctx.hostRun));
+      NVPYR_CUDA(cudaMemcpyAsync(hout + from, dev + from, chainBytes - from, cudaMemcpyDeviceToHost, hp.run));
     return NVPYR_SUCCESS;
   }
 
+  // Pageable source / destination: stage through pinned memory (same offsets as the chain).
+  const bool stageIn = isPageable(hin), stageOut = isPageable(hout);
+  if((stageIn || stageOut) && hp.stageBytes < chainBytes)
+  {
+    if(hp.stage)
+      cudaFreeHost(hp.stage);
+    hp.stage      = nullptr;
+    hp.stageBytes = 0;
+    NVPYR_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&hp.stage), chainBytes, cudaHostAllocDefault));
+    hp.stageBytes = chainBytes;
+  }
+  const unsigned char* upSrc   = stageIn ? hp.stage : hin;
+  unsigned char*       downDst = stageOut ? hp.stage : hout;
+
   const uint32_t bandLevels = 2;  // levels 1..2 travel back band by band, the small rest at the end
-  uint32_t       band       = 0;
+  struct OutPiece
+  {
+    size_t off, bytes;
+  };
+  std::vector<OutPiece> outPieces[kMaxHostBands + 1];  // what band b's download event covers
+  // Pageable destination: a helper thread follows the download events and moves each band out of the staging chain
+  // while the main thread is still feeding later bands in (both directions of the host copy run at once).
+  std::atomic<uint32_t>    recorded{0};      // download events recorded so far
+  std::atomic<bool>        stop{false};      // main thread gave up (error): the helper must not wait for more events
+  std::atomic<cudaError_t> drainError{cudaSuccess};
+  uint32_t                 totalEvents = 0;  // set before the last event is published
+  std::thread              drainer;
+  struct JoinDrainer
+  {
+    std::thread&       t;
+    std::atomic<bool>& stop;
+    ~JoinDrainer()
+    {
+      stop = true;
+      if(t.joinable())
+        t.join();
+    }
+  } joinDrainer{drainer, stop};
+  if(stageOut)
+    drainer = std::thread([&] {
+      cudaSetDevice(ctx.device);
+      for(uint32_t b = 0;; ++b)
+      {
+        while(recorded.load(std::memory_order_acquire) <= b)
+        {
+          if(stop.load())
+            return;
+          std::this_thread::yield();
+        }
+        const cudaError_t q = cudaEventSynchronize(hp.evDown[b]);
+        if(q != cudaSuccess)
+        {
+          drainError = q;
+          return;
+        }
+        for(const OutPiece& o : outPieces[b])
+          parallelCopy(hout + o.off, hp.stage + o.off, o.bytes);
+        if(totalEvents != 0 && b + 1 == totalEvents)
+          return;
+      }
+    });
+
+  uint32_t band = 0;
   for(uint32_t row0 = 0; row0 < r.h; row0 += bandRows, ++band)
   {
     const uint32_t rows = std::min(bandRows, r.h - row0);
-    NVPYR_CUDA(cudaMemcpyAsync(dev + row0 * rowBytes, hin + row0 * rowBytes, rows * rowBytes, cudaMemcpyHostToDevice, ctx.hostUp));
-    NVPYR_CUDA(cudaEventRecord(ctx.hostEvUp[band], ctx.hostUp));
-    NVPYR_CUDA(cudaStreamWaitEvent(ctx.hostRun, ctx.hostEvUp[band], 0));
+    if(stageIn)
+      parallelCopy(hp.stage + row0 * rowBytes, hin + row0 * rowBytes, rows * rowBytes);
+    NVPYR_CUDA(cudaMemcpyAsync(dev + row0 * rowBytes, upSrc + row0 * rowBytes, rows * rowBytes, cudaMemcpyHostToDevice, hp.up));
+    NVPYR_CUDA(cudaEventRecord(hp.evUp[band], hp.up));
+    NVPYR_CUDA(cudaStreamWaitEvent(hp.run, hp.evUp[band], 0));
     FastParams p{};
     for(uint32_t k = 0; k <= M; ++k)
     {
@@ -1025,31 +1371,43 @@ nvpyrStatus generateHostPipelined(DeviceContext& ctx, const ResolvedDesc& r, con
     const bool fusePremul = premul && tunedFastOk<F>(p.lv);
     if(premul && !fusePremul)
     {
-      nvpyrStatus st = launchPremultiply(ctx, dev + row0 * rowBytes, dev + row0 * rowBytes, uint64_t(rows) * r.w, ctx.hostRun);
+      nvpyrStatus st = launchPremultiply(ctx, dev + row0 * rowBytes, dev + row0 * rowBytes, uint64_t(rows) * r.w, hp.run);
       if(st != NVPYR_SUCCESS)
         return st;
     }
-    nvpyrStatus st = launchFast<F>(ctx, p, M, ctx.hostRun, fusePremul);
+    nvpyrStatus st = launchFast<F>(ctx, p, M, hp.run, fusePremul);
     if(st != NVPYR_SUCCESS)
       return st;
-    NVPYR_CUDA(cudaEventRecord(ctx.hostEvRun[band], ctx.hostRun));
-    NVPYR_CUDA(cudaStreamWaitEvent(ctx.hostDown, ctx.hostEvRun[band], 0));
+    NVPYR_CUDA(cudaEventRecord(hp.evRun[band], hp.run));
+    NVPYR_CUDA(cudaStreamWaitEvent(hp.down, hp.evRun[band], 0));
     for(uint32_t k = level0Back ? 0u : 1u; k <= bandLevels; ++k)
     {
       const size_t off = size_t(p.lv[k].ptr - dev), sz = size_t(p.lv[k].h) * p.lv[k].pitch;
-      NVPYR_CUDA(cudaMemcpyAsync(hout + off, dev + off, sz, cudaMemcpyDeviceToHost, ctx.hostDown));
+      NVPYR_CUDA(cudaMemcpyAsync(downDst + off, dev + off, sz, cudaMemcpyDeviceToHost, hp.down));
+      outPieces[band].push_back({off, sz});
     }
+    NVPYR_CUDA(cudaEventRecord(hp.evDown[band], hp.down));
+    recorded.store(band + 1, std::memory_order_release);
   }
   // the rest of the plan, then levels 3.. in one piece
   nvpyrStatus st = runPlan<F>(ctx, r, 1);
   if(st != NVPYR_SUCCESS)
     return st;
-  NVPYR_CUDA(cudaEventRecord(ctx.hostEvRun[kMaxHostBands], ctx.hostRun));
-  NVPYR_CUDA(cudaStreamWaitEvent(ctx.hostDown, ctx.hostEvRun[kMaxHostBands], 0));
+  NVPYR_CUDA(cudaEventRecord(hp.evRun[kMaxHostBands], hp.run));
+  NVPYR_CUDA(cudaStreamWaitEvent(hp.down, hp.evRun[kMaxHostBands], 0));
   if(r.levels > bandLevels + 1)
   {
     const size_t off = size_t(r.lv[bandLevels + 1].ptr - dev);
-    NVPYR_CUDA(cudaMemcpyAsync(hout + off, dev + off, chainBytes - off, cudaMemcpyDeviceToHost, ctx.hostDown));
+    NVPYR_CUDA(cudaMemcpyAsync(downDst + off, dev + off, chainBytes - off, cudaMemcpyDeviceToHost, hp.down));
+    outPieces[band].push_back({off, size_t(chainBytes - off)});
+  }
+  NVPYR_CUDA(cudaEventRecord(hp.evDown[band], hp.down));
+  totalEvents = band + 1;
+  recorded.store(band + 1, std::memory_order_release);
+  if(stageOut)
+  {
+    drainer.join();
+    NVPYR_CUDA(drainError.load());
   }
   return NVPYR_SUCCESS;
 }
@@ -1246,17 +1604,8 @@ nvpyrStatus nvpyrGenerateHost(const void* hostLevel0, void* hostChain, nvpyrExte
   st                 = getContext(&ctx);
   if(st != NVPYR_SUCCESS)
     return st;
-  std::lock_guard<std::mutex> lock(ctx->scratchMutex);
-  if(ctx->scratchBytes < bytes)
-  {
-    if(ctx->scratch)
-      cudaFree(ctx->scratch);
-    ctx->scratch      = nullptr;
-    ctx->scratchBytes = 0;
-    NVPYR_CUDA(cudaMalloc(&ctx->scratch, bytes));
-    ctx->scratchBytes = bytes;
-  }
-  st = hostPipelineInit(*ctx);
+  HostPipeline* hp = nullptr;
+  st               = acquireHostPipeline(*ctx, bytes, &hp);
   if(st != NVPYR_SUCCESS)
     return st;
   nvpyrDispatchDesc d;
@@ -1266,28 +1615,36 @@ nvpyrStatus nvpyrGenerateHost(const void* hostLevel0, void* hostChain, nvpyrExte
   d.flags      = flags;
   d.extent     = extent;
   d.levelCount = levelCount;
-  d.base       = ctx->scratch;
-  d.stream     = reinterpret_cast<nvpyrStream>(ctx->hostRun);
+  d.base       = hp->scratch;
+  d.stream     = reinterpret_cast<nvpyrStream>(hp->run);
   ResolvedDesc r;
   st = resolve(&d, r);
-  if(st != NVPYR_SUCCESS)
-    return st;
-  if(r.flags & NVPYR_FLAG_F16_SHARED)
-    st = generateHostPipelined<Srgba8F16Shared>(*ctx, r, hostLevel0, hostChain, bytes);
-  else if(r.flags & NVPYR_FLAG_SRGB_SHARED)
-    st = generateHostPipelined<Srgba8SrgbShared>(*ctx, r, hostLevel0, hostChain, bytes);
-  else
-    st = r.format == NVPYR_FORMAT_SRGBA8 ? generateHostPipelined<Srgba8>(*ctx, r, hostLevel0, hostChain, bytes)
-                                         : generateHostPipelined<Rgba32f>(*ctx, r, hostLevel0, hostChain, bytes);
-  // Never leave work in flight on the shared scratch chain, success or not.
-  const cudaError_t e0 = cudaStreamSynchronize(ctx->hostUp), e1 = cudaStreamSynchronize(ctx->hostRun),
-                    e2 = cudaStreamSynchronize(ctx->hostDown);
+  if(st == NVPYR_SUCCESS)
+  {
+    if(r.flags & NVPYR_FLAG_F16_SHARED)
+      st = generateHostPipelined<Srgba8F16Shared>(*ctx, *hp, r, hostLevel0, hostChain, bytes);
+    else if(r.flags & NVPYR_FLAG_SRGB_SHARED)
+      st = generateHostPipelined<Srgba8SrgbShared>(*ctx, *hp, r, hostLevel0, hostChain, bytes);
+    else
+      st = r.format == NVPYR_FORMAT_SRGBA8 ? generateHostPipelined<Srgba8>(*ctx, *hp, r, hostLevel0, hostChain, bytes)
+                                           : generateHostPipelined<Rgba32f>(*ctx, *hp, r, hostLevel0, hostChain, bytes);
+  }
+  // Never leave work in flight on the pipeline's scratch chain, success or not.
+  const cudaError_t e0 = cudaStreamSynchronize(hp->up), e1 = cudaStreamSynchronize(hp->run),
+                    e2 = cudaStreamSynchronize(hp->down);
+  releaseHostPipeline(*ctx, hp);
   if(st != NVPYR_SUCCESS)
     return st;
   NVPYR_CUDA(e0);
   NVPYR_CUDA(e1);
   NVPYR_CUDA(e2);
   return NVPYR_SUCCESS;
+}
+
+nvpyrStatus nvpyrInit(void)
+{
+  DeviceContext* ctx = nullptr;
+  return getContext(&ctx);
 }
 
 struct nvpyrExternalMemory_t
@@ -1376,16 +1733,12 @@ nvpyrStatus nvpyrShutdown(void)
     cudaFree(c->tables);
     cudaFree(c->tickets);
     cudaFree(c->batchBases);
-    if(c->scratch)
-      cudaFree(c->scratch);
-    if(c->hostUp != nullptr)
-    {
-      cudaStreamDestroy(c->hostUp), cudaStreamDestroy(c->hostRun), cudaStreamDestroy(c->hostDown);
-      for(cudaEvent_t e : c->hostEvUp)
-        cudaEventDestroy(e);
-      for(cudaEvent_t e : c->hostEvRun)
-        cudaEventDestroy(e);
-    }
+    for(HostPipeline* hp : c->hostIdle)
+      destroyHostPipeline(hp);
+    for(DeviceContext::BatchSlice& f : c->batchInFlight)
+      cudaEventDestroy(f.done);
+    for(cudaEvent_t e : c->batchEventPool)
+      cudaEventDestroy(e);
     delete c;
   }
   g_ctx.clear();

@@ -152,6 +152,8 @@ struct Srgba8FastSmem
 };
 #if NVPYR_FAST_TMA
 static_assert(sizeof(Srgba8FastSmem) + 1024 <= 227 * 1024, "TMA ring: build with NVPYR_FAST_ENC_LOW_OCTAVES=3");
+static_assert(offsetof(Srgba8FastSmem, ring) % 128 == 0 && alignof(Srgba8FastSmem) >= 128,
+              "cp.async.bulk.tensor destinations must be 128-byte aligned inside a 128-byte aligned block");
 #endif
 constexpr bool kFastTma = NVPYR_FAST_TMA != 0;
 // Dynamic shared memory of a launch: only the kernels that stage through the TMA ring pay for it (the others keep
@@ -448,7 +450,7 @@ __device__ __forceinline__ bool premultiplyRow(const unsigned char* dec, const u
 __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
     premultiplySrgba8Kernel(const uint4* in, uint4* out, uint64_t n4, const DeviceTables* tables)
 {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
+  extern __shared__ __align__(128) unsigned char smemRaw[];
   Srgba8FastSmem& sm = *reinterpret_cast<Srgba8FastSmem*>(smemRaw);
   srgba8FastInit(sm, tables);
   __syncthreads();
@@ -503,7 +505,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
   constexpr uint32_t kTileH = M >= 3 ? (1u << M) : 8u, kSlabs = kTileH / 8u;
   constexpr int      kSlabUnroll = kPremul ? 1 : kFastSlabUnroll;
   constexpr bool     kPinPrefetch = NVPYR_FAST_PIN_PREFETCH != 0 && kSlabUnroll > 1 && kSlabs > 1;
-  extern __shared__ __align__(16) unsigned char smemRaw[];
+  extern __shared__ __align__(128) unsigned char smemRaw[];  // the TMA ring inside needs 128-byte alignment
   __shared__ uint32_t tileArrivals[kFastWarps];  // slab tasks: slabs of local tile j that have arrived
   Srgba8FastSmem& sm = *reinterpret_cast<Srgba8FastSmem*>(smemRaw);
   if(kSlabTasks && threadIdx.x < kFastWarps)

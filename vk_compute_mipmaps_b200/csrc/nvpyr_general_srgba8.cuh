@@ -203,6 +203,15 @@ __device__ __forceinline__ V4 shflDown(V4 v, int d)
   return r;
 }
 
+// Reports where the dynamic shared-memory window of a kernel without static shared memory starts (run once per
+// device by the host; the strip kernels below are only used where the answer is kGenWindowBase).
+__global__ void genWindowProbeKernel(uint32_t* out)
+{
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  if(threadIdx.x == 0)
+    *out = uint32_t(__cvta_generic_to_shared(smemRaw));
+}
+
 // The strip kernel is written once and instantiated with a texel codec: how a raw texel is fetched, turned
 // into a float vector and stored again (the NVPRO_PYRAMID_LOAD / _STORE macros of this kernel).
 struct GenCodecSrgba8
@@ -235,7 +244,7 @@ struct GenCodecRgba32f
 template <class C, int kLevels, bool kX3, bool kY3>
 __global__ void __launch_bounds__(C::kWarps * 32, 1) generalStripKernel(const GenStripParams p)
 {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
+  extern __shared__ __align__(128) unsigned char smemRaw[];
   using Raw                 = typename C::Raw;
   constexpr uint32_t TB     = C::kTexelBytes;
   constexpr uint32_t kWarps = uint32_t(C::kWarps);
@@ -441,10 +450,40 @@ __global__ void __launch_bounds__(C::kWarps * 32, 1) generalStripKernel(const Ge
 // / (2n + 1); float32 carry to level +2), hence the same bits, with ~half the instructions per texel.
 constexpr int kGen4Warps = 16;  // 512 threads per CTA, one CTA per SM, up to 128 registers per thread
 
-template <int kLevels, bool kX3, bool kY3>
+// kStaged: the source rows of a strip are staged in shared memory by asynchronous copies instead of per-lane loads
+// into registers.  NPOT levels have row pitches that are not multiples of 16 bytes (4095 texels = 16380 bytes), so
+// rows start at 0 / 12 / 8 / 4 bytes modulo 16: a lane cannot fetch its four columns with one 16-byte load.  The
+// register path issues four 4-byte loads per row and lane, 16 bytes apart from lane to lane -- every instruction
+// touches 16 sectors and every sector is fetched four times from L1 (ncu, round 1: 302 MB of L1 sector traffic for
+// 67 MB of input) -- and keeps two output rows of raw texels in prefetch registers (121 registers per thread).
+// The TMA unit cannot help: a tensor-map box must start at a 16-byte aligned global address (measured with
+// tools/tma1d_probe.cu: a 1-D map accepts element 0, element 1 raises an illegal-instruction fault; 2-D maps need
+// 16-byte strides).  cp.async (LDGSTS) can: it copies 4-byte words, so lane l moves WORD l + 32 j of the strip's
+// 512-byte row segment -- consecutive lanes, consecutive words: 4-5 sectors per instruction, each fetched once --
+// into a 16-byte aligned stage of the warp's ring, and every lane then reads its four columns of both rows back with
+// two LDS.128.  No prefetch registers; kGenStages output rows are in flight ahead of the one being computed instead
+// of two.  Copies beyond the end of a row are suppressed (src-size 0: zero fill, no global access).
+constexpr uint32_t kGenStages     = 4;
+constexpr uint32_t kGenStageBytes = 1024;                     // two source rows x 128 texels
+constexpr uint32_t kGenRingAddr   = kGenDecodeAddr + 0x10000u;  // window address of the first warp's ring
+constexpr uint32_t kGenStagedSmemBytes = kGenRingAddr + kGen4Warps * kGenStages * kGenStageBytes - kGenWindowBase;
+static_assert(kGenRingAddr % 16u == 0 && kGenStagedSmemBytes + 1024u <= 227u * 1024u, "ring placement");
+
+__device__ __forceinline__ void cpAsync4(uint32_t dst, const void* src, uint32_t srcBytes)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(srcBytes) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cpAsyncWait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
+template <int kLevels, bool kX3, bool kY3, bool kStaged>
 __global__ void __launch_bounds__(kGen4Warps * 32, 1) generalStrip4Kernel(const GenStripParams p)
 {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
+  extern __shared__ __align__(128) unsigned char smemRaw[];
   if(uint32_t(__cvta_generic_to_shared(smemRaw)) != kGenWindowBase)
     __trap();  // the absolute table addresses assume this window layout: fail loudly, never silently
   genSrgba8Init<kGen4Warps * 32>(smemRaw, p.tables);
@@ -461,6 +500,10 @@ __global__ void __launch_bounds__(kGen4Warps * 32, 1) generalStrip4Kernel(const 
   const float fH2 = kLevels == 2 ? float(L2.h) : 0.f, fW2 = kLevels == 2 ? float(L2.w) : 0.f;
   const float rcpY2 = y3b ? genRcp(L2.h) : 0.f, rcpX2 = x3b ? genRcp(L2.w) : 0.f;
   const V4    zero = toV4(make_float4(0.f, 0.f, 0.f, 0.f));
+
+  // staging ring of this warp: stage = (rows consumed so far) mod kGenStages
+  const uint32_t ringBase = kGenRingAddr + warp * kGenStages * kGenStageBytes;
+  uint32_t       consumed = 0, issued = 0;
 
   const uint32_t numTasks = p.stripsX * p.segsY;
   for(uint32_t task = blockIdx.x + gridDim.x * warp; task < numTasks; task += gridDim.x * kGen4Warps)
@@ -532,8 +575,40 @@ __global__ void __launch_bounds__(kGen4Warps * 32, 1) generalStrip4Kernel(const 
       nextRows += rowStep;
     };
     Slot r0{{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}}, r1{{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
-    loadRow(true, r0);
-    loadRow(ya + 1u <= yb, r1);
+    // staged variant: this lane's four words of a row segment (word lane + 32 j) and whether they exist
+    const unsigned char* segSrc = L0.ptr + size_t(2u * 62u * sx + lane) * 4u;  // word `lane` of the strip's segment in row 0
+    uint32_t             segBytes[4];
+#pragma unroll
+    for(uint32_t j = 0; j < 4u; ++j)
+      segBytes[j] = 2u * 62u * sx + lane + 32u * j < L0.w ? 4u : 0u;
+    // The copies of output row yy: its two new source rows.  One commit group per output row, also when the row does
+    // not exist (an empty group keeps the wait count uniform).
+    auto stageIssue = [&](uint32_t yy) {
+      if(yy <= yb)
+      {
+        const uint32_t       dst = ringBase + (issued & (kGenStages - 1u)) * kGenStageBytes + lane * 4u;
+        const unsigned char* r0  = segSrc + size_t(kY3 ? 2u * yy + 1u : 2u * yy) * L0.pitch;
+#pragma unroll
+        for(uint32_t j = 0; j < 4u; ++j)
+        {
+          cpAsync4(dst + 128u * j, r0 + 128u * j, segBytes[j]);
+          cpAsync4(dst + 512u + 128u * j, r0 + L0.pitch + 128u * j, segBytes[j]);
+        }
+      }
+      cpAsyncCommit();
+      ++issued;
+    };
+    if(kStaged)
+    {
+#pragma unroll
+      for(uint32_t i = 0; i < kGenStages; ++i)
+        stageIssue(ya + i);
+    }
+    else
+    {
+      loadRow(true, r0);
+      loadRow(ya + 1u <= yb, r1);
+    }
     V4 q0a = zero, q1a = zero, q0b = zero, q1b = zero;  // last level +1 values of the lane's two columns
 
     unsigned char* d1 = L1.ptr + size_t(ya) * L1.pitch + size_t(xa) * 4u;
@@ -542,8 +617,22 @@ __global__ void __launch_bounds__(kGen4Warps * 32, 1) generalStrip4Kernel(const 
 
     auto row = [&](uint32_t y, Slot& slot, auto parity) {
       constexpr bool kOdd = decltype(parity)::value;
-      const Slot     m    = slot;
-      loadRow(y + 2u <= yb, slot);
+      Slot           m    = slot;
+      if(kStaged)
+      {
+        // wait for this row's stage (the oldest of kGenStages groups), read the lane's four columns of both source
+        // rows, hand the stage back
+        cpAsyncWait<kGenStages - 1>();
+        __syncwarp();  // every lane's words of the stage have landed
+        const uint32_t mine = ringBase + (consumed & (kGenStages - 1u)) * kGenStageBytes + lane * 16u;
+        ++consumed;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m.a.w0), "=r"(m.a.w1), "=r"(m.a.w2), "=r"(m.a.w3) : "r"(mine));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+512];" : "=r"(m.b.w0), "=r"(m.b.w1), "=r"(m.b.w2), "=r"(m.b.w3) : "r"(mine));
+        __syncwarp();  // all lanes have read the stage before anyone overwrites it
+        stageIssue(y + kGenStages);
+      }
+      else
+        loadRow(y + 2u <= yb, slot);
       // ---- vertical reduction of the lane's four source columns ----
       const V4 a0 = genDecodeTexel(laneAddr, m.a.w0), a1 = genDecodeTexel(laneAddr, m.a.w1);
       const V4 a2 = genDecodeTexel(laneAddr, m.a.w2), a3 = genDecodeTexel(laneAddr, m.a.w3);

@@ -217,7 +217,7 @@ __device__ __forceinline__ void fastTileLoop(const FastParams& p, const typename
 template <class F, int M, bool kVec>
 __global__ void __launch_bounds__(256) fastKernel(const FastParams p)
 {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
+  extern __shared__ __align__(128) unsigned char smemRaw[];
   FastSmem<F>& sm = *reinterpret_cast<FastSmem<F>*>(smemRaw);
   F::sharedInit(sm.tables, p.tables);
   __syncthreads();
@@ -249,7 +249,7 @@ __device__ __forceinline__ void fastLoop1(const FastParams& p, const typename F:
 template <class F>
 __global__ void __launch_bounds__(256) fastKernel1(const FastParams p)
 {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
+  extern __shared__ __align__(128) unsigned char smemRaw[];
   FastSmem<F>& sm = *reinterpret_cast<FastSmem<F>*>(smemRaw);
   F::sharedInit(sm.tables, p.tables);
   __syncthreads();
@@ -412,7 +412,7 @@ __device__ __forceinline__ void generalTileLoop(const GeneralParams& p, const ty
 template <class F>
 __global__ void __launch_bounds__(256) generalKernel(const GeneralParams p)
 {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
+  extern __shared__ __align__(128) unsigned char smemRaw[];
   GeneralSmem<F>& sm = *reinterpret_cast<GeneralSmem<F>*>(smemRaw);
   F::sharedInit(sm.tables, p.tables);
   __syncthreads();
@@ -516,7 +516,7 @@ __device__ __forceinline__ void tailRunStep(const TailStep& st, TailSmem<F>& sm,
 template <class F>
 __global__ void __launch_bounds__(kTailThreads) tailKernel(const __grid_constant__ TailParams tp)
 {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
+  extern __shared__ __align__(128) unsigned char smemRaw[];
   TailSmem<F>& sm = *reinterpret_cast<TailSmem<F>*>(smemRaw);
   F::sharedInit(sm.tables, tp.tables);
   __syncthreads();
@@ -557,7 +557,7 @@ template <class F>
 __global__ void __launch_bounds__(kTailThreads) tailBatchKernel(const __grid_constant__ TailParams tp,
                                                         const unsigned char* const* bases, uint32_t count)
 {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
+  extern __shared__ __align__(128) unsigned char smemRaw[];
   TailSmem<F>& sm = *reinterpret_cast<TailSmem<F>*>(smemRaw);
   F::sharedInit(sm.tables, tp.tables);
   __syncthreads();
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(kTailThreads) tailBatchKernel(const __grid_con
 __global__ void __launch_bounds__(256) premultiplyKernel(const uint32_t* in, uint32_t* out, uint64_t texels,
                                                          const DeviceTables* tables)
 {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
+  extern __shared__ __align__(128) unsigned char smemRaw[];
   Srgba8::Shared& sm = *reinterpret_cast<Srgba8::Shared*>(smemRaw);
   Srgba8::sharedInit(sm, tables);
   __syncthreads();

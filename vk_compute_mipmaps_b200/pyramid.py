@@ -21,7 +21,7 @@ from ._lib import (FLAG_F16_SHARED, FLAG_SRGB_SHARED, FLAG_FORCE_GENERAL, FLAG_N
 
 __all__ = [
     "PyramidPipelines", "cmd_pyramid_dispatch", "dispatch_batch", "level_count", "level_extent", "level_offset_texels",
-    "chain_bytes", "chain_texels", "get_plan", "generate_host", "premultiply_alpha", "level_views", "launch_count",
+    "chain_bytes", "chain_texels", "get_plan", "generate_host", "premultiply_alpha", "level_views", "launch_count", "init",
     "write_tga", "level_filename", "write_mipmaps_tga", "read_image",
     "FORMAT_SRGBA8", "FORMAT_RGBA32F", "FLAG_NONE", "FLAG_FORCE_GENERAL", "FLAG_PREMULTIPLY_ALPHA", "FLAG_F16_SHARED", "FLAG_SRGB_SHARED", "NvpyrError",
 ]
@@ -174,6 +174,10 @@ def generate_host(level0, width, height, mip_levels=0, fmt=FORMAT_SRGBA8, flags=
     n = chain_bytes(width, height, mip_levels, fmt) // np.dtype(dt).itemsize
     if out is None:
         out = np.empty(n, dtype=dt)
+    elif not (isinstance(out, np.ndarray) and out.dtype == dt and out.flags.c_contiguous and out.flags.writeable
+              and out.size >= n):
+        raise ValueError(f"out must be a writable C-contiguous {np.dtype(dt).name} array of at least {n} elements "
+                         "(the packed chain, level 0 included)")
     check(lib.nvpyrGenerateHost(level0.ctypes.data, out.ctypes.data, Extent2D(width, height), mip_levels, fmt, flags),
           "nvpyrGenerateHost")
     return out
@@ -223,6 +227,12 @@ def level_views(chain, width, height, mip_levels=0):
         views.append(chain[4 * off:4 * (off + w * h)].reshape(h, w, 4))
         off += w * h
     return views
+
+
+def init():
+    """nvpyrInit: create the per-device state for the current device now (required before a CUDA-graph capture
+    if no dispatch has run on the device yet)."""
+    check(lib.nvpyrInit(), "nvpyrInit")
 
 
 def launch_count():
