@@ -121,7 +121,8 @@ bool buildHostTables(DeviceTables& t)
 }
 
 // ------------------------------------------------------------ device context
-// Ticket counters of tailKernel ("which CTA finished the grid step last").  A counter may only be shared by
+// Counters of tailKernel ("which CTA finished the grid step last") and of the tuned fast kernel (dynamic tile
+// hand-out); both return to zero when their launch ends.  A counter may only be shared by
 // launches that are ordered one after the other, so: every STREAM owns one slot (launches of a stream are ordered;
 // each kernel executes griddepcontrol.wait before it touches anything, so with programmatic dependent launch the
 // counter is still used by one launch at a time), and every launch recorded into a CUDA GRAPH gets a dedicated slot
@@ -140,7 +141,7 @@ struct DeviceContext
   int           device   = -1;
   int           smCount  = 0;
   DeviceTables* tables   = nullptr;
-  uint32_t*     tickets  = nullptr;  // kTicketPool zero-initialised counters for tailKernel
+  uint32_t*     tickets  = nullptr;  // kTicketPool zero-initialised slots of two counters: [0] tailKernel's ticket, [1] the fast kernel's tile hand-out
   std::mutex                       ticketMutex;
   std::map<cudaStream_t, uint32_t> ticketOfStream;
   uint32_t                         ticketsUsed = 0;
@@ -193,9 +194,9 @@ nvpyrStatus getContext(DeviceContext** out)
   if(e == cudaSuccess)
     e = cudaMemcpy(d, &host, sizeof(DeviceTables), cudaMemcpyHostToDevice);
   if(e == cudaSuccess)
-    e = cudaMalloc(&tickets, kTicketPool * sizeof(uint32_t));
+    e = cudaMalloc(&tickets, 2 * kTicketPool * sizeof(uint32_t));
   if(e == cudaSuccess)
-    e = cudaMemset(tickets, 0, kTicketPool * sizeof(uint32_t));
+    e = cudaMemset(tickets, 0, 2 * kTicketPool * sizeof(uint32_t));
   if(e == cudaSuccess)
     e = cudaMalloc(&ring, size_t(kBatchRing) * sizeof(void*));
   // Where does the dynamic shared-memory window of a kernel without static shared memory start on this
@@ -253,7 +254,7 @@ nvpyrStatus acquireTicket(DeviceContext& ctx, cudaStream_t stream, uint32_t** ti
     auto it = ctx.ticketOfStream.find(stream);
     if(it != ctx.ticketOfStream.end())
     {
-      *ticket = ctx.tickets + it->second;
+      *ticket = ctx.tickets + 2u * it->second;
       return NVPYR_SUCCESS;
     }
   }
@@ -262,7 +263,7 @@ nvpyrStatus acquireTicket(DeviceContext& ctx, cudaStream_t stream, uint32_t** ti
   const uint32_t slot = ctx.ticketsUsed++;
   if(!capturing)
     ctx.ticketOfStream[stream] = slot;
-  *ticket = ctx.tickets + slot;
+  *ticket = ctx.tickets + 2u * slot;
   return NVPYR_SUCCESS;
 }
 
@@ -386,7 +387,16 @@ nvpyrStatus launchFastSrgba8K(const DeviceContext& ctx, const FastParams& p, con
       return NVPYR_ERROR_CUDA;
   }
 #endif
-  NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, kBatch, kPremul, kSlabTasks>, grid, kFastWarps * 32, smem, stream, p, b, tmap));
+  FastParams pp = p;
+  if(!kSlabTasks)
+  {
+    uint32_t*   slot = nullptr;
+    nvpyrStatus tst  = acquireTicket(const_cast<DeviceContext&>(ctx), stream, &slot);
+    if(tst != NVPYR_SUCCESS)
+      return tst;
+    pp.tileCounter = slot + 1;
+  }
+  NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, kBatch, kPremul, kSlabTasks>, grid, kFastWarps * 32, smem, stream, pp, b, tmap));
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
@@ -749,7 +759,7 @@ const uint64_t kTailMaxTexels = [] {
   return e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : 512ull * 512ull;
 }();
 constexpr uint64_t kSoloMaxTexelsFast    = 64ull * 64ull;  // one 64x64 tile
-constexpr uint64_t kSoloMaxTexelsGeneral = 32ull * 32ull;  // one 8x8 tile of level +2
+// general steps run solo when the input is at most kSoloMaxEdgeGeneral wide and high (one tile, nvpyr_kernels.cuh)
 
 template <class F>
 struct TailFunctors
@@ -788,7 +798,7 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
       ts.tilesY = (ts.lv[0].h + 63u) / 64u;
     }
     else
-      generalTiles(ts.lv, s.levelCount, kGenTile2Small, &ts.tilesX, &ts.tilesY);
+      generalTiles(ts.lv, s.levelCount, i == 0 ? kGenTile2Small : SoloTile2<typename TF::Value>::value, &ts.tilesX, &ts.tilesY);
   }
   uint64_t work = uint64_t(tp.steps[0].tilesX) * tp.steps[0].tilesY;
   if(tp.steps[0].pipeline == 1 && tp.steps[0].levels == 1)  // fastLoop1 is thread-strided, not tiled
@@ -823,7 +833,9 @@ nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0
       // grid step i, then as many solo steps as follow (level sizes only shrink)
       int count = 1;
       while(i + count < n && count < int(kMaxTailSteps)
-            && texels(i + count) <= (steps[i + count].pipeline == 1 ? kSoloMaxTexelsFast : kSoloMaxTexelsGeneral))
+            && (steps[i + count].pipeline == 1
+                    ? texels(i + count) <= kSoloMaxTexelsFast
+                    : std::max(steps[i + count].srcWidth, steps[i + count].srcHeight) <= kSoloMaxEdgeGeneral))
         ++count;
       st = launchTail<F>(ctx, r, steps + i, count);
       i += count;
@@ -1058,7 +1070,7 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
       ts.tilesY = (ts.lv[0].h + 63u) / 64u;
     }
     else
-      generalTiles(ts.lv, s.levelCount, kGenTile2Small, &ts.tilesX, &ts.tilesY);
+      generalTiles(ts.lv, s.levelCount, SoloTile2<TF::Value>::value, &ts.tilesX, &ts.tilesY);  // every batch-tail step is solo
   }
   const size_t smem = sizeof(TailSmem<TF>);
   int          grid = 1;

@@ -71,7 +71,7 @@ namespace nvpyr {
 #define NVPYR_ENC_WAYS 8
 #endif
 #ifndef NVPYR_FAST_ENC_CLAMP
-#define NVPYR_FAST_ENC_CLAMP 0
+#define NVPYR_FAST_ENC_CLAMP 1  // round 2: with the stashes inside the decode table (below) every encode clamps
 #endif
 #ifndef NVPYR_FAST_TMA
 #define NVPYR_FAST_TMA 2  // see below
@@ -116,6 +116,34 @@ namespace nvpyr {
 #ifndef NVPYR_FAST_UNCOND_LOADS
 #define NVPYR_FAST_UNCOND_LOADS 0
 #endif
+// NVPYR_FAST_L3_IN_DECODE = 1: the per-warp stashes of level +3 sums (32 KB) live in the UNUSED HALVES of the decode
+// table's rows (row = 256 bytes per code, of which the 32 lane copies take 128): stash row (warp, slab) -- eight
+// texels of 16 bytes -- is the spare half of decode row 8 * warp + slab.  Frees 32 KB of shared memory, which is what
+// lets a 16-way encode table (131 KB) fit under the ~200 KB above which per-lane global loads lose their L1.  The
+// zero words of the clamp-free encode would collide with the stashes, so this layout clamps every encode.
+// Measured at 16384^2 (round 2, one box, us whole chain / 6-level kernel; Julia | uniform random | gradient):
+//   round-1 layout (TMA ring, 8-way, 3 low octaves, stashes apart, 224.6 KB)  252.1 / 243.4 | 291.2 / 283.2 | 260.1 / 250.9
+//   this layout    (TMA ring, 8-way, clamp everywhere, 192 KB): the default   253.1 / 242.8 | 283.3 / 274.8 | 255.1 / 245.2
+//   register path, 16-way, clamp, this layout (193 KB)                        265.3 / 256.5 | 271.5 / 263.2 | 265.7 / 257.1
+//   register path, 8-way, clamp, this layout (132 KB)                         264.5 / 255.4 | 282.9 / 273.6 | 267.0 / 256.7
+//   register path, 8-way, 3 low octaves, stashes apart (164 KB)               259.9 / 249.9 | 282.5 / 273.9 | 263.6 / 253.1
+// The 32 KB given back to L1 are worth 3 % on high-entropy input and cost nothing on the reference's Julia texture.
+// A 16-way table takes another 10 us off the random input but only fits without the TMA ring (64 + 131 + 64 KB >
+// 227 KB), and the register path costs the Julia input 13 us.
+#ifndef NVPYR_FAST_L3_IN_DECODE
+#define NVPYR_FAST_L3_IN_DECODE 1
+#endif
+// NVPYR_FAST_DYNAMIC_TILES = 1: after its first (statically dealt) tile a warp takes further tiles from one global
+// counter, so that CTAs that start late (their SM still runs the previous chain's tail kernel) take fewer tiles.
+// Measured (round 2, same box, 16384^2 whole chain / kernel alone): static 252.7 / 244.6 us on Julia, 284.3 / 275.4 on
+// random bytes; dynamic 261.4 / 254.1 and 292.8 / 283.4 -- the hand-out costs 9 us even with the atomic issued a whole
+// tile ahead of its use (8192^2 80.5 -> 86.9 us, 1080p 14.7 -> 16.5 us).  Kept for A/B runs; static dealing is the default.
+#ifndef NVPYR_FAST_DYNAMIC_TILES
+#define NVPYR_FAST_DYNAMIC_TILES 0
+#endif
+constexpr bool     kDynTiles        = NVPYR_FAST_DYNAMIC_TILES != 0;
+constexpr bool     kL3InDecode      = NVPYR_FAST_L3_IN_DECODE != 0;
+constexpr uint32_t kL3RowFloats     = kL3InDecode ? 64u : 32u;  // floats from one stash row (8 texels) to the next
 constexpr bool     kFastUncondLoads = NVPYR_FAST_UNCOND_LOADS != 0;
 constexpr int      kFastSlabUnroll = NVPYR_FAST_SLAB_UNROLL;
 constexpr uint32_t kEncWays       = NVPYR_ENC_WAYS;
@@ -143,7 +171,7 @@ struct Srgba8FastSmem
   float    decode[256 * 64];        // [code][64]: floats 0..31 = per-lane copies, 32..63 spare (zero words live there)
   float    pad[32];                 // keeps the zero words in the spare halves (see encScaled)
   alignas(16) uint32_t encode[(kEncEntriesExt + 3) * kEncWays];  // bucket table, extended downwards, kEncWays copies per entry
-  alignas(16) float l3[kFastWarps][8][8][4];  // per warp: level +3 sums of its 64x64 tile, [slab][x][channel]
+  alignas(16) float l3[kL3InDecode ? 1 : kFastWarps][8][8][4];  // per warp: level +3 sums of its 64x64 tile, [slab][x][channel]
   unsigned char unused[NVPYR_FAST_PAD_BYTES];  // A/B experiments on the shared-memory carve-out
 #if NVPYR_FAST_TMA
   alignas(128) unsigned char ring[kFastWarps][2048];  // per warp: the level-0 slab in flight (8 rows x 256 bytes)
@@ -156,6 +184,13 @@ static_assert(offsetof(Srgba8FastSmem, ring) % 128 == 0 && alignof(Srgba8FastSme
               "cp.async.bulk.tensor destinations must be 128-byte aligned inside a 128-byte aligned block");
 #endif
 constexpr bool kFastTma = NVPYR_FAST_TMA != 0;
+static_assert(!kL3InDecode || (NVPYR_FAST_ENC_CLAMP != 0 && kFastWarps * 8 <= 256),
+              "stashes in the decode table's spare halves: every encode clamps (no zero words), at most 256 stash rows");
+// First float of the stash of warp (or local tile) j.
+__device__ __forceinline__ float* stashOf(Srgba8FastSmem& sm, uint32_t j)
+{
+  return kL3InDecode ? &sm.decode[j * 8u * 64u + 32u] : &sm.l3[kL3InDecode ? 0u : j][0][0][0];
+}
 // Dynamic shared memory of a launch: only the kernels that stage through the TMA ring pay for it (the others keep
 // the SM's L1 for their loads in flight).
 constexpr size_t fastSmemBytes(bool tma)
@@ -529,7 +564,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
     return reinterpret_cast<unsigned char*>(__ldg(reinterpret_cast<const unsigned long long*>(batch.bases) + t / batch.tilesPerImage)) + reinterpret_cast<size_t>(p.lv[k].ptr);
   };
   const size_t   pitch0 = p.lv[0].pitch, pitch1 = p.lv[1].pitch, pitch2 = p.lv[2].pitch;
-  float*         myL3 = &sm.l3[warp][0][0][0];
+  float*         myL3 = stashOf(sm, warp);
 
   // level +3 transpose-reduce roles
   const bool     xOdd = lane & 1u, yOdd = lane & 16u;
@@ -617,10 +652,33 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
   {
     // this unit of work, and the one after it (for the prefetch)
     const uint32_t nextTask  = task + kFastWarps;
-    const uint32_t nextTileI = kSlabTasks ? blockIdx.x + gridDim.x * (nextTask / kSlabs) : tile + tileStep;
     const uint32_t nextSlab0 = kSlabTasks ? nextTask % kSlabs : 0u;
+    uint32_t       nextTileI = blockIdx.x + gridDim.x * (nextTask / kSlabs), fetched = 0;
+    if(!kSlabTasks && !kDynTiles)
+      nextTileI = tile + tileStep;
+    if(!kSlabTasks && kDynTiles)
+    {
+      // Tile mode: the first tile of every warp is dealt statically (CTA-major), all further ones are handed out
+      // through one global counter, so that a CTA that starts late -- its SM was still busy with the previous
+      // chain's tail kernel -- simply takes fewer tiles instead of finishing late.  One atomic per 64 x 2^M tile,
+      // fetched a whole tile ahead of its use.  Every processed tile fetches exactly once, so the fetch that
+      // returns numTiles - 1 is the last of the launch: it puts the counter back to zero for the next one.
+      // (lane 0 issues the atomic here; the warp only looks at the answer when it reaches the tile's last slab)
+      if(lane == 0u)
+      {
+        fetched = atomicAdd(p.tileCounter, 1u);
+        if(fetched == numTiles - 1u)
+          *p.tileCounter = 0u;
+      }
+    }
+    // The next unit of work becomes known (and its cursor is computed) at the last slab of this one.
+    auto resolveNext = [&]() {
+      if(!kSlabTasks && kDynTiles)
+        nextTileI = __shfl_sync(0xffffffffu, fetched, 0) + tileStep;
+      return tileCursor(nextTileI, nextSlab0);
+    };
     if(kSlabTasks)
-      myL3 = &sm.l3[task / kSlabs][0][0][0];  // the tile's stash (local tile index < kFastWarps, see the launch code)
+      myL3 = stashOf(sm, task / kSlabs);  // the tile's stash (local tile index < kFastWarps, see the launch code)
     const uint32_t tileInImage = kBatch ? tile % batch.tilesPerImage : tile;
     const uint32_t tileX = tileInImage % p.tilesX, tileY = tileInImage / p.tilesX;
     const uint32_t x0 = tileX * 64u + tx * 4u;
@@ -629,7 +687,6 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
     unsigned char* d1 = levelPtr(1, tile) + size_t(y0 >> 1) * pitch1 + size_t(x0 >> 1) * 4u;
     unsigned char* d2 = levelPtr(2, tile) + size_t(y0 >> 2) * pitch2 + size_t(x0 >> 2) * 4u;
     unsigned char* d3 = M >= 3 ? levelPtr(3, tile) + size_t(y0 >> 3) * p.lv[3].pitch + size_t(x0 >> 3) * 4u : nullptr;
-    const Cursor   nextTile = tileCursor(nextTileI, nextSlab0);
     const uint32_t slabEnd  = kSlabTasks ? slab0 + 1u : kSlabs;
 #pragma unroll kSlabUnroll
     for(uint32_t slab = slab0; slab < slabEnd; ++slab, y0 += 8u, d1 += 4u * pitch1, d2 += 2u * pitch2)
@@ -654,7 +711,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
         if(slab + 1u < kSlabs)
           tmaIssue(tile, slab + 1u);
         else
+        {
+          resolveNext();
           tmaIssue(nextTileI, 0u);
+        }
       }
       unsigned char* const curSrc = const_cast<unsigned char*>(nxt.src);
       // the next slab (of this tile, or the first one of this warp's next tile)
@@ -668,7 +728,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
           nxt.active = x0 < W && y0 + 8u < H;
       }
       else
-        nxt = nextTile;
+        nxt = resolveNext();
       if(!kTma && kFastPrefetch)
       {
         if(kPinPrefetch)
@@ -755,7 +815,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
           if(ch == 0u)
             *reinterpret_cast<uint32_t*>(d3) = word;
           if(M >= 4)
-            myL3[(slab * 8u + (tx >> 1)) * 4u + ch] = u;
+            myL3[slab * kL3RowFloats + (tx >> 1) * 4u + ch] = u;
         }
         d3 += p.lv[3].pitch;
       }
@@ -786,8 +846,9 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
       if(valid)
       {
         const float4* l3 = reinterpret_cast<const float4*>(myL3);
-        const V4      ul = toV4(l3[(2 * j) * 8 + 2 * i]), ur = toV4(l3[(2 * j) * 8 + 2 * i + 1]);
-        const V4      ll = toV4(l3[(2 * j + 1) * 8 + 2 * i]), lr = toV4(l3[(2 * j + 1) * 8 + 2 * i + 1]);
+        constexpr uint32_t kRow4 = kL3RowFloats / 4u;  // float4s per stash row
+        const V4      ul = toV4(l3[(2 * j) * kRow4 + 2 * i]), ur = toV4(l3[(2 * j) * kRow4 + 2 * i + 1]);
+        const V4      ll = toV4(l3[(2 * j + 1) * kRow4 + 2 * i]), lr = toV4(l3[(2 * j + 1) * kRow4 + 2 * i + 1]);
         s4               = sum4Paired(fastPairingIsHorizontal(4, M), ul, ur, ll, lr);
         *reinterpret_cast<uint32_t*>(levelPtr(4, tile) + size_t(oy >> 4) * p.lv[4].pitch + size_t(ox >> 4) * 4u) =
             encWordScaled<4>(enc, s4);
@@ -819,7 +880,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
       slab0 = nextSlab0;
     }
     else
-      tile += tileStep;
+      tile = nextTileI;
   }
 }
 

@@ -448,7 +448,10 @@ __global__ void __launch_bounds__(C::kWarps * 32, 1) generalStripKernel(const Ge
 // strip recomputes, strips advance by 62) and 31 columns of level +2.  Same float32 expression tree per
 // output texel (vertical reduction of each source column, then horizontal; weights (n - i, n, 1 - w0 - w1)
 // / (2n + 1); float32 carry to level +2), hence the same bits, with ~half the instructions per texel.
-constexpr int kGen4Warps = 16;  // 512 threads per CTA, one CTA per SM, up to 128 registers per thread
+#ifndef NVPYR_GEN4_WARPS
+#define NVPYR_GEN4_WARPS 16
+#endif
+constexpr int kGen4Warps = NVPYR_GEN4_WARPS;  // 16: 512 threads per CTA, one CTA per SM, up to 128 registers per thread
 
 // kStaged: the source rows of a strip are staged in shared memory by asynchronous copies instead of per-lane loads
 // into registers.  NPOT levels have row pitches that are not multiples of 16 bytes (4095 texels = 16380 bytes), so

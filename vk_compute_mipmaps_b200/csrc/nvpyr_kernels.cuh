@@ -77,6 +77,7 @@ struct FastParams
   LevelView           lv[7];  // lv[0] = input level, lv[k] = input + k
   uint32_t            tilesX, tilesY;
   const DeviceTables* tables;
+  uint32_t*           tileCounter;  // tuned sRGBA8 kernel: dynamic tile hand-out (zero on entry, zero again on exit)
 };
 
 template <class F>
@@ -270,7 +271,18 @@ struct GeneralParams
 };
 
 constexpr int kGenTile2 = 16;  // tile edge in level +2 of the stand-alone general kernel
-constexpr int kGenTile2Small = 8;  // ... of the tail kernel (more, smaller tiles: the levels are tiny)
+constexpr int kGenTile2Small = 8;  // ... of the tail kernel's grid step (more, smaller tiles: the levels are tiny)
+// ... and of its SOLO steps, which one CTA runs alone.  Measured (round 2): making the solo tile as large as shared
+// memory allows (32 x 32 of level +2, so that a 127^2 or 63^2 input is ONE tile and the chain needs one tail launch
+// instead of two) is SLOWER -- 4095^2 47.3 -> 52.4 us, 2047^2 24.7 -> 31.5 us: one CTA walks the 3969 (961) texels
+// of level +1 in 8 (2) rounds of nine L2-latency loads each, whereas a second launch spreads them over 16 (4) CTAs in
+// one round and hides its launch latency behind the first through programmatic dependent launch.
+template <class V>
+struct SoloTile2
+{
+  static constexpr int value = kGenTile2Small;
+};
+constexpr uint32_t kSoloMaxEdgeGeneral = 32;  // a general step whose input is at most this wide and high runs solo
 
 // Shared scratch of a T2 x T2 tile of level +2: (2 T2 + 1)^2 texels of level +1 (float32 carry).
 template <int T2, class V = float4>
@@ -462,13 +474,15 @@ struct TailSmem
   typename F::Shared tables;
   union
   {
-    typename F::Value                          l3[2][8][8];
-    GenTile<kGenTile2Small, typename F::Value> tile;
+    typename F::Value                                        l3[2][8][8];
+    GenTile<kGenTile2Small, typename F::Value>               tile;
+    GenTile<SoloTile2<typename F::Value>::value, typename F::Value> soloTile;
   };
   uint32_t isLast;
 };
 
-template <class F>
+// kSolo: the step is run by one CTA alone (its general tiles were counted for soloTile2).
+template <class F, bool kSolo>
 __device__ __forceinline__ void tailRunStep(const TailStep& st, TailSmem<F>& sm, const DeviceTables* tables,
                                             uint32_t first, uint32_t stride)
 {
@@ -509,7 +523,10 @@ __device__ __forceinline__ void tailRunStep(const TailStep& st, TailSmem<F>& sm,
     p.tilesX = st.tilesX;
     p.tilesY = st.tilesY;
     p.tables = tables;
-    generalTileLoop<F, kGenTile2Small>(p, sm.tables, sm.tile, first, stride);
+    if(kSolo)
+      generalTileLoop<F, SoloTile2<typename F::Value>::value>(p, sm.tables, sm.soloTile, first, stride);
+    else
+      generalTileLoop<F, kGenTile2Small>(p, sm.tables, sm.tile, first, stride);
   }
 }
 
@@ -523,7 +540,7 @@ __global__ void __launch_bounds__(kTailThreads) tailKernel(const __grid_constant
   gridDependencyWait();    // the previous kernel's levels are complete and visible
   gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
 
-  tailRunStep<F>(tp.steps[0], sm, tp.tables, blockIdx.x, gridDim.x);
+  tailRunStep<F, false>(tp.steps[0], sm, tp.tables, blockIdx.x, gridDim.x);
   if(tp.numSteps == 1u)
     return;
 
@@ -544,7 +561,7 @@ __global__ void __launch_bounds__(kTailThreads) tailKernel(const __grid_constant
 
   for(uint32_t s = 1; s < tp.numSteps; ++s)
   {
-    tailRunStep<F>(tp.steps[s], sm, tp.tables, 0u, 1u);
+    tailRunStep<F, true>(tp.steps[s], sm, tp.tables, 0u, 1u);
     __threadfence_block();
     __syncthreads();  // the reference's inter-dispatch pipeline barrier (one CTA: a CTA barrier suffices)
   }
@@ -572,7 +589,7 @@ __global__ void __launch_bounds__(kTailThreads) tailBatchKernel(const __grid_con
 #pragma unroll
       for(int k = 0; k < 7; ++k)
         st.lv[k].ptr = base + reinterpret_cast<size_t>(st.lv[k].ptr);
-      tailRunStep<F>(st, sm, tp.tables, 0u, 1u);
+      tailRunStep<F, true>(st, sm, tp.tables, 0u, 1u);
       __threadfence_block();
       __syncthreads();  // the reference's inter-dispatch pipeline barrier
     }
