@@ -224,6 +224,11 @@ NVPYR_API const char* nvpyrGetErrorString(nvpyrStatus status);
 NVPYR_API int nvpyrGetLastCudaError(void);
 /* Number of kernels the library has launched in this process (for launch accounting). */
 NVPYR_API uint64_t nvpyrGetLaunchCount(void);
+/* Host-only self-test of the tuned fast kernel's sRGB encode table: every float32 pattern the kernel can present
+ * (linearFromSrgb(1)/4 .. 1.0 and zero, ~110 M values) goes through the kernel's own look-up arithmetic and is compared
+ * with srgbFromLinear restated as "number of pinned thresholds <= x" (reference shaders/srgb.h:30-41).  Returns the
+ * number of mismatches: 0.  Needs no GPU; takes about a second. */
+NVPYR_API uint64_t nvpyrSelfTestEncodeTable(void);
 /* Creates the library's per-device state (tables, counters) for the CURRENT device now instead of inside the first
  * dispatch.  Call it before capturing nvpyrDispatch* into a CUDA graph: the first call on a device allocates and
  * copies, which a stream capture forbids.  NVPYR_ERROR_UNSUPPORTED on anything but an sm_100 device. */

@@ -87,6 +87,7 @@ def _load():
         "nvpyrGetErrorString": (C.c_char_p, [st]),
         "nvpyrGetLastCudaError": (C.c_int, []),
         "nvpyrGetLaunchCount": (u64, []),
+        "nvpyrSelfTestEncodeTable": (u64, []),
         "nvpyrInit": (st, []),
         "nvpyrShutdown": (st, []),
         "nvpyrGetVersion": (u32, []),

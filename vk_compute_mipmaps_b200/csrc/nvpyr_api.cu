@@ -111,13 +111,100 @@ bool buildEncodeTable(uint32_t* out, uint32_t shift, uint32_t entriesPadded)
   return true;
 }
 
+// Row of the tuned fast kernel's encode table (nvpyr_functors.cuh): key of RN(x + kRowEncC).  IEEE float32 addition,
+// the same value the kernel's FFMA produces (x = S' * 2^k is exact).
+uint32_t rowOfBits(uint32_t xbits)
+{
+  volatile float z = bitsToFloat(xbits) + bitsToFloat(kRowEncCBits);
+  const float    f = z;
+  uint32_t       b;
+  memcpy(&b, &f, 4);
+  return (b >> 16) - kRowEncFirstKey;
+}
+// The smallest non-zero value a level +1 encode (the unclamped one) can see: linearFromSrgb(1) / 4.
+constexpr uint32_t rowEncFloorBits() { return NVPYR_SRGB_DECODE_BITS[1] - (2u << 23); }
+
+// entry[row] + bits(x) carries srgbFromLinear(x) in bits 24..31 for every x of the row that the kernel can present.
+// Fails (returns false) if a row held two thresholds or spanned 2^24 patterns or more -- impossible with the pinned
+// thresholds, checked so that a regenerated table cannot silently break the encode.
+bool buildRowEncodeTable(uint32_t* out)
+{
+  const uint32_t* thr       = NVPYR_SRGB_ENCODE_THRESHOLD_BITS;
+  const uint32_t  floorBits = rowEncFloorBits();
+  if(rowOfBits(0u) != 0u || rowOfBits(floorBits) < 1u || rowOfBits(kEncMinBits) < 1u || floorBits > kEncMinBits
+     || rowOfBits(kEncMaxBits) != kRowEncRows - 1u)
+    return false;
+  auto firstOfRow = [](uint32_t row) {  // rowOfBits is monotone over the non-negative floats
+    uint32_t lo = 0u, hi = kEncMaxBits + 1u;
+    while(lo < hi)
+    {
+      const uint32_t mid = lo + (hi - lo) / 2u;
+      if(rowOfBits(mid) >= row)
+        hi = mid;
+      else
+        lo = mid + 1u;
+    }
+    return lo;
+  };
+  out[0] = 0u - kRowEncZeroBits;  // exact zero of level +1, the only pattern that reaches row 0
+  uint32_t code = 0;              // thresholds <= first pattern of the row
+  for(uint32_t row = 1; row < kRowEncRows; ++row)
+  {
+    const uint32_t lo = std::max(firstOfRow(row), floorBits), hi = firstOfRow(row + 1u);  // [lo, hi)
+    if(hi <= lo)
+    {
+      out[row] = 0u;  // below the floor: never read
+      continue;
+    }
+    while(code < 255u && thr[code] <= lo)
+      ++code;
+    if(code < 255u && thr[code] < hi)
+    {
+      const uint32_t t = thr[code];
+      if((code + 1u < 255u && thr[code + 1u] < hi) || hi - t > (1u << 24) || t - lo > (1u << 24))
+        return false;
+      out[row] = ((code + 1u) << 24) - t;  // x >= t: code + 1;  x < t: the borrow leaves code
+    }
+    else
+    {
+      if(hi - lo > (1u << 24))
+        return false;
+      out[row] = (code << 24) - lo;
+    }
+  }
+  for(uint32_t i = kRowEncRows; i < ((kRowEncRows + 3u) & ~3u); ++i)
+    out[i] = 0u;
+  return true;
+}
+
 bool buildHostTables(DeviceTables& t)
 {
   static_assert(kEncShift <= 16 && kFastEncShift <= 16, "entry + bits must not carry past the code byte");
   for(int c = 0; c < 256; ++c)
     t.decode[c] = bitsToFloat(NVPYR_SRGB_DECODE_BITS[c]);
   return buildEncodeTable(t.encode, kEncShift, kEncEntriesPadded)
-         && buildEncodeTable(t.encodeFast, kFastEncShift, kFastEncEntriesPadded);
+         && buildEncodeTable(t.encodeFast, kFastEncShift, kFastEncEntriesPadded) && buildRowEncodeTable(t.encodeRows);
+}
+
+// Host-only proof of the row table: EVERY float pattern the kernel can present (the floor .. 1.0, and the zero of
+// level +1) is pushed through the kernel's own arithmetic -- row from RN(x + c), entry + bits, byte 3 -- and compared
+// with "number of pinned thresholds <= x".  Returns the number of mismatches (0 expected), ~0 if the build failed.
+uint64_t checkRowEncodeTable()
+{
+  static uint32_t rows[(kRowEncRows + 3u) & ~3u];
+  if(!buildRowEncodeTable(rows))
+    return ~0ull;
+  const uint32_t* thr  = NVPYR_SRGB_ENCODE_THRESHOLD_BITS;
+  uint64_t        bad  = ((rows[0] + kRowEncZeroBits) >> 24) != 0u;
+  uint32_t        code = 0;
+  for(uint32_t x = rowEncFloorBits(); x <= kEncMaxBits; ++x)
+  {
+    while(code < 255u && thr[code] <= x)
+      ++code;
+    const uint32_t row = rowOfBits(x);
+    bad += row >= kRowEncRows || ((rows[row] + x) >> 24) != code;
+  }
+  return bad;
 }
 
 // ------------------------------------------------------------ device context
@@ -1732,6 +1819,11 @@ int nvpyrGetLastCudaError(void)
 uint64_t nvpyrGetLaunchCount(void)
 {
   return g_launchCount.load();
+}
+
+uint64_t nvpyrSelfTestEncodeTable(void)
+{
+  return checkRowEncodeTable();
 }
 
 nvpyrStatus nvpyrShutdown(void)

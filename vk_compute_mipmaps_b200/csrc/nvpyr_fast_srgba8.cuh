@@ -141,8 +141,21 @@ namespace nvpyr {
 #ifndef NVPYR_FAST_DYNAMIC_TILES
 #define NVPYR_FAST_DYNAMIC_TILES 0
 #endif
+// NVPYR_FAST_ENC_ROWS = 1 (default, round 2): the encode bucket is keyed on RN(x + 1/32 - 2^-14) instead of on x
+// (nvpyr_functors.cuh "Row table"): 645 rows cover [0, 1], so every lane owns a private copy of every entry and a
+// warp-wide encode look-up is ONE conflict-free wavefront for any data, like the decode.  Decode and encode share one
+// table of 645 rows x 256 bytes: bytes 0..127 of row r = the 32 lane copies of linearFromSrgb(r) (r < 256) or a
+// level +3 stash row (256 <= r < 512), bytes 128..255 = the 32 lane copies of encode entry r.  The look-up is
+// FFMA (z = S' * 2^k + c, on the idle FMA pipe), PRMT (address = key(z) << 8 | lane << 2), LDS, IADD3 -- one
+// 16-lane-ALU instruction fewer than shift + mask -- and level +1 (12 of every 16 encodes) needs no clamp: exact
+// zero has row 0 to itself.  161 KB of tables + 64 KB TMA ring = 225.5 KB.
+// NVPYR_FAST_ENC_ROWS = 0: the bank-partitioned bucket tables of round 1 (NVPYR_ENC_WAYS etc. below apply).
+#ifndef NVPYR_FAST_ENC_ROWS
+#define NVPYR_FAST_ENC_ROWS 1
+#endif
+constexpr bool     kEncRows         = NVPYR_FAST_ENC_ROWS != 0;
 constexpr bool     kDynTiles        = NVPYR_FAST_DYNAMIC_TILES != 0;
-constexpr bool     kL3InDecode      = NVPYR_FAST_L3_IN_DECODE != 0;
+constexpr bool     kL3InDecode      = kEncRows || NVPYR_FAST_L3_IN_DECODE != 0;
 constexpr uint32_t kL3RowFloats     = kL3InDecode ? 64u : 32u;  // floats from one stash row (8 texels) to the next
 constexpr bool     kFastUncondLoads = NVPYR_FAST_UNCOND_LOADS != 0;
 constexpr int      kFastSlabUnroll = NVPYR_FAST_SLAB_UNROLL;
@@ -151,7 +164,7 @@ constexpr bool     kEncClamp      = NVPYR_FAST_ENC_CLAMP != 0;
 constexpr int      kFastWarps     = NVPYR_FAST_WARPS;
 constexpr int      kFastCtasPerSm = NVPYR_ENC_WAYS == 1 ? 2 : 1;
 constexpr bool     kFastPrefetch  = NVPYR_FAST_PREFETCH != 0;
-constexpr int      kDecScaleExp   = 100;  // decode table holds 2^-100 * linearFromSrgb(code)
+constexpr int      kDecScaleExp   = kFastDecScaleExp;  // decode table holds 2^-100 * linearFromSrgb(code)
 constexpr uint32_t kEncKeysPerOctave = 1u << (23 - kFastEncShift);
 constexpr uint32_t kEncLowOctaves = kEncClamp ? 0 : NVPYR_FAST_ENC_LOW_OCTAVES;  // bucket table extended below 2^-13
 // Is every non-zero value of level K inside the extended table?  linearFromSrgb(1) = 2^-11.7: sums of level K
@@ -166,6 +179,17 @@ constexpr uint32_t kEncStride     = 4u * kEncWays;  // bytes per bucket entry (a
 constexpr uint32_t kEncStrideLog2 = kEncWays == 1 ? 2 : kEncWays == 2 ? 3 : kEncWays == 4 ? 4 : kEncWays == 8 ? 5 : 6;
 static_assert((1u << kEncStrideLog2) == kEncStride, "1, 2, 4, 8 or 16 copies");
 
+#if NVPYR_FAST_ENC_ROWS
+struct Srgba8FastSmem
+{
+  // row r: floats 0..31 = lane copies of 2^-100 * linearFromSrgb(r) (r < 256) / stash row r - 256 (256 <= r < 512),
+  //        floats 32..63 = lane copies of encode entry r
+  float decode[kRowEncRows * 64];
+  alignas(128) unsigned char ring[kFastWarps][2048];  // per warp: the level-0 slab in flight (8 rows x 256 bytes)
+  unsigned long long tmaBar[kFastWarps];              // per warp: mbarrier the slab's copy completes on
+};
+static_assert(NVPYR_FAST_TMA != 1, "row-table layout: tensor-map staging or the register path");
+#else
 struct Srgba8FastSmem
 {
   float    decode[256 * 64];        // [code][64]: floats 0..31 = per-lane copies, 32..63 spare (zero words live there)
@@ -178,24 +202,30 @@ struct Srgba8FastSmem
   unsigned long long tmaBar[kFastWarps];              // per warp: mbarrier the slab's row copies complete on
 #endif
 };
-#if NVPYR_FAST_TMA
+#endif
+#if NVPYR_FAST_TMA || NVPYR_FAST_ENC_ROWS
 static_assert(sizeof(Srgba8FastSmem) + 1024 <= 227 * 1024, "TMA ring: build with NVPYR_FAST_ENC_LOW_OCTAVES=3");
 static_assert(offsetof(Srgba8FastSmem, ring) % 128 == 0 && alignof(Srgba8FastSmem) >= 128,
               "cp.async.bulk.tensor destinations must be 128-byte aligned inside a 128-byte aligned block");
 #endif
 constexpr bool kFastTma = NVPYR_FAST_TMA != 0;
-static_assert(!kL3InDecode || (NVPYR_FAST_ENC_CLAMP != 0 && kFastWarps * 8 <= 256),
+static_assert(kEncRows || !kL3InDecode || (NVPYR_FAST_ENC_CLAMP != 0 && kFastWarps * 8 <= 256),
               "stashes in the decode table's spare halves: every encode clamps (no zero words), at most 256 stash rows");
 // First float of the stash of warp (or local tile) j.
 __device__ __forceinline__ float* stashOf(Srgba8FastSmem& sm, uint32_t j)
 {
+#if NVPYR_FAST_ENC_ROWS
+  static_assert(256 + kFastWarps * 8 <= kRowEncRows, "stash rows live below the encode entries of rows 256..");
+  return &sm.decode[(256u + j * 8u) * 64u];
+#else
   return kL3InDecode ? &sm.decode[j * 8u * 64u + 32u] : &sm.l3[kL3InDecode ? 0u : j][0][0][0];
+#endif
 }
 // Dynamic shared memory of a launch: only the kernels that stage through the TMA ring pay for it (the others keep
 // the SM's L1 for their loads in flight).
 constexpr size_t fastSmemBytes(bool tma)
 {
-#if NVPYR_FAST_TMA
+#if NVPYR_FAST_TMA || NVPYR_FAST_ENC_ROWS
   return tma ? sizeof(Srgba8FastSmem) : offsetof(Srgba8FastSmem, ring);
 #else
   return sizeof(Srgba8FastSmem) + 0 * size_t(tma);
@@ -250,9 +280,47 @@ struct FastTensorMap
   int unused;
 };
 #endif
+#if !NVPYR_FAST_ENC_ROWS
 static_assert(offsetof(Srgba8FastSmem, decode) == 0 && offsetof(Srgba8FastSmem, encode) == 65536 + 128,
               "encScaled's zero words assume this layout");
+#endif
 
+#if NVPYR_FAST_ENC_ROWS
+// Per-level constants of the scaled encode.  The carried value is S' = 2^-E * 4^K * x, so
+// bits(x) = bits(S') + ((E - 2K) << 23) and RN(x + c) = fma(S', 2^(E - 2K), c).
+template <int K>
+struct EncConst
+{
+  static constexpr uint32_t kAdd = uint32_t(kDecScaleExp - 2 * K) << 23;
+  // Level +1 sees exact zero or values >= linearFromSrgb(1) / 4: zero has row 0 to itself and its entry is made for
+  // the pattern bits(0) + kAdd, everything else lies inside the table.  Deeper levels (and the premultiply, K = 0)
+  // can see smaller non-zero values: they clamp S' from below to 2^-13 (below the first threshold) first.
+  static constexpr bool     kClamp   = K != 1;
+  static constexpr uint32_t kMinBits = kEncMinBits - kAdd;
+  static constexpr uint32_t kScaleBits = uint32_t(127 + kDecScaleExp - 2 * K) << 23;  // 2^(E - 2K)
+};
+static_assert(EncConst<1>::kAdd == kRowEncZeroBits, "row 0 of the encode table is built for the zero of level +1");
+
+// Address bias of the encode half-rows: row key k lives at byte (k - kRowEncFirstKey) * 256 + 128 of the table.
+constexpr int32_t kRowEncBias = int32_t(kRowEncFirstKey << 8) - 128;
+
+__device__ __forceinline__ void srgba8FastInit(Srgba8FastSmem& sm, const DeviceTables* t)
+{
+  // thread -> (row, 16-byte column): eight consecutive threads write the 128 contiguous bytes of one half row
+  uint4* tab = reinterpret_cast<uint4*>(sm.decode);  // 16 uint4 per row: 0..7 decode / stash, 8..15 encode
+  for(uint32_t i = threadIdx.x; i < kRowEncRows * 8u; i += blockDim.x)
+  {
+    const uint32_t row = i >> 3, col = i & 7u;
+    const uint32_t e   = __ldg(&t->encodeRows[row]);
+    tab[row * 16u + 8u + col] = make_uint4(e, e, e, e);
+    if(row < 256u)
+    {
+      const uint32_t v = __float_as_uint(__fmul_rn(__ldg(&t->decode[row]), 7.888609052210118e-31f));  // * 2^-100, exact
+      tab[row * 16u + col] = make_uint4(v, v, v, v);
+    }
+  }
+}
+#else
 // Per-level constants of the scaled encode.  The carried value is S' = 2^-E * 4^K * x, so
 // bits(x) = bits(S') + ((E - 2K) << 23) and key(x) = key(S') + (E - 2K) * kEncKeysPerOctave.
 template <int K>
@@ -318,6 +386,8 @@ __device__ __forceinline__ void srgba8FastInit(Srgba8FastSmem& sm, const DeviceT
     putZeroWord<4>(sm), putZeroWord<5>(sm), putZeroWord<6>(sm);
   }
 }
+
+#endif
 
 // 2^-100 * linearFromSrgb of byte k (0..2) of a packed texel: PRMT + LDS.
 template <int kByte>
@@ -400,6 +470,27 @@ __device__ __forceinline__ V4 quadSumV(const unsigned char* dec, uint32_t laneOf
               add4(decodeTexel(dec, laneOff, ur), decodeTexel(dec, laneOff, lr)));
 }
 
+#if NVPYR_FAST_ENC_ROWS
+// Encode of one RGB channel carried as S' = 2^-100 * 4^K * x; the code lands in bits 24..31 (kEncCodeByte).
+// encSel = lane * 4: the lane's private column of the row table.  encBytes = table base - kRowEncBias.
+constexpr uint32_t kEncCodeByte = 3;
+template <int K>
+__device__ __forceinline__ uint32_t encScaled(const unsigned char* encBytes, float s, uint32_t encSel = 0)
+{
+  if(EncConst<K>::kClamp)
+    s = fmaxf(s, __uint_as_float(EncConst<K>::kMinBits));  // below the first threshold everything encodes to 0
+  const float    z   = __fmaf_rn(s, __uint_as_float(EncConst<K>::kScaleBits), __uint_as_float(kRowEncCBits));  // RN(x + c)
+  const uint32_t off = __byte_perm(__float_as_uint(z), encSel, 0x5324);  // key(z) << 8 | lane << 2
+  const uint32_t e   = *reinterpret_cast<const uint32_t*>(encBytes + off);
+  return e + __float_as_uint(s) + EncConst<K>::kAdd;
+}
+__device__ __forceinline__ uint32_t encSelOfLane(uint32_t lane) { return lane * 4u; }
+__device__ __forceinline__ const unsigned char* encBaseOf(const Srgba8FastSmem& sm)
+{
+  return reinterpret_cast<const unsigned char*>(sm.decode) - kRowEncBias;
+}
+#else
+constexpr uint32_t kEncCodeByte = 2;
 // Encode of one RGB channel carried as S' = 2^-100 * 4^K * x; the code lands in bits 16..23.
 // Covered levels (encCovered): every non-zero S' lies inside the extended table, zero reads its dedicated word.
 // encWay = (lane & (kEncWays - 1)) * 4: which copy of the entry this lane reads.
@@ -417,6 +508,15 @@ __device__ __forceinline__ uint32_t encScaled(const unsigned char* encBytes, flo
   const uint32_t e = *reinterpret_cast<const uint32_t*>(encBytes + off - EncConst<K>::kBias);
   return e + b + EncConst<K>::kAdd;
 }
+__device__ __forceinline__ uint32_t encSelOfLane(uint32_t lane) { return kEncWays == 1 ? 0u : (lane & (kEncWays - 1u)) * 4u; }
+__device__ __forceinline__ const unsigned char* encBaseOf(const Srgba8FastSmem& sm)
+{
+  return reinterpret_cast<const unsigned char*>(sm.encode);
+}
+#endif
+// PRMT selectors that gather code bytes: (own code byte, other's code byte) etc.
+constexpr uint32_t kSelCC = kEncCodeByte | ((kEncCodeByte + 4u) << 4);  // byte0 = a.code, byte1 = b.code
+constexpr uint32_t kSelCA = kEncCodeByte | (4u << 4);                   // byte0 = a.code, byte1 = b.byte0 (alpha)
 // uint(a * 255 + 0.5) for a = S / 4^K (alpha is not pre-scaled); code in bits 0..7 (a <= 1: no clamp).
 template <int K>
 __device__ __forceinline__ uint32_t encAlphaScaled(float s)
@@ -428,10 +528,10 @@ __device__ __forceinline__ uint32_t encAlphaScaled(float s)
 template <int K>
 __device__ __forceinline__ uint32_t encWordScaled(const unsigned char* encBytes, float4 s)
 {
-  const uint32_t w = kEncWays == 1 ? 0u : (threadIdx.x & (kEncWays - 1u)) * 4u;
+  const uint32_t w = encSelOfLane(threadIdx.x & 31u);
   const uint32_t r = encScaled<K>(encBytes, s.x, w), g = encScaled<K>(encBytes, s.y, w), b = encScaled<K>(encBytes, s.z, w);
   const uint32_t a = encAlphaScaled<K>(s.w);
-  return __byte_perm(__byte_perm(r, g, 0x0062), __byte_perm(b, a, 0x0042), 0x5410);
+  return __byte_perm(__byte_perm(r, g, kSelCC), __byte_perm(b, a, kSelCA), 0x5410);
 }
 
 template <int K>
@@ -467,8 +567,8 @@ __device__ __forceinline__ uint32_t premultiplyWord(const unsigned char* dec, co
   const uint32_t r = encScaled<0>(enc, __fmul_rn(dec8<0>(dec, w, laneOff), a), encWay);
   const uint32_t g = encScaled<0>(enc, __fmul_rn(dec8<1>(dec, w, laneOff), a), encWay);
   const uint32_t b = encScaled<0>(enc, __fmul_rn(dec8<2>(dec, w, laneOff), a), encWay);
-  // codes sit in byte 2 of r, g, b; alpha stays in byte 3 of w
-  return __byte_perm(__byte_perm(r, g, 0x0062), __byte_perm(b, w, 0x0072), 0x5410);
+  // codes sit in byte kEncCodeByte of r, g, b; alpha stays in byte 3 of w
+  return __byte_perm(__byte_perm(r, g, kSelCC), __byte_perm(b, w, kEncCodeByte | (7u << 4)), 0x5410);
 }
 __device__ __forceinline__ bool premultiplyRow(const unsigned char* dec, const unsigned char* enc, uint32_t laneOff,
                                                uint32_t encWay, uint4& c)
@@ -492,9 +592,9 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
   gridDependencyWait();
   gridLaunchDependents();
   const unsigned char* dec = reinterpret_cast<const unsigned char*>(sm.decode);
-  const unsigned char* enc = reinterpret_cast<const unsigned char*>(sm.encode);
+  const unsigned char* enc = encBaseOf(sm);
   const uint32_t       lane = threadIdx.x & 31u, laneOff = lane * 4u;
-  const uint32_t       way  = kEncWays == 1 ? 0u : (lane & (kEncWays - 1u)) * 4u;
+  const uint32_t       way  = encSelOfLane(lane);
   const uint64_t       step = uint64_t(gridDim.x) * blockDim.x;
   for(uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += 2u * step)
   {
@@ -550,7 +650,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
   gridDependencyWait();    // the previous kernel's levels are complete and visible
   gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
   const unsigned char* dec = reinterpret_cast<const unsigned char*>(sm.decode);
-  const unsigned char* enc = reinterpret_cast<const unsigned char*>(sm.encode);
+  const unsigned char* enc = encBaseOf(sm);
 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t tx = lane & 15u, ty = lane >> 4;  // lane = 4x4 texels at (4 tx, 4 ty) of a 64x8 slab
@@ -572,7 +672,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
   // gather selectors: step 1 (xor 16) builds the 2-byte pair of this column, step 2 (xor 1) the word
   //   x even: pair = (R from y-even lane, G from y-odd lane), codes in byte 2 of both
   //   x odd : pair = (B from y-even lane (byte 2), A from y-odd lane (byte 0))
-  const uint32_t sel1 = xOdd ? (yOdd ? 0x0006u : 0x0042u) : (yOdd ? 0x0026u : 0x0062u);
+  constexpr uint32_t kOwn = kEncCodeByte, kOther = kEncCodeByte + 4u;  // PRMT indices of the two code bytes
+  const uint32_t sel1 = xOdd ? (yOdd ? (kOther | 0u << 4) : (kOwn | 4u << 4)) : (yOdd ? (kOther | kOwn << 4) : (kOwn | kOther << 4));
   const uint32_t sel2 = xOdd ? 0x1054u : 0x5410u;
 
   // Tiles are dealt CTA-major so that mid-size images still spread over every SM.
@@ -747,7 +848,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
 
       if(kPremul && active)
       {
-        const uint32_t way = kEncWays == 1 ? 0u : (lane & (kEncWays - 1u)) * 4u;
+        const uint32_t way = encSelOfLane(lane);
         bool           changed = premultiplyRow(dec, enc, laneOff, way, c0);
         changed |= premultiplyRow(dec, enc, laneOff, way, c1);
         changed |= premultiplyRow(dec, enc, laneOff, way, c2);
@@ -807,7 +908,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
         const float u = __fadd_rn(yOdd ? t1 : t0, __shfl_xor_sync(0xffffffffu, yOdd ? t0 : t1, 16));
         // encode this lane's channel, gather the four bytes
         const uint32_t code =
-            ch == 3u ? encAlphaScaled<3>(u) : encScaled<3>(enc, u, kEncWays == 1 ? 0u : (lane & (kEncWays - 1u)) * 4u);
+            ch == 3u ? encAlphaScaled<3>(u) : encScaled<3>(enc, u, encSelOfLane(lane));
         const uint32_t pair = __byte_perm(code, __shfl_xor_sync(0xffffffffu, code, 16), sel1);
         const uint32_t word = __byte_perm(pair, __shfl_xor_sync(0xffffffffu, pair, 1), sel2);
         if(active)

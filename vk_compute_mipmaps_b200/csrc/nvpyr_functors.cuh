@@ -65,11 +65,29 @@ constexpr uint32_t kFastEncMaxKey  = kEncMaxBits >> kFastEncShift;
 constexpr uint32_t kFastEncEntries = kFastEncMaxKey - kFastEncMinKey + 1;
 constexpr uint32_t kFastEncEntriesPadded = (kFastEncEntries + 3u) & ~3u;
 
+// Row table of the tuned fast kernel (round 2).  The bucket of a value x in [0, 1] is taken from the float
+//     z = RN(x + kRowEncC),   row = (bits(z) >> 16) - kRowEncFirstKey        (sign/exponent + 7 mantissa bits of z)
+// instead of from x itself.  Adding the constant compresses the twelve low octaves of x, where the sRGB thresholds
+// are far apart, into the linear part of z's first octave, so 645 rows cover [0, 1] where keys on x need 1665 --
+// few enough rows to give EVERY LANE ITS OWN COPY of every entry (a row = 32 lanes x 4 bytes): a warp-wide
+// look-up is one conflict-free wavefront whatever the data.  RN(x + c) is monotone in x, so a row is an interval
+// of x; it holds at most one threshold and spans less than 2^24 float patterns (checked when the table is built),
+// and the entry is biased so that
+//     t = entry[row] + bits(x);   code = t >> 24
+// (x clamped from below to 2^-13; exact zero has row 0 to itself -- kRowEncC lies half a row below 1/32 -- whose
+// entry is made for the bit pattern the kernel presents for a zero of level +1, the only level encoded unclamped).
+constexpr uint32_t kRowEncCBits    = 0x3CFF8000u;  // 1/32 - 2^-14
+constexpr uint32_t kRowEncFirstKey = kRowEncCBits >> 16;
+constexpr uint32_t kRowEncRows     = 645;          // keys 0x3CFF (x = 0) .. 0x3F83 (x = 1)
+constexpr int      kFastDecScaleExp = 100;         // the tuned fast kernel carries 2^-100 * 4^K * x
+constexpr uint32_t kRowEncZeroBits = uint32_t(kFastDecScaleExp - 2) << 23;  // what bits(0) + kAdd<1> presents
+
 struct alignas(16) DeviceTables
 {
   float    decode[256];                // linearFromSrgb(c), shaders/srgb.h:18-28 (pinned bits)
   uint32_t encode[kEncEntriesPadded];  // bucket table described above
   uint32_t encodeFast[kFastEncEntriesPadded];  // the same, keyed on bits >> kFastEncShift
+  uint32_t encodeRows[(kRowEncRows + 3u) & ~3u];  // row table described above
 };
 
 // Programmatic dependent launch (sm_90+): every kernel of the library is launched with
