@@ -1,7 +1,7 @@
 #!/bin/bash
 # tools/sass_loop.sh <lib.so> [mangled-substring]: SASS of one kernel with the loop structure (backward branches)
 # and an opcode histogram of its innermost hot loop (the longest backward-branch span is printed first).
-LIB=$1; PAT=${2:-fastSrgba8KernelILi6ELb0ELb0ELb0EEE}
+LIB=$1; PAT=${2:-fastSrgba8KernelILi6ELb0ELb0ELb0ELi24EEE}
 cuobjdump -sass $LIB | awk -v pat="$PAT" '/Function :/{f=($0 ~ pat)} f' | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed -E 's/^\s*\/\*([0-9a-f]+)\*\/\s+/\1 /; s/\s*\/\*.*//; s/ +/ /g' > /tmp/kernel.sass
 echo "instructions: $(wc -l < /tmp/kernel.sass)"
 python3 - <<'PY'

@@ -447,13 +447,13 @@ const bool g_noSlabTasks = [] {
   return e != nullptr && e[0] == '1';
 }();
 
-template <int M, bool kBatch, bool kPremul, bool kSlabTasks>
-nvpyrStatus launchFastSrgba8K(const DeviceContext& ctx, const FastParams& p, const FastBatch& b, uint64_t work,
+template <int M, bool kBatch, bool kPremul, bool kSlabTasks, int kWarps>
+nvpyrStatus launchFastSrgba8W(const DeviceContext& ctx, const FastParams& p, const FastBatch& b, uint64_t work,
                               cudaStream_t stream)
 {
   const size_t smem = fastSmemBytes(kFastTma && !kBatch && !kPremul && !kSlabTasks);
   int          grid = 1;
-  nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M, kBatch, kPremul, kSlabTasks>, smem, ctx, work, &grid, kFastWarps * 32);
+  nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M, kBatch, kPremul, kSlabTasks, kWarps>, smem, ctx, work, &grid, kWarps * 32);
   if(st != NVPYR_SUCCESS)
     return st;
   FastTensorMap tmap{};
@@ -483,9 +483,35 @@ nvpyrStatus launchFastSrgba8K(const DeviceContext& ctx, const FastParams& p, con
       return tst;
     pp.tileCounter = slot + 1;
   }
-  NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, kBatch, kPremul, kSlabTasks>, grid, kFastWarps * 32, smem, stream, pp, b, tmap));
+  NVPYR_CUDA(launchKernel(fastSrgba8Kernel<M, kBatch, kPremul, kSlabTasks, kWarps>, grid, kWarps * 32, smem, stream, pp, b, tmap));
   ++g_launchCount;
   return NVPYR_SUCCESS;
+}
+
+// Warps per CTA of a tile-mode launch (see fastSrgba8Kernel): the launch takes ceil(tiles / resident warps) rounds of
+// one tile per warp; a round of the 24-warp build is shorter (measured 12.8 vs 18.1 us for 64 x 64 tiles at 16384^2) but
+// holds fewer tiles.  NVPYR_FAST_WARPS_LARGE=32 pins the 32-warp build (A/B timing).
+constexpr int kFastWarpsLarge = 24;
+const bool g_noLargeWarps = [] {
+  const char* e = getenv("NVPYR_FAST_WARPS_LARGE");
+  return e != nullptr && atoi(e) == 32;
+}();
+inline bool preferFewerWarps(const DeviceContext& ctx, uint64_t tiles)
+{
+  if(g_noLargeWarps)
+    return false;
+  const uint64_t r32 = (tiles + uint64_t(ctx.smCount) * kFastWarps - 1) / (uint64_t(ctx.smCount) * kFastWarps);
+  const uint64_t r24 = (tiles + uint64_t(ctx.smCount) * kFastWarpsLarge - 1) / (uint64_t(ctx.smCount) * kFastWarpsLarge);
+  return r24 * 128u < r32 * 181u;
+}
+
+template <int M, bool kBatch, bool kPremul, bool kSlabTasks>
+nvpyrStatus launchFastSrgba8K(const DeviceContext& ctx, const FastParams& p, const FastBatch& b, uint64_t work,
+                              cudaStream_t stream)
+{
+  if(!kSlabTasks && !kPremul && preferFewerWarps(ctx, work))
+    return launchFastSrgba8W<M, kBatch, false, false, kFastWarpsLarge>(ctx, p, b, work, stream);
+  return launchFastSrgba8W<M, kBatch, kPremul, kSlabTasks, kFastWarps>(ctx, p, b, work, stream);
 }
 
 // premul: level 0 has straight alpha; premultiply it on the fly (scoped_image.hpp:233-255 fused into the read).

@@ -631,10 +631,15 @@ struct FastBatch
 // and the warp that arrives last at the tile (shared-memory counter, nobody waits) finishes levels +4..+M.
 // A 1024^2 image has 256 tiles for 4736 resident warps: in tile mode 5 % of the warps walk 8 slabs each, in
 // slab mode 43 % walk one.  Same expression trees, same bits.
-template <int M, bool kBatch, bool kPremul, bool kSlabTasks>
-__global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
+// kWarps: warps per CTA (one CTA per SM).  32 warps leave 64 registers per thread -- ptxas then spills a tile
+// coordinate and re-derives lane constants inside the slab loop -- 24 warps get 80 and need neither: with enough tiles
+// to keep every warp busy for several rounds the 24-warp build is 4 % faster (16384^2: 262 -> 251 us), while images
+// of about one tile per warp want the 32-warp build's extra tasks in flight (4096^2: 24.1 vs 27.1 us).
+template <int M, bool kBatch, bool kPremul, bool kSlabTasks, int kWarps = kFastWarps>
+__global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
     fastSrgba8Kernel(const FastParams p, const FastBatch batch, const __grid_constant__ FastTensorMap tmap)
 {
+  static_assert(kWarps <= kFastWarps, "the shared-memory layout is sized for kFastWarps");
   static_assert(M >= 2 && M <= 6, "2..6 levels");
   static_assert(!kSlabTasks || (M >= 4 && !kBatch), "slab tasks: single image, levels beyond +3");
   constexpr uint32_t kTileH = M >= 3 ? (1u << M) : 8u, kSlabs = kTileH / 8u;
@@ -652,7 +657,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
   const unsigned char* dec = reinterpret_cast<const unsigned char*>(sm.decode);
   const unsigned char* enc = encBaseOf(sm);
 
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  // (the shuffle tells the compiler that the warp index -- and with it the tile bookkeeping -- is warp-uniform)
+  const uint32_t lane = threadIdx.x & 31u, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t tx = lane & 15u, ty = lane >> 4;  // lane = 4x4 texels at (4 tx, 4 ty) of a 64x8 slab
   const uint32_t laneOff = lane * 4u;
   const uint32_t W = p.lv[0].w, H = p.lv[0].h;
@@ -677,7 +683,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
   const uint32_t sel2 = xOdd ? 0x1054u : 0x5410u;
 
   // Tiles are dealt CTA-major so that mid-size images still spread over every SM.
-  const uint32_t tileStep = gridDim.x * kFastWarps;
+  const uint32_t tileStep = gridDim.x * kWarps;
   uint32_t       task     = warp;  // slab tasks: local task index = local tile * kSlabs + slab
   uint32_t       tile     = kSlabTasks ? blockIdx.x + gridDim.x * (task / kSlabs) : blockIdx.x + gridDim.x * warp;
   uint32_t       slab0    = kSlabTasks ? task % kSlabs : 0u;  // first slab of this warp's current unit of work
@@ -752,7 +758,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
   while(tile < numTiles)
   {
     // this unit of work, and the one after it (for the prefetch)
-    const uint32_t nextTask  = task + kFastWarps;
+    const uint32_t nextTask  = task + kWarps;
     const uint32_t nextSlab0 = kSlabTasks ? nextTask % kSlabs : 0u;
     uint32_t       nextTileI = blockIdx.x + gridDim.x * (nextTask / kSlabs), fetched = 0;
     if(!kSlabTasks && !kDynTiles)
