@@ -447,6 +447,13 @@ const bool g_noSlabTasks = [] {
   return e != nullptr && e[0] == '1';
 }();
 
+// NVPYR_SLAB_MAX_TILES_PER_WARP_X100: up to how many tiles per resident warp (x 100) a single-image fast step runs in
+// slab-task mode (A/B timing; see launchFastSrgba8T).
+const uint32_t g_slabMaxTilesPerWarpX100 = [] {
+  const char* e = getenv("NVPYR_SLAB_MAX_TILES_PER_WARP_X100");
+  return e != nullptr ? uint32_t(atoi(e)) : 25u;
+}();
+
 template <int M, bool kBatch, bool kPremul, bool kSlabTasks, int kWarps>
 nvpyrStatus launchFastSrgba8W(const DeviceContext& ctx, const FastParams& p, const FastBatch& b, uint64_t work,
                               cudaStream_t stream)
@@ -491,7 +498,10 @@ nvpyrStatus launchFastSrgba8W(const DeviceContext& ctx, const FastParams& p, con
 // Warps per CTA of a tile-mode launch (see fastSrgba8Kernel): the launch takes ceil(tiles / resident warps) rounds of
 // one tile per warp; a round of the 24-warp build is shorter (measured 12.8 vs 18.1 us for 64 x 64 tiles at 16384^2) but
 // holds fewer tiles.  NVPYR_FAST_WARPS_LARGE=32 pins the 32-warp build (A/B timing).
-constexpr int kFastWarpsLarge = 24;
+#ifndef NVPYR_FAST_WARPS_LARGE_N
+#define NVPYR_FAST_WARPS_LARGE_N 24
+#endif
+constexpr int kFastWarpsLarge = NVPYR_FAST_WARPS_LARGE_N;
 const bool g_noLargeWarps = [] {
   const char* e = getenv("NVPYR_FAST_WARPS_LARGE");
   return e != nullptr && atoi(e) == 32;
@@ -533,10 +543,13 @@ nvpyrStatus launchFastSrgba8T(const DeviceContext& ctx, FastParams p, cudaStream
   // Few tiles for the resident warps (images up to ~2048^2): warps take single slabs, not whole tiles.  With a
   // tile or more per warp the tile mode wins (the slab-to-slab prefetch stays inside one warp): measured
   // 1024^2 9.7 -> 5.7 us, 2048^2 14.2 -> 12.8 us, but 2560x1440 16.1 -> 16.5 us and 4096^2 26.6 -> 28.4 us.
+  // Round 2: the slab-task kernel recycles its stash slots, so it is no longer limited to 32 tiles per CTA, and was
+  // measured on larger images (NVPYR_SLAB_MAX_TILES_PER_WARP_X100): 4096^2 22.4 -> 27.1 us, 8192^2 69 -> 90 us.  The
+  // kernel is issue-bound and a slab task costs ~25 % more instructions than a slab of a tile walk (tile coordinates,
+  // output pointers, hand-off), which is more than the partly filled last round of whole tiles wastes (~4 % at 8192^2).
   constexpr bool kCanSlab = M >= 4;
-  const uint64_t ctas     = std::min<uint64_t>(work, uint64_t(ctx.smCount));
-  if(kCanSlab && !g_noSlabTasks && (work + ctas - 1) / ctas <= uint64_t(kFastWarps)
-     && 4u * work <= uint64_t(ctx.smCount) * kFastWarps)
+  const uint64_t resident = uint64_t(ctx.smCount) * kFastWarps;
+  if(kCanSlab && !g_noSlabTasks && 100u * work <= uint64_t(premul ? 25u : g_slabMaxTilesPerWarpX100) * resident)
     return premul ? launchFastSrgba8K<M, false, true, kCanSlab>(ctx, p, b, work, stream)
                   : launchFastSrgba8K<M, false, false, kCanSlab>(ctx, p, b, work, stream);
   return premul ? launchFastSrgba8K<M, false, true, false>(ctx, p, b, work, stream)

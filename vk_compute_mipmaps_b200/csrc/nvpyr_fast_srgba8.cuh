@@ -625,12 +625,15 @@ struct FastBatch
 // kPremul: level 0 holds straight (un-premultiplied) alpha; it is premultiplied on the fly, written back in
 // place (only 4x4 blocks that changed) and the chain is generated from the premultiplied codes -- exactly what
 // premultiplyKernel followed by this kernel produce, minus one full read + write pass over level 0.
-// kSlabTasks (M >= 4, images of up to 32 tiles per CTA, i.e. up to ~4096^2): the unit of work of a warp is ONE
-// 64x8 slab instead of a whole 64 x 2^M tile.  A CTA owns tiles c, c + G, ... (local index j < 32); its warps
-// take the slabs of those tiles round-robin, drop their row of level +3 sums into the tile's stash (sm.l3[j])
-// and the warp that arrives last at the tile (shared-memory counter, nobody waits) finishes levels +4..+M.
+// kSlabTasks (M >= 4; launches of few tiles per resident warp, up to ~8192^2): the unit of work of a warp is ONE
+// 64x8 slab instead of a whole 64 x 2^M tile.  A CTA owns tiles c, c + G, ... (local index j); its warps take the
+// slabs of those tiles round-robin, drop their row of level +3 sums into the tile's stash (slot j mod 32) and the
+// warp that arrives last at the tile (shared-memory counter, nobody waits) finishes levels +4..+M.  A slot is handed
+// to local tile j + 32 by a generation counter that the finishing warp bumps (eight warps work on a tile at a time, so
+// a slot is free again long before it is needed: the check never spins in practice, it is there for correctness).
 // A 1024^2 image has 256 tiles for 4736 resident warps: in tile mode 5 % of the warps walk 8 slabs each, in
-// slab mode 43 % walk one.  Same expression trees, same bits.
+// slab mode 43 % walk one; 8192^2 is 3.46 tiles per warp -- the fourth round of whole tiles runs 46 % full -- but 27.7
+// slabs.  Same expression trees, same bits.
 // kWarps: warps per CTA (one CTA per SM).  32 warps leave 64 registers per thread -- ptxas then spills a tile
 // coordinate and re-derives lane constants inside the slab loop -- 24 warps get 80 and need neither: with enough tiles
 // to keep every warp busy for several rounds the 24-warp build is 4 % faster (16384^2: 262 -> 251 us), while images
@@ -646,10 +649,12 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
   constexpr int      kSlabUnroll = kPremul ? 1 : kFastSlabUnroll;
   constexpr bool     kPinPrefetch = NVPYR_FAST_PIN_PREFETCH != 0 && kSlabUnroll > 1 && kSlabs > 1;
   extern __shared__ __align__(128) unsigned char smemRaw[];  // the TMA ring inside needs 128-byte alignment
-  __shared__ uint32_t tileArrivals[kFastWarps];  // slab tasks: slabs of local tile j that have arrived
+  constexpr uint32_t kSlots = kFastWarps;          // stash slots of the slab-task mode
+  __shared__ uint32_t tileArrivals[kSlots];        // slab tasks: slabs of the slot's current tile that have arrived
+  __shared__ uint32_t slotGeneration[kSlots];      // slab tasks: tiles the slot has seen completed
   Srgba8FastSmem& sm = *reinterpret_cast<Srgba8FastSmem*>(smemRaw);
-  if(kSlabTasks && threadIdx.x < kFastWarps)
-    tileArrivals[threadIdx.x] = 0u;
+  if(kSlabTasks && threadIdx.x < kSlots)
+    tileArrivals[threadIdx.x] = 0u, slotGeneration[threadIdx.x] = 0u;
   srgba8FastInit(sm, p.tables);
   __syncthreads();  // the only CTA-wide barrier
   gridDependencyWait();    // the previous kernel's levels are complete and visible
@@ -716,6 +721,8 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
     }
   };
   // TMA variant: this warp's staging buffer, its mbarrier and the phase the next wait expects
+  // (slab tasks keep the register path: measured with TMA staging, round 2, 2048^2 12.2 -> 15.5 us -- a warp runs one
+  // or two tasks there and the first copy of a CTA pays the tensor-map fetch on top of the DRAM latency)
   constexpr bool kTma = kFastTma && !kBatch && !kPremul && !kSlabTasks;
   uint32_t       tmaBar = 0u, tmaRing = 0u, tmaPhase = 0u;
   // Issues the row copies of slab s of tile t (rows cut at the image edges; nothing for a tile that does not exist).
@@ -750,7 +757,7 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fenceProxyAsync();
     __syncwarp();
-    tmaIssue(tile, 0u);
+    tmaIssue(tile, slab0);
   }
   else if(kFastPrefetch)
     loadRows(nxt);
@@ -784,8 +791,16 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
         nextTileI = __shfl_sync(0xffffffffu, fetched, 0) + tileStep;
       return tileCursor(nextTileI, nextSlab0);
     };
+    const uint32_t slot = kSlabTasks ? (task / kSlabs) % kSlots : 0u, generation = kSlabTasks ? (task / kSlabs) / kSlots : 0u;
     if(kSlabTasks)
-      myL3 = stashOf(sm, task / kSlabs);  // the tile's stash (local tile index < kFastWarps, see the launch code)
+    {
+      myL3 = stashOf(sm, slot);
+      // the slot's previous tile (local tile - kSlots) must have been finished before its stash is overwritten
+      if(lane == 0u)
+        while(*reinterpret_cast<volatile uint32_t*>(&slotGeneration[slot]) != generation)
+          ;
+      __syncwarp();
+    }
     const uint32_t tileInImage = kBatch ? tile % batch.tilesPerImage : tile;
     const uint32_t tileX = tileInImage % p.tilesX, tileY = tileInImage / p.tilesX;
     const uint32_t x0 = tileX * 64u + tx * 4u;
@@ -815,7 +830,9 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+768];" : "=r"(c3.x), "=r"(c3.y), "=r"(c3.z), "=r"(c3.w) : "r"(mine));
         __syncwarp();
         fenceProxyAsync();  // the generic-proxy reads above are ordered before the async-proxy writes below
-        if(slab + 1u < kSlabs)
+        if(kSlabTasks)
+          tmaIssue(nextTileI, nextSlab0);
+        else if(slab + 1u < kSlabs)
           tmaIssue(tile, slab + 1u);
         else
         {
@@ -936,7 +953,7 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
       __threadfence_block();
       uint32_t arrived = 0;
       if(lane == 0u)
-        arrived = atomicAdd(&tileArrivals[task / kSlabs], 1u);
+        arrived = atomicAdd(&tileArrivals[slot], 1u);
       arrived    = __shfl_sync(0xffffffffu, arrived, 0);
       finishTile = arrived == kSlabs - 1u;
       if(finishTile)
@@ -978,6 +995,13 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
         }
       }
       __syncwarp();  // the warp's level +3 tile is free again
+      if(kSlabTasks && lane == 0u)
+      {
+        // hand the slot to local tile + kSlots: counter back to zero, then the generation (in this order)
+        tileArrivals[slot] = 0u;
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t*>(&slotGeneration[slot]) = generation + 1u;
+      }
     }
     // next unit of work
     if(kSlabTasks)
