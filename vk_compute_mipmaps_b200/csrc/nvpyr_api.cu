@@ -887,6 +887,26 @@ const uint64_t kTailMaxTexels = [] {
 constexpr uint64_t kSoloMaxTexelsFast    = 64ull * 64ull;  // one 64x64 tile
 // general steps run solo when the input is at most kSoloMaxEdgeGeneral wide and high (one tile, nvpyr_kernels.cuh)
 
+// NVPYR_NO_SOLO_SMEM=1: solo general steps read their input from global memory tile by tile as in round 1 (A/B timing).
+const bool g_noSoloSmem = [] {
+  const char* e = getenv("NVPYR_NO_SOLO_SMEM");
+  return e != nullptr && e[0] == '1';
+}();
+// Largest input level (texels) of a solo general step in shared memory.  One CTA with un-replicated tables is
+// LSU-bound: measured (round 2) with 127^2 inputs allowed, 2047^2 27.2 -> 40.2 us and 3095x990 24.1 -> 31.7 us (the
+// 127 -> 63 -> 31 step alone takes ~20 us on one SM); with 63^2 the saved launch and the slower step cancel (4095^2
+// 51.0 us either way); up to 32^2 -- the steps that ran solo anyway -- shared memory wins: 4095^2 51.3 -> 48.4 us,
+// 4094^2 48.4 -> 45.8 us.
+const uint64_t g_soloSmemMaxTexels = [] {
+  const char* e = getenv("NVPYR_SOLO_SMEM_MAX_TEXELS");
+  return e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : 32ull * 32ull;
+}();
+template <class TF>
+bool soloSmemOk(uint32_t w, uint32_t h, uint32_t levels)
+{
+  return !g_noSoloSmem && uint64_t(w) * h <= g_soloSmemMaxTexels && soloSmemFits<TF>(w, h, levels);
+}
+
 template <class F>
 struct TailFunctors
 {
@@ -904,6 +924,7 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
 {
   using TF = typename TailFunctors<F>::type;
   TailParams tp{};
+  bool       anySoloSmem = false;
   tp.numSteps = uint32_t(count);
   tp.tables   = ctx.tables;
   nvpyrStatus tst = acquireTicket(ctx, r.stream, &tp.ticket);
@@ -924,14 +945,21 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
       ts.tilesY = (ts.lv[0].h + 63u) / 64u;
     }
     else
+    {
       generalTiles(ts.lv, s.levelCount, i == 0 ? kGenTile2Small : SoloTile2<typename TF::Value>::value, &ts.tilesX, &ts.tilesY);
+      ts.soloSmem = i > 0 && soloSmemOk<TF>(ts.lv[0].w, ts.lv[0].h, s.levelCount) ? 1u : 0u;
+      anySoloSmem |= ts.soloSmem != 0u;
+    }
   }
   uint64_t work = uint64_t(tp.steps[0].tilesX) * tp.steps[0].tilesY;
   if(tp.steps[0].pipeline == 1 && tp.steps[0].levels == 1)  // fastLoop1 is thread-strided, not tiled
     work = (uint64_t(tp.steps[0].lv[1].w) * tp.steps[0].lv[1].h + 255u) / 256u;
-  const size_t smem = sizeof(TailSmem<TF>);
+  // The whole-level buffers of the solo steps are only allocated by launches that use them (a small footprint lets
+  // the next kernel's CTAs move in early); the opt-in and the grid size are those of the larger footprint.
+  const size_t smemSolo = ((sizeof(TailSmem<TF>) + 15u) & ~size_t(15)) + sizeof(SoloSmem);
+  const size_t smem     = anySoloSmem ? smemSolo : sizeof(TailSmem<TF>);
   int          grid = 1;
-  nvpyrStatus  st   = persistentGrid(tailKernel<TF>, smem, ctx, work, &grid, kTailThreads);
+  nvpyrStatus  st   = persistentGrid(tailKernel<TF>, smemSolo, ctx, work, &grid, kTailThreads);
   if(st != NVPYR_SUCCESS)
     return st;
   NVPYR_CUDA(launchKernel(tailKernel<TF>, grid, kTailThreads, smem, r.stream, tp));
@@ -961,7 +989,9 @@ nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0
       while(i + count < n && count < int(kMaxTailSteps)
             && (steps[i + count].pipeline == 1
                     ? texels(i + count) <= kSoloMaxTexelsFast
-                    : std::max(steps[i + count].srcWidth, steps[i + count].srcHeight) <= kSoloMaxEdgeGeneral))
+                    : (std::max(steps[i + count].srcWidth, steps[i + count].srcHeight) <= kSoloMaxEdgeGeneral
+                       || soloSmemOk<typename TailFunctors<F>::type>(steps[i + count].srcWidth, steps[i + count].srcHeight,
+                                                                     steps[i + count].levelCount))))
         ++count;
       st = launchTail<F>(ctx, r, steps + i, count);
       i += count;

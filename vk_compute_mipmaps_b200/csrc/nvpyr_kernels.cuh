@@ -456,6 +456,7 @@ struct TailStep
   uint32_t  pipeline;  // 1 fast, 0 general
   uint32_t  levels;
   uint32_t  vec;       // fast: vector loads/stores allowed
+  uint32_t  soloSmem;  // solo general step that runs on whole levels held in shared memory (soloGeneralSmem)
   uint32_t  tilesX, tilesY;
   LevelView lv[7];
 };
@@ -480,6 +481,96 @@ struct TailSmem
   };
   uint32_t isLast;
 };
+
+// ---------------------------------------------------------------------------
+// Solo general steps on levels held in shared memory.
+//
+// The last steps of every NPOT chain are general dispatches on tiny levels (127^2, 63^2, 31^2, ...): three to
+// five dependent dispatches that the reference separates with pipeline barriers.  Run by one CTA straight from
+// global memory, each costs several dependent L2 round trips (nine texel fetches per output texel, 2 us or more
+// per step); spread over a second launch they cost its latency.  Here the CTA that runs the solo steps copies the
+// step's whole input level into shared memory once (coalesced), computes level +1 from there, keeps it as float32
+// values in shared memory for level +2 -- the reference's sharedLevel_ carry, glsl:555,664,717, for the whole level
+// instead of per work group: the same values -- and leaves the step's last level, as stored texels, in a small
+// shared buffer that is the next solo step's input.  Every level is also written to global memory as before; what
+// changes is only where the next step reads it from (the same bytes).  The functor set is used unchanged: its
+// load / store work on generic pointers.
+constexpr uint32_t kSoloInBytes  = 65536;  // a step's input level, stored texels, tight rows (127^2 sRGBA8, 63^2 rgba32f)
+constexpr uint32_t kSoloMidBytes = 65536;  // its level +1 as values (63^2 float4)
+constexpr uint32_t kSoloOutBytes = 16384;  // its last level, stored texels = the next step's input (ping-pong)
+struct SoloSmem
+{
+  alignas(16) unsigned char in[kSoloInBytes];
+  alignas(16) unsigned char mid[kSoloMidBytes];
+  alignas(16) unsigned char out[2][kSoloOutBytes];
+};
+// Can a general step (input w0 x h0, `levels` levels) run on SoloSmem with functor set F?
+template <class F>
+__host__ __device__ inline bool soloSmemFits(uint32_t w0, uint32_t h0, uint32_t levels)
+{
+  const uint64_t w1 = w0 > 1u ? w0 / 2u : 1u, h1 = h0 > 1u ? h0 / 2u : 1u;
+  const uint64_t w2 = w1 > 1u ? w1 / 2u : 1u, h2 = h1 > 1u ? h1 / 2u : 1u;
+  const uint64_t last = levels == 2u ? w2 * h2 : w1 * h1;
+  return uint64_t(w0) * h0 * F::kTexelBytes <= kSoloInBytes && w1 * h1 * sizeof(typename F::Value) <= kSoloMidBytes
+         && last * F::kTexelBytes <= kSoloOutBytes;
+}
+
+// One general step.  inSmem: where the input level lies in shared memory as tight rows of stored texels (nullptr:
+// copy it from global memory into solo.in first).  Leaves the step's last level in `outSmem` the same way.
+template <class F>
+__device__ __forceinline__ void soloGeneralSmem(const TailStep& st, const typename F::Shared& tables, SoloSmem& solo,
+                                                const unsigned char* inSmem, unsigned char* outSmem)
+{
+  using V                  = typename F::Value;
+  constexpr uint32_t TB    = F::kTexelBytes;
+  static_assert(TB % 4u == 0, "levels are staged in 4- or 16-byte words");
+  const LevelView    L0 = st.lv[0], L1 = st.lv[1], L2 = st.lv[2];
+  const uint32_t     pitchIn = L0.w * TB;
+  if(inSmem == nullptr)
+  {
+    // rows are tight in shared memory; in global memory they start on texel boundaries only (NPOT pitches)
+    constexpr uint32_t kWord = TB % 16u == 0 ? 16u : 4u;
+    const uint32_t     wordsPerRow = pitchIn / kWord, words = wordsPerRow * L0.h;
+    for(uint32_t i = threadIdx.x; i < words; i += blockDim.x)
+    {
+      const uint32_t       y = i / wordsPerRow, x = i - y * wordsPerRow;
+      const unsigned char* g = L0.ptr + size_t(y) * L0.pitch + size_t(x) * kWord;
+      if(kWord == 16u)
+        *reinterpret_cast<uint4*>(solo.in + size_t(i) * 16u) = __ldcg(reinterpret_cast<const uint4*>(g));
+      else
+        *reinterpret_cast<uint32_t*>(solo.in + size_t(i) * 4u) = __ldcg(reinterpret_cast<const uint32_t*>(g));
+    }
+    inSmem = solo.in;
+    __syncthreads();
+  }
+  const int k1x = kernelTaps(L0.w), k1y = kernelTaps(L0.h);
+  V*        mid = reinterpret_cast<V*>(solo.mid);
+  for(uint32_t t = threadIdx.x; t < L1.w * L1.h; t += blockDim.x)
+  {
+    const uint32_t       y = t / L1.w, x = t - y * L1.w;
+    const unsigned char* s = inSmem + size_t(2u * y) * pitchIn + size_t(2u * x) * TB;
+    const V out = reduceSample<F>(k1x, k1y, L1.w, L1.h, x, y,
+                                  [&](int dx, int dy) { return F::load(tables, s + size_t(dy) * pitchIn + size_t(dx) * TB); });
+    F::template store<true>(tables, L1.ptr + size_t(y) * L1.pitch + size_t(x) * TB, out);
+    if(st.levels == 2u)
+      mid[t] = F::sharedRound(out);  // sharedLevel_ (glsl:717)
+    else
+      F::template store<true>(tables, outSmem + size_t(t) * TB, out);
+  }
+  if(st.levels == 2u)
+  {
+    __syncthreads();
+    const int k2x = kernelTaps(L1.w), k2y = kernelTaps(L1.h);
+    for(uint32_t t = threadIdx.x; t < L2.w * L2.h; t += blockDim.x)
+    {
+      const uint32_t y = t / L2.w, x = t - y * L2.w;
+      const V*       m = mid + size_t(2u * y) * L1.w + 2u * x;
+      const V        out = reduceSample<F>(k2x, k2y, L2.w, L2.h, x, y, [&](int dx, int dy) { return m[size_t(dy) * L1.w + dx]; });
+      F::template store<true>(tables, L2.ptr + size_t(y) * L2.pitch + size_t(x) * TB, out);
+      F::template store<true>(tables, outSmem + size_t(t) * TB, out);
+    }
+  }
+}
 
 // kSolo: the step is run by one CTA alone (its general tiles were counted for soloTile2).
 template <class F, bool kSolo>
@@ -559,9 +650,24 @@ __global__ void __launch_bounds__(kTailThreads) tailKernel(const __grid_constant
     return;
   __threadfence();  // acquire side of the ticket
 
+  // (launched with sizeof(TailSmem<F>) + sizeof(SoloSmem) bytes when a step has soloSmem set)
+  SoloSmem&            solo = *reinterpret_cast<SoloSmem*>(smemRaw + ((sizeof(TailSmem<F>) + 15u) & ~size_t(15)));
+  const unsigned char* levelInSmem = nullptr;  // the previous step's last level, if that step left it in shared memory
+  uint32_t             pingPong = 0;
   for(uint32_t s = 1; s < tp.numSteps; ++s)
   {
-    tailRunStep<F, true>(tp.steps[s], sm, tp.tables, 0u, 1u);
+    if(tp.steps[s].soloSmem)
+    {
+      unsigned char* out = solo.out[pingPong];
+      soloGeneralSmem<F>(tp.steps[s], sm.tables, solo, levelInSmem, out);
+      levelInSmem = out;
+      pingPong ^= 1u;
+    }
+    else
+    {
+      tailRunStep<F, true>(tp.steps[s], sm, tp.tables, 0u, 1u);
+      levelInSmem = nullptr;
+    }
     __threadfence_block();
     __syncthreads();  // the reference's inter-dispatch pipeline barrier (one CTA: a CTA barrier suffices)
   }
