@@ -12,6 +12,11 @@
 //   2. MyRgba32f  -- the sRGBA8 preamble's reduce functions (srgba8_mipmap_preamble.glsl:24-25,:35,:37-38) on
 //                    float4 texels, written as a user set: must reproduce the library's own RGBA32F instance
 //                    (nvpyrDispatchEx) bit for bit.
+//   3. MinFirst   -- DepthMax with its own NVPRO_PYRAMID_LOAD_REDUCE4 (nvpro_pyramid.glsl:78-88): the hook returns the
+//                    MINIMUM of the 2x2 square, so its effect is visible -- the first level of every fast dispatch
+//                    must hold minima, every other level maxima, and a chain without the fast pipeline none at all
+//                    (the general pipeline never expands the macro).  Checked against a CPU loop that follows the
+//                    plan, for one-dispatch images, multi-dispatch images and M = 1 steps.
 //
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -std=c++17 -I include examples/custom_functors.cu
 //             -L vk_compute_mipmaps_b200 -lnvpyr -o examples/custom_functors
@@ -34,6 +39,24 @@ struct DepthMax : nvpyr::PyramidFunctors<DepthMax>
   __device__ static Value load(const Params*, const void* t) { return *static_cast<const float*>(t); }
   __device__ static void  store(const Params* p, void* t, Value v) { *static_cast<float*>(t) = fminf(v, p->clampMax); }
   __device__ static Value reduce(float, Value v0, float, Value v1, float, Value v2) { return fmaxf(v0, fmaxf(v1, v2)); }
+};
+
+struct MinFirst : nvpyr::PyramidFunctors<MinFirst>
+{
+  using Value                      = float;
+  static constexpr int kTexelBytes = 4;
+  __device__ static Value load(const Params*, const void* t) { return *static_cast<const float*>(t); }
+  __device__ static void  store(const Params*, void* t, Value v) { *static_cast<float*>(t) = v; }
+  __device__ static Value reduce(float, Value v0, float, Value v1, float, Value v2) { return fmaxf(v0, fmaxf(v1, v2)); }
+  // NVPRO_PYRAMID_LOAD_REDUCE4(srcCoord, srcLevel, out_); checks the coordinates it is given against the address
+  __device__ static Value loadReduce4(const Params*, const void* texel00, size_t pitch, uint32_t x, uint32_t y, uint32_t level)
+  {
+    const unsigned char* t = static_cast<const unsigned char*>(texel00);
+    const float a = *reinterpret_cast<const float*>(t), b = *reinterpret_cast<const float*>(t + 4);
+    const float c = *reinterpret_cast<const float*>(t + pitch), d = *reinterpret_cast<const float*>(t + pitch + 4);
+    const bool  coordsOk = (x & 1u) == 0u && (y & 1u) == 0u && level < 32u;
+    return coordsOk ? fminf(fminf(a, b), fminf(c, d)) : -1.0f;
+  }
 };
 
 struct MyRgba32f : nvpyr::PyramidFunctors<MyRgba32f>
@@ -168,6 +191,73 @@ static void checkDepth(uint32_t w, uint32_t h, const char* what, uint32_t flags,
   cudaFree(params);
 }
 
+// MinFirst against a CPU loop that follows the plan: level l + 1 holds 2x2 minima when it is the first level of a
+// fast dispatch, footprint maxima otherwise.
+static void checkMinFirst(uint32_t w, uint32_t h, const char* what, uint32_t flags, uint32_t div, uint32_t maxLevels)
+{
+  const uint32_t     levels = nvpyr::levelCountFor(w, h);
+  std::vector<float> chain(size_t(w) * h);
+  uint32_t           s = 4242u + w * 17u + h;
+  for(float& v : chain)
+  {
+    s = s * 1664525u + 1013904223u;
+    v = float(s >> 8) * (1.0f / 16777216.0f);
+  }
+  const size_t       l0Texels = chain.size();
+  nvpyrPlanStep      steps[NVPYR_MAX_STEPS];
+  nvpyr::dispatcher_t fast = (flags & NVPYR_FLAG_FORCE_GENERAL) ? nullptr : nvpyr::selectFastDispatcher(div, maxLevels);
+  const int           n    = nvpyr::buildPlan(w, h, levels, nvpyr::defaultGeneralDispatcher, fast, steps, NVPYR_MAX_STEPS);
+  std::vector<bool>   minLevel(levels + 1, false);  // minLevel[l]: level l is the first output of a fast dispatch
+  size_t              hooks = 0;
+  for(int i = 0; i < n; ++i)
+    if(steps[i].pipeline == 1)
+      minLevel[steps[i].inputLevel + 1] = true, ++hooks;
+  size_t src = 0;
+  for(uint32_t l = 0; l + 1 < levels; ++l)
+  {
+    const uint32_t sw = dim(w, l), sh = dim(h, l), dw = dim(w, l + 1), dh = dim(h, l + 1);
+    const int      kx = taps(sw), ky = taps(sh);
+    const size_t   dst = chain.size();
+    chain.resize(dst + size_t(dw) * dh);
+    for(uint32_t y = 0; y < dh; ++y)
+      for(uint32_t x = 0; x < dw; ++x)
+      {
+        float m = minLevel[l + 1] ? INFINITY : -INFINITY;
+        for(int j = 0; j < ky; ++j)
+          for(int i = 0; i < kx; ++i)
+          {
+            const float v = chain[src + size_t(2 * y + j) * sw + (2 * x + i)];
+            m             = minLevel[l + 1] ? fminf(m, v) : fmaxf(m, v);
+          }
+        chain[dst + size_t(y) * dw + x] = m;
+      }
+    src = dst;
+  }
+  float* dev = nullptr;
+  CK(cudaMalloc(&dev, chain.size() * 4));
+  CK(cudaMemset(dev, 0xFF, chain.size() * 4));
+  CK(cudaMemcpy(dev, chain.data(), l0Texels * 4, cudaMemcpyHostToDevice));
+  nvpyrDispatchDesc d;
+  memset(&d, 0, sizeof(d));
+  d.structSize       = sizeof(d);
+  d.flags            = flags;
+  d.extent           = {w, h};
+  d.base             = dev;
+  d.fastDivisibility = div;
+  d.fastMaxLevels    = maxLevels;
+  const nvpyrStatus st = nvpyr::dispatch<MinFirst>(d);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> got(chain.size());
+  CK(cudaMemcpy(got.data(), dev, got.size() * 4, cudaMemcpyDeviceToHost));
+  size_t bad = 0;
+  for(size_t i = l0Texels; i < chain.size(); ++i)
+    bad += memcmp(&got[i], &chain[i], 4) != 0;
+  printf("MinFirst  %5ux%-5u %-34s status %d, %zu fast dispatches use the hook, %zu of %zu texels differ\n", w, h, what, int(st),
+         hooks, bad, chain.size() - l0Texels);
+  failures += st != NVPYR_SUCCESS || bad != 0;
+  cudaFree(dev);
+}
+
 static void checkRgba32f(uint32_t w, uint32_t h)
 {
   const uint32_t levels = nvpyr::levelCountFor(w, h);
@@ -244,6 +334,13 @@ int main()
     printf("bad dispatchers: status %d %d %d, %zu texels written -> %s\n", int(a), int(b), int(c), written, ok ? "rejected" : "NOT rejected");
     failures += !ok;
     cudaFree(dev);
+  }
+  const uint32_t msizes[][2] = {{64, 64}, {256, 256}, {1024, 512}, {260, 260}, {2052, 1028}, {2, 2}, {333, 97}};
+  for(const auto& sz : msizes)
+  {
+    checkMinFirst(sz[0], sz[1], "LOAD_REDUCE4 hook, default", 0, 0, 0);
+    checkMinFirst(sz[0], sz[1], "LOAD_REDUCE4 hook, fast <2, 5>", 0, 2, 5);
+    checkMinFirst(sz[0], sz[1], "no fast pipeline: hook unused", NVPYR_FLAG_FORCE_GENERAL, 0, 0);
   }
   const uint32_t fsizes[][2] = {{512, 256}, {255, 129}, {260, 260}, {96, 1000}};
   for(const auto& sz : fsizes)

@@ -36,8 +36,15 @@
  *   S::reduce2(v0, v1)                          default reduce(0.5, v0, 0.5, v1, 0, v1)          (glsl:164-167)
  *   S::reduce4(v00, v01, v10, v11)              default reduce2(reduce2(v00, v01), reduce2(v10, v11)) (:169-177)
  *   S::sharedRound(v)                           SHARED_STORE followed by SHARED_LOAD, default identity (:196-207)
- * Not offered: _LOAD_REDUCE4 (a hardware-bilinear shortcut; the default "4 loads + reduce4", glsl:179-189, is
- * what runs) and _LEVEL_SIZE (level sizes come from the descriptor: max(1, size >> level)).
+ *   S::loadReduce4(params, texel00, rowPitchBytes, x, y, level)
+ *                                               _LOAD_REDUCE4: load the 2x2 square whose upper-left texel is (x, y) of
+ *                                               mip level `level` (its address: texel00) and reduce it.  Fast pipeline
+ *                                               only, first level of every dispatch, exactly where the GLSL template
+ *                                               expands the macro (glsl:78-88); default = the four loads + reduce4 of
+ *                                               glsl:179-189.  A set may fetch through a texture object kept in its
+ *                                               Params here to use the hardware's bilinear filter.
+ * _LEVEL_SIZE has no counterpart: in GLSL it is how the shader learns a size the host scheduler has already assumed
+ * (dispatch.hpp derives every level size from the base size); here the kernels get the same sizes from the descriptor.
  * Value must be trivially copyable and made of 1..16 32-bit words (it travels through warp shuffles and
  * shared memory).  reduce4's argument order tells which neighbours share a bracket; the kernels call it with
  * the reference's per-site pairing (SURVEY.md section 8a note 1).
@@ -80,6 +87,16 @@ struct PyramidFunctors
   __device__ __forceinline__ static V sharedRound(V v)
   {
     return v;
+  }
+  // NVPRO_PYRAMID_LOAD_REDUCE4's default (glsl:179-189): loads (0,0), (0,1), (1,0), (1,1), then reduce4 in that order.
+  template <class P>
+  __device__ __forceinline__ static auto loadReduce4(const P* params, const void* texel00, size_t rowPitchBytes, uint32_t,
+                                                     uint32_t, uint32_t)
+  {
+    const unsigned char* t   = static_cast<const unsigned char*>(texel00);
+    const auto           v00 = S::load(params, t), v01 = S::load(params, t + rowPitchBytes);
+    const auto           v10 = S::load(params, t + S::kTexelBytes), v11 = S::load(params, t + rowPitchBytes + S::kTexelBytes);
+    return S::reduce4(v00, v01, v10, v11);
   }
 };
 
@@ -127,6 +144,11 @@ struct UserSet
   __device__ __forceinline__ static Value reduce2(Value v0, Value v1) { return S::reduce2(v0, v1); }
   __device__ __forceinline__ static Value reduce4(Value a, Value b, Value c, Value d) { return S::reduce4(a, b, c, d); }
   __device__ __forceinline__ static Value sharedRound(Value v) { return S::sharedRound(v); }
+  __device__ __forceinline__ static Value loadReduce4(const Shared& s, const void* texel00, size_t rowPitchBytes, uint32_t x,
+                                                      uint32_t y, uint32_t level)
+  {
+    return S::loadReduce4(s.params, texel00, rowPitchBytes, x, y, level);
+  }
 };
 
 // Blocks per SM of a kernel on the current device (and the opt-in to its dynamic shared memory), looked up once per
@@ -216,8 +238,9 @@ inline nvpyrStatus dispatch(const nvpyrDispatchDesc& desc, const typename S::Par
   uint64_t  off = 0;
   for(uint32_t i = 0; i < levels; ++i)
   {
-    lv[i].w = levelDim(w, i);
-    lv[i].h = levelDim(h, i);
+    lv[i].w     = levelDim(w, i);
+    lv[i].h     = levelDim(h, i);
+    lv[i].level = i;
     if(desc.levels[i] != nullptr)
     {
       lv[i].ptr   = static_cast<unsigned char*>(desc.levels[i]);

@@ -81,7 +81,16 @@ typedef enum nvpyrFlags
   /* The reference's optional SRGB_SHARED build (srgba8_mipmap_preamble.glsl:60-101, demo_app alternative
    * "srgbShared"): values that pass through shared memory inside a dispatch are packed to 8-bit sRGB and unpacked
    * again.  Non-default and lossy; sRGBA8 only; mutually exclusive with F16_SHARED; functor-template kernels. */
-  NVPYR_FLAG_SRGB_SHARED = 1u << 3
+  NVPYR_FLAG_SRGB_SHARED = 1u << 3,
+  /* demo_app's "generalblit" alternative (demo_app/pipeline_alternative.cpp:16, mipmap_pipelines.cpp:350-453): levels
+   * the fast pipeline does not take are filled ONE AT A TIME by a linear-filter blit of the previous level
+   * (vkCmdBlitImage with VK_FILTER_LINEAR, mipmap_pipelines.cpp:418-426) instead of by the general pipeline.  Together
+   * with NVPYR_FLAG_FORCE_GENERAL it is the "blit" alternative (every level blitted).  Cheaper and, on odd sizes, WRONG
+   * in the reference's own words ("may trade correctness for performance"): a blit samples two source texels per axis
+   * whatever the scale, so a 5 -> 2 reduction ignores a fifth of the image.  Vulkan leaves a blit's filtering arithmetic
+   * to the implementation; ours is pinned in DESIGN.md section 4.10 and restated by the oracle.  Not combinable with the
+   * shared-type flags. */
+  NVPYR_FLAG_GENERAL_BLIT = 1u << 4
 } nvpyrFlags;
 
 typedef struct CUstream_st* nvpyrStream; /* == cudaStream_t == CUstream */

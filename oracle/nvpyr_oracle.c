@@ -879,8 +879,48 @@ static void a_general_workgroup(actx* c, uint32_t wg, uint32_t pc)
   }
 }
 
+/* ---- blit fallback -------------------------------------------------------- */
+/* demo_app/mipmap_pipelines.cpp:404-441: when the fast dispatcher declines, ONE level is filled by
+ * vkCmdBlitImage(level -> level + 1, whole extents, VK_FILTER_LINEAR).  Vulkan's rule for a scaled blit: the centre of
+ * destination texel (i, j) maps to source coordinates u = (i + 0.5) * srcW / dstW, v likewise, sampled with an
+ * unnormalised clamp-to-edge linear filter (texels floor(u - 0.5), floor(u - 0.5) + 1; weight of the second =
+ * frac(u - 0.5)).  The precision of that arithmetic is implementation-defined in Vulkan and no Vulkan device exists
+ * here to pin it: PARITY UNPINNED.  What is pinned is OUR contract, restated here: float32,
+ * scale by IEEE division, u = (i + 0.5) * scale - 0.5 in two roundings, lerps through NVPRO_PYRAMID_REDUCE as
+ * reduce(1 - a, p, a, q, 0, q), rows first. */
+static void a_blit_tap(uint32_t i, float scale, uint32_t src_size, int* i0, int* i1, float* a)
+{
+  float u    = ((float)i + 0.5f) * scale;
+  u          = u - 0.5f;
+  float f    = floorf(u);
+  *a         = u - f;
+  int k      = (int)f, last = (int)src_size - 1;
+  *i0        = k < 0 ? 0 : (k > last ? last : k);
+  *i1        = k + 1 < 0 ? 0 : (k + 1 > last ? last : k + 1);
+}
+static void a_blit_level(actx* c, int src_level)
+{
+  const uint32_t sw = c->lw[src_level], sh = c->lh[src_level], dw = c->lw[src_level + 1], dh = c->lh[src_level + 1];
+  const float    sx = (float)sw / (float)dw, sy = (float)sh / (float)dh;
+  for(uint32_t y = 0; y < dh; ++y)
+    for(uint32_t x = 0; x < dw; ++x)
+    {
+      int   x0, x1, y0, y1;
+      float a, b;
+      a_blit_tap(x, sx, sw, &x0, &x1, &a);
+      a_blit_tap(y, sy, sh, &y0, &y1, &b);
+      ivec2 p00 = {x0, y0}, p10 = {x1, y0}, p01 = {x0, y1}, p11 = {x1, y1}, d = {(int)x, (int)y};
+      vec4  t00 = a_load(c, p00, src_level), t10 = a_load(c, p10, src_level);
+      vec4  t01 = a_load(c, p01, src_level), t11 = a_load(c, p11, src_level);
+      float ia = 1.0f - a, ib = 1.0f - b;
+      vec4  top = a_reduce(ia, t00, a, t10, 0.0f, t10), bot = a_reduce(ia, t01, a, t11, 0.0f, t11);
+      a_store(c, d, src_level + 1, a_reduce(ib, top, b, bot, 0.0f, bot));
+    }
+}
+
 /* Whole chain in shader order.  fmt 0: chain = uint8 RGBA; fmt 1: float RGBA.
- * flags bit0: force general pipeline (no fast pipeline available); bit1: F16_SHARED build; bit2: SRGB_SHARED build.
+ * flags bit0: force general pipeline (no fast pipeline available); bit1: F16_SHARED build; bit2: SRGB_SHARED build;
+ * bit3: the blit fallback replaces the general pipeline (demo_app alternatives "generalblit", with bit0 "blit").
  * Returns number of dispatches, <0 on error.  stores_out (optional) receives
  * the number of texel stores executed (coverage accounting). */
 int nvo_shader_chain(int fmt, void* chain, uint32_t w, uint32_t h, uint32_t mip_levels, uint32_t flags,
@@ -893,13 +933,43 @@ int nvo_shader_chain(int fmt, void* chain, uint32_t w, uint32_t h, uint32_t mip_
     mip_levels = nvo_level_count(w, h);
   if(mip_levels > 32)
     return -1;
-  int n = nvo_plan(w, h, mip_levels, !(flags & 1u), fast_div, fast_max_levels, steps, 40);
-  if(n < 0)
-    return n;
   actx c;
   actx_init(&c, fmt, chain, w, h, mip_levels);
   c.shared_f16  = (flags & 2u) != 0;
   c.shared_srgb = (flags & 4u) != 0;
+  if(flags & 8u)
+  {
+    /* the loop of demo_app/mipmap_pipelines.cpp:376-453 */
+    uint32_t level = 0, remaining = mip_levels - 1u, x = w, y = h;
+    int      count = 0;
+    while(remaining != 0u)
+    {
+      uint32_t wg = 0, done = 0;
+      if(!(flags & 1u))
+        done = fast_dispatcher(x, y, remaining, fast_div ? fast_div : 4u, fast_max_levels ? fast_max_levels : 6u, &wg);
+      if(done != 0u)
+      {
+        for(uint32_t g = 0; g < wg; ++g)
+          a_fast_workgroup(&c, g, level << 5 | done);
+      }
+      else
+      {
+        a_blit_level(&c, (int)level);
+        done = 1u;
+      }
+      level += done;
+      remaining -= done;
+      x = (x >> done) ? (x >> done) : 1u;
+      y = (y >> done) ? (y >> done) : 1u;
+      ++count;
+    }
+    if(stores_out)
+      *stores_out = c.stores;
+    return count;
+  }
+  int n = nvo_plan(w, h, mip_levels, !(flags & 1u), fast_div, fast_max_levels, steps, 40);
+  if(n < 0)
+    return n;
   for(int i = 0; i < n; ++i)
   {
     for(uint32_t wg = 0; wg < steps[i].workgroups; ++wg)

@@ -73,13 +73,14 @@ class Oracle:
         return buf
 
     def shader_chain(self, level0, w, h, fmt=0, levels=0, force_general=False, div=4, max_levels=6, f16_shared=False,
-                     srgb_shared=False):
+                     srgb_shared=False, general_blit=False):
         """Oracle A: chain in shader order. Returns (chain, stores).  f16_shared / srgb_shared: the F16_SHARED /
-        SRGB_SHARED builds of the shaders."""
+        SRGB_SHARED builds of the shaders.  general_blit: the demo's blit fallback instead of the general pipeline."""
         buf = self.new_chain(level0, w, h, fmt, levels)
         st = C.c_uint64()
         n = self.lib.nvo_shader_chain(fmt, buf.ctypes.data, w, h, levels,
-                                      (1 if force_general else 0) | (2 if f16_shared else 0) | (4 if srgb_shared else 0),
+                                      (1 if force_general else 0) | (2 if f16_shared else 0) | (4 if srgb_shared else 0)
+                                      | (8 if general_blit else 0),
                                       div, max_levels, C.byref(st))
         assert n >= 0
         return buf, st.value

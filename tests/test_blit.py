@@ -1,0 +1,70 @@
+"""The blit fallback (NVPYR_FLAG_GENERAL_BLIT; demo_app/mipmap_pipelines.cpp:404-441).  CPU tests: the oracle's
+restatement against Vulkan's scaled-blit rule evaluated in exact rational arithmetic, the loop structure, and the
+encode table self-test of the tuned fast kernel (host only)."""
+from fractions import Fraction
+import math
+
+import numpy as np
+import pytest
+
+import _oracle
+
+
+def vulkan_linear_weights(src, dst):
+    """W[d][s]: weight of source texel s in destination texel d along one axis -- vkCmdBlitImage of [0, src) onto
+    [0, dst) with VK_FILTER_LINEAR, unnormalised coordinates, clamp to edge (Vulkan spec, "Image Blits with Scaling"
+    and "Texel Filtering")."""
+    w = np.zeros((dst, src))
+    for d in range(dst):
+        u = (Fraction(2 * d + 1, 2)) * Fraction(src, dst) - Fraction(1, 2)
+        i0 = math.floor(u)
+        a = float(u - i0)
+        w[d][min(max(i0, 0), src - 1)] += 1.0 - a
+        w[d][min(max(i0 + 1, 0), src - 1)] += a
+    return w
+
+
+@pytest.mark.parametrize("size", [(5, 3), (7, 7), (4, 4), (9, 2), (1, 5), (6, 1), (13, 10), (31, 17)])
+def test_oracle_blit_equals_vulkan_rule(oracle, size):
+    """rgba32f (identity load / store): blitting impulses gives the filter weights themselves."""
+    w, h = size
+    dw, dh = max(1, w // 2), max(1, h // 2)
+    wx, wy = vulkan_linear_weights(w, dw), vulkan_linear_weights(h, dh)
+    rng = np.random.default_rng(5)
+    l0 = rng.random((h, w, 4), dtype=np.float32)
+    chain, _ = oracle.shader_chain(l0.reshape(-1), w, h, fmt=1, levels=2, force_general=True, general_blit=True)
+    got = chain[4 * w * h:].reshape(dh, dw, 4).astype(np.float64)
+    want = np.einsum("ys,xt,stc->yxc", wy, wx, l0.astype(np.float64))
+    # float32 coordinates: u < 32 here, so a weight is off by at most ulp(32) = 3.8e-6 (texture units keep far fewer
+    # sub-texel bits)
+    assert np.abs(got - want).max() <= 1e-5, size
+
+
+def test_oracle_blit_loop_structure(oracle):
+    """'generalblit' takes the fast pipeline where the default dispatcher would and blits single levels elsewhere;
+    'blit' blits every level (mipmap_pipelines.cpp:376-453)."""
+    w, h = 260, 260  # fast 2 levels -> 65x65: blits down to 1x1
+    l0 = _oracle.random_level0(w, h, 3)
+    _, stores_gb = oracle.shader_chain(l0, w, h, general_blit=True)
+    _, stores_b = oracle.shader_chain(l0, w, h, general_blit=True, force_general=True)
+    texels = oracle.chain_texels(w, h) - w * h
+    assert stores_b == texels  # one store per texel: no overlapping work groups in a blit
+    assert stores_gb == texels
+    a, _ = oracle.shader_chain(l0, w, h, general_blit=True)
+    d, _ = oracle.shader_chain(l0, w, h)
+    n2 = 4 * (w * h + 130 * 130 + 65 * 65)
+    assert (a[:n2] == d[:n2]).all() and (a[n2:] != d[n2:]).any()  # the two fast levels agree, the rest differs
+
+
+def test_constant_image_stays_constant_under_blit(oracle):
+    for w, h in ((37, 21), (64, 64), (5, 1)):
+        l0 = np.tile(np.array([200, 17, 99, 128], dtype=np.uint8), w * h)
+        chain, _ = oracle.shader_chain(l0, w, h, general_blit=True, force_general=True)
+        assert (chain.reshape(-1, 4) == np.array([200, 17, 99, 128], dtype=np.uint8)).all()
+
+
+def test_fast_kernel_encode_table_exhaustive():
+    """Every float32 pattern the tuned fast kernel can present to its row-table encode (~110 M values) gives the
+    code of the pinned thresholds (host-side arithmetic identical to the kernel's: IEEE add, shift, table, add)."""
+    from vk_compute_mipmaps_b200._lib import lib
+    assert lib.nvpyrSelfTestEncodeTable() == 0

@@ -318,6 +318,34 @@ def test_srgb_shared_variant_bit_exact(nv, cuda, oracle, size):
             gpu_chain(nv, cuda, l0, w, h, flags=nv.FLAG_SRGB_SHARED | nv.FLAG_F16_SHARED)
 
 
+@pytest.mark.parametrize("size", [(256, 256), (1000, 700), (333, 97), (2052, 1028), (5, 5), (1, 37), (1920, 1080), (260, 260)])
+def test_general_blit_variant_bit_exact(nv, cuda, oracle, size):
+    """NVPYR_FLAG_GENERAL_BLIT = demo_app's "generalblit" alternative (pipeline_alternative.cpp:16,
+    mipmap_pipelines.cpp:350-453): levels the fast pipeline does not take are blitted one at a time with a linear
+    filter; with the fast pipeline absent it is the "blit" alternative.  Bit-exact against the oracle's restatement of
+    the same loop and of the pinned blit arithmetic (a Vulkan blit's precision is implementation-defined: that part
+    of the parity is unpinned), for sRGBA8 and rgba32f, through the host round trip, and rejected
+    together with the shared-type flags."""
+    w, h = size
+    for fmt in (0, 1):
+        l0 = _oracle.random_level0(w, h, 31, fmt=fmt)
+        for fg in (False, True):
+            want, _ = oracle.shader_chain(l0, w, h, fmt=fmt, force_general=fg, general_blit=True)
+            got = gpu_chain(nv, cuda, l0, w, h, fmt=fmt, pipelines=nv.PyramidPipelines(format=fmt, fast_pipeline=not fg),
+                            flags=nv.FLAG_GENERAL_BLIT)
+            if fmt == 0:
+                assert_same(got, want, w, h, oracle, f"general blit, force_general={fg}")
+            else:
+                assert (got.view(np.uint32) == want.view(np.uint32)).all(), (size, fg)
+    l0 = _oracle.random_level0(w, h, 31)
+    want, _ = oracle.shader_chain(l0, w, h, general_blit=True)
+    assert (nv.generate_host(l0, w, h, flags=nv.FLAG_GENERAL_BLIT) == want).all()
+    if size == (333, 97):
+        assert (want != oracle.shader_chain(l0, w, h)[0]).any()  # not the general pipeline's result
+        with pytest.raises(nv.NvpyrError):
+            gpu_chain(nv, cuda, l0, w, h, flags=nv.FLAG_GENERAL_BLIT | nv.FLAG_F16_SHARED)
+
+
 def test_partial_level_count(nv, cuda, oracle):
     w, h = 256, 256
     l0 = _oracle.random_level0(w, h, 6)
@@ -518,8 +546,11 @@ def test_user_defined_functor_sets(nv, cuda):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "custom functor sets ok" in r.stdout
-    assert r.stdout.count("0 of") == 36 + 1 + 4, r.stdout
+    assert r.stdout.count("0 of") == 36 + 1 + 4 + 21, r.stdout
     assert "-> rejected" in r.stdout
+    # the set with its own NVPRO_PYRAMID_LOAD_REDUCE4 (glsl:78-88): the hook runs for the first level of every fast
+    # dispatch and nowhere else (minima there, maxima elsewhere, checked against a CPU loop that follows the plan)
+    assert r.stdout.count("MinFirst") == 21 and "2 fast dispatches use the hook, 0 of" in r.stdout
 
 
 @pytest.mark.parametrize("size", [(1024, 512), (333, 201), (1920, 1080)], ids=lambda s: f"{s[0]}x{s[1]}")

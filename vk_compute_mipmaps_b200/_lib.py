@@ -17,6 +17,7 @@ NVPYR_MAX_STEPS = 40
 SUCCESS, ERROR_INVALID_VALUE, ERROR_UNSUPPORTED, ERROR_CUDA, ERROR_OUT_OF_MEMORY, ERROR_IO = range(6)
 FORMAT_SRGBA8, FORMAT_RGBA32F = 0, 1
 FLAG_NONE, FLAG_FORCE_GENERAL, FLAG_PREMULTIPLY_ALPHA, FLAG_F16_SHARED, FLAG_SRGB_SHARED = 0, 1, 2, 4, 8
+FLAG_GENERAL_BLIT = 16
 
 
 class Extent2D(C.Structure):

@@ -823,8 +823,10 @@ nvpyrStatus resolve(const nvpyrDispatchDesc* d, ResolvedDesc& r)
   if(d->format != NVPYR_FORMAT_SRGBA8 && d->format != NVPYR_FORMAT_RGBA32F)
     return NVPYR_ERROR_UNSUPPORTED;
   constexpr uint32_t kSharedFlags = NVPYR_FLAG_F16_SHARED | NVPYR_FLAG_SRGB_SHARED;
-  if(d->flags & ~uint32_t(NVPYR_FLAG_FORCE_GENERAL | NVPYR_FLAG_PREMULTIPLY_ALPHA | kSharedFlags))
+  if(d->flags & ~uint32_t(NVPYR_FLAG_FORCE_GENERAL | NVPYR_FLAG_PREMULTIPLY_ALPHA | kSharedFlags | NVPYR_FLAG_GENERAL_BLIT))
     return NVPYR_ERROR_UNSUPPORTED;
+  if((d->flags & NVPYR_FLAG_GENERAL_BLIT) && (d->flags & kSharedFlags))
+    return NVPYR_ERROR_INVALID_VALUE;  // a blit has no shared-memory carry the shared types could apply to
   if((d->flags & (NVPYR_FLAG_PREMULTIPLY_ALPHA | kSharedFlags)) && d->format != NVPYR_FORMAT_SRGBA8)
     return NVPYR_ERROR_UNSUPPORTED;
   if((d->flags & kSharedFlags) == kSharedFlags)
@@ -839,7 +841,8 @@ nvpyrStatus resolve(const nvpyrDispatchDesc* d, ResolvedDesc& r)
   r.levels                 = d->levelCount == 0 ? maxLevels : d->levelCount;
   if(r.levels > maxLevels || r.levels > NVPYR_MAX_LEVELS)
     return NVPYR_ERROR_INVALID_VALUE;
-  r.fast = nullptr;
+  r.general = (d->flags & NVPYR_FLAG_GENERAL_BLIT) ? DispatcherRef(blitDispatcher) : DispatcherRef(defaultGeneralDispatcher);
+  r.fast    = nullptr;
   if(!(d->flags & NVPYR_FLAG_FORCE_GENERAL))
   {
     r.fast = selectFastDispatcher(d->fastDivisibility, d->fastMaxLevels);
@@ -852,6 +855,7 @@ nvpyrStatus resolve(const nvpyrDispatchDesc* d, ResolvedDesc& r)
     LevelView& v = r.lv[i];
     v.w          = levelDim(r.w, i);
     v.h          = levelDim(r.h, i);
+    v.level      = i;
     if(d->levels[i] != nullptr)
     {
       v.ptr   = static_cast<unsigned char*>(d->levels[i]);
@@ -967,6 +971,22 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
   return NVPYR_SUCCESS;
 }
 
+// One level by a linear-filter blit (NVPYR_FLAG_GENERAL_BLIT).
+template <class F>
+nvpyrStatus launchBlit(DeviceContext& ctx, const LevelView& src, const LevelView& dst, cudaStream_t stream)
+{
+  using TF = typename TailFunctors<F>::type;
+  BlitParams p{src, dst, ctx.tables};
+  const size_t smem = sizeof(typename TF::Shared);
+  int          grid = 1;
+  nvpyrStatus  st   = persistentGrid(blitKernel<TF>, smem, ctx, (uint64_t(dst.w) * dst.h + 255u) / 256u, &grid);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  NVPYR_CUDA(launchKernel(blitKernel<TF>, grid, 256, smem, stream, p));
+  ++g_launchCount;
+  return NVPYR_SUCCESS;
+}
+
 // firstStep > 0: the steps before it have been enqueued by the caller (nvpyrGenerateHost runs step 0
 // band by band).
 // premulFirst: step 0 also premultiplies level 0 on the fly (the caller checked canFusePremultiply).
@@ -978,15 +998,23 @@ nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0
   if(n < 0)
     return NVPYR_ERROR_INVALID_VALUE;
   auto texels = [&](int i) { return uint64_t(steps[i].srcWidth) * steps[i].srcHeight; };
+  const bool blit = (r.flags & NVPYR_FLAG_GENERAL_BLIT) != 0;  // general steps are one-level blits (never fused into a tail)
   for(int i = firstStep; i < n;)
   {
     const nvpyrPlanStep& s = steps[i];
     nvpyrStatus          st;
-    if(!g_noTailFusion && texels(i) <= kTailMaxTexels)
+    if(blit && s.pipeline == 0)
+    {
+      if(s.levelCount != 1)
+        return NVPYR_ERROR_INVALID_VALUE;
+      st = launchBlit<F>(ctx, r.lv[s.inputLevel], r.lv[s.inputLevel + 1], r.stream);
+      ++i;
+    }
+    else if(!g_noTailFusion && texels(i) <= kTailMaxTexels)
     {
       // grid step i, then as many solo steps as follow (level sizes only shrink)
       int count = 1;
-      while(i + count < n && count < int(kMaxTailSteps)
+      while(i + count < n && count < int(kMaxTailSteps) && !(blit && steps[i + count].pipeline == 0)
             && (steps[i + count].pipeline == 1
                     ? texels(i + count) <= kSoloMaxTexelsFast
                     : (std::max(steps[i + count].srcWidth, steps[i + count].srcHeight) <= kSoloMaxEdgeGeneral
@@ -1100,6 +1128,8 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
          || size_t(d.lv[k].ptr - d.lv[0].ptr) != size_t(levelOffsetTexels(d.w, d.h, k)) * 4u)
         return NVPYR_SUCCESS;
   }
+  if(a.flags & NVPYR_FLAG_GENERAL_BLIT)
+    return NVPYR_SUCCESS;  // blitted levels are separate launches: one dispatch per image
   nvpyrPlanStep steps[NVPYR_MAX_STEPS];
   const int     n = buildPlan(a.w, a.h, a.levels, a.general, a.fast, steps, NVPYR_MAX_STEPS);
   if(n < 1)

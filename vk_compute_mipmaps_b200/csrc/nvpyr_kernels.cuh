@@ -20,6 +20,9 @@
 // neighbours share a bracket in 0.25*((a+b)+(c+d)) at each level ("pairing"), so
 // the stored bits are identical to the shader-order oracle.
 #pragma once
+#include <type_traits>
+#include <utility>
+
 #include "nvpyr_functors.cuh"
 
 namespace nvpyr {
@@ -29,6 +32,22 @@ struct LevelView
   unsigned char* ptr;
   uint32_t       pitch;  // bytes
   uint32_t       w, h;
+  uint32_t       level;  // index of the level in its chain (handed to user hooks; the kernels do not use it)
+};
+
+// NVPRO_PYRAMID_LOAD_REDUCE4 (nvpro_pyramid.glsl:78-88, default :179-189): a functor set MAY define
+//   static Value loadReduce4(const Shared&, const void* texel00, size_t rowPitchBytes, uint32_t x, uint32_t y, uint32_t level)
+// = "load the 2x2 square whose upper-left texel is (x, y) of mip level `level` (at texel00) and reduce it".  Like the
+// macro it is used by the fast pipeline only, for the first level of every dispatch, and replaces load + reduce4
+// there (a user set may fetch through a texture object in its Params to use the hardware's bilinear filter).
+template <class F, class = void>
+struct HasLoadReduce4 : std::false_type
+{
+};
+template <class F>
+struct HasLoadReduce4<F, std::void_t<decltype(F::loadReduce4(std::declval<const typename F::Shared&>(), static_cast<const void*>(nullptr),
+                                                             size_t(0), 0u, 0u, 0u))>> : std::true_type
+{
 };
 
 // Pairing of the 2x2 reduction that produces level (input + k) in an M-level fast
@@ -123,23 +142,32 @@ __device__ __forceinline__ void fastTileLoop(const FastParams& p, const typename
         V                    a[4], b[4];
         const unsigned char* r0 = p.lv[0].ptr + size_t(y0 + 2 * qy) * p.lv[0].pitch + size_t(x0) * F::kTexelBytes;
         const unsigned char* r1 = r0 + p.lv[0].pitch;
-        if(kVec)
+        if constexpr(HasLoadReduce4<F>::value && !kVec)
         {
-          F::load4(tables, r0, a);
-          F::load4(tables, r1, b);
+          // the set's own NVPRO_PYRAMID_LOAD_REDUCE4
+          l1[qy][0] = F::loadReduce4(tables, r0, p.lv[0].pitch, x0, y0 + 2 * qy, p.lv[0].level);
+          l1[qy][1] = F::loadReduce4(tables, r0 + 2 * F::kTexelBytes, p.lv[0].pitch, x0 + 2u, y0 + 2 * qy, p.lv[0].level);
         }
         else
         {
-#pragma unroll
-          for(int i = 0; i < 4; ++i)
+          if(kVec)
           {
-            a[i] = F::load(tables, r0 + i * F::kTexelBytes);
-            b[i] = F::load(tables, r1 + i * F::kTexelBytes);
+            F::load4(tables, r0, a);
+            F::load4(tables, r1, b);
           }
+          else
+          {
+#pragma unroll
+            for(int i = 0; i < 4; ++i)
+            {
+              a[i] = F::load(tables, r0 + i * F::kTexelBytes);
+              b[i] = F::load(tables, r1 + i * F::kTexelBytes);
+            }
+          }
+          // level +1: vertical pairing (k = 1)
+          l1[qy][0] = F::reduce4(a[0], b[0], a[1], b[1]);
+          l1[qy][1] = F::reduce4(a[2], b[2], a[3], b[3]);
         }
-        // level +1: vertical pairing (k = 1)
-        l1[qy][0] = F::reduce4(a[0], b[0], a[1], b[1]);
-        l1[qy][1] = F::reduce4(a[2], b[2], a[3], b[3]);
         unsigned char* d = p.lv[1].ptr + size_t((y0 >> 1) + qy) * p.lv[1].pitch + size_t(x0 >> 1) * F::kTexelBytes;
         if(kVec)
           F::template store2<false>(tables, d, l1[qy][0], l1[qy][1]);
@@ -240,10 +268,16 @@ __device__ __forceinline__ void fastLoop1(const FastParams& p, const typename F:
   {
     const uint32_t       x = uint32_t(g % W1), y = uint32_t(g / W1);
     const unsigned char* s = p.lv[0].ptr + size_t(2 * y) * p.lv[0].pitch + size_t(2 * x) * F::kTexelBytes;
-    const V ul = F::load(tables, s), ur = F::load(tables, s + F::kTexelBytes);
-    const V ll = F::load(tables, s + p.lv[0].pitch), lr = F::load(tables, s + p.lv[0].pitch + F::kTexelBytes);
-    F::template store<false>(tables, p.lv[1].ptr + size_t(y) * p.lv[1].pitch + size_t(x) * F::kTexelBytes,
-                             F::reduce4(ul, ll, ur, lr));
+    V out;
+    if constexpr(HasLoadReduce4<F>::value)
+      out = F::loadReduce4(tables, s, p.lv[0].pitch, 2u * x, 2u * y, p.lv[0].level);
+    else
+    {
+      const V ul = F::load(tables, s), ur = F::load(tables, s + F::kTexelBytes);
+      const V ll = F::load(tables, s + p.lv[0].pitch), lr = F::load(tables, s + p.lv[0].pitch + F::kTexelBytes);
+      out        = F::reduce4(ul, ll, ur, lr);
+    }
+    F::template store<false>(tables, p.lv[1].ptr + size_t(y) * p.lv[1].pitch + size_t(x) * F::kTexelBytes, out);
   }
 }
 
@@ -699,6 +733,59 @@ __global__ void __launch_bounds__(kTailThreads) tailBatchKernel(const __grid_con
       __threadfence_block();
       __syncthreads();  // the reference's inter-dispatch pipeline barrier
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Linear-filter blit of one level into the next (NVPYR_FLAG_GENERAL_BLIT; demo_app/mipmap_pipelines.cpp:418-426:
+// vkCmdBlitImage(level -> level + 1, whole extents, VK_FILTER_LINEAR)).  Vulkan's blit rule: the centre of destination
+// texel (i, j) maps to source coordinates ((i + 0.5) * srcW / dstW, (j + 0.5) * srcH / dstH), which are sampled with
+// an unnormalised, clamp-to-edge linear filter: texels floor(u - 0.5) and floor(u - 0.5) + 1 with weights (1 - a, a),
+// a = frac(u - 0.5).  Arithmetic pinned here (Vulkan leaves it implementation-defined): float32; scale = srcW / dstW
+// (IEEE division); u = (i + 0.5) * scale - 0.5 (two roundings); the three lerps go through the functor set's own
+// REDUCE as reduce(1 - a, p, a, q, 0, q): horizontally in both rows, then vertically -- so the blit works for any
+// functor set and an sRGB image is filtered in linear space, like a texture unit does it.
+struct BlitParams
+{
+  LevelView           src, dst;
+  const DeviceTables* tables;
+};
+__device__ __forceinline__ void blitTap(uint32_t i, float scale, uint32_t srcSize, uint32_t& i0, uint32_t& i1, float& a)
+{
+  const float u = __fsub_rn(__fmul_rn(__fadd_rn(float(i), 0.5f), scale), 0.5f);
+  const float f = floorf(u);
+  a             = __fsub_rn(u, f);
+  const int   k = int(f), last = int(srcSize) - 1;
+  i0            = uint32_t(min(max(k, 0), last));
+  i1            = uint32_t(min(max(k + 1, 0), last));
+}
+template <class F>
+__global__ void __launch_bounds__(256) blitKernel(const BlitParams p)
+{
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  typename F::Shared& tables = *reinterpret_cast<typename F::Shared*>(smemRaw);
+  F::sharedInit(tables, p.tables);
+  __syncthreads();
+  gridDependencyWait();
+  gridLaunchDependents();
+  using V                = typename F::Value;
+  constexpr uint32_t TB  = F::kTexelBytes;
+  const float        sx  = __fdiv_rn(float(p.src.w), float(p.dst.w)), sy = __fdiv_rn(float(p.src.h), float(p.dst.h));
+  const uint64_t     n   = uint64_t(p.dst.w) * p.dst.h;
+  for(uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += uint64_t(gridDim.x) * blockDim.x)
+  {
+    const uint32_t y = uint32_t(t / p.dst.w), x = uint32_t(t - uint64_t(y) * p.dst.w);
+    uint32_t       x0, x1, y0, y1;
+    float          a, b;
+    blitTap(x, sx, p.src.w, x0, x1, a);
+    blitTap(y, sy, p.src.h, y0, y1, b);
+    const unsigned char* r0  = p.src.ptr + size_t(y0) * p.src.pitch;
+    const unsigned char* r1  = p.src.ptr + size_t(y1) * p.src.pitch;
+    const V              t00 = F::load(tables, r0 + size_t(x0) * TB), t10 = F::load(tables, r0 + size_t(x1) * TB);
+    const V              t01 = F::load(tables, r1 + size_t(x0) * TB), t11 = F::load(tables, r1 + size_t(x1) * TB);
+    const float          ia = __fsub_rn(1.0f, a), ib = __fsub_rn(1.0f, b);
+    const V              top = F::reduce(ia, t00, a, t10, 0.0f, t10), bot = F::reduce(ia, t01, a, t11, 0.0f, t11);
+    F::template store<true>(tables, p.dst.ptr + size_t(y) * p.dst.pitch + size_t(x) * TB, F::reduce(ib, top, b, bot, 0.0f, bot));
   }
 }
 

@@ -83,6 +83,15 @@ inline uint32_t defaultGeneralDispatcher(const PyramidState& s, nvpyrPlanStep& s
   return n;
 }
 
+// The blit fallback of demo_app/mipmap_pipelines.cpp:404-441 as a "general dispatcher": one level per step, no compute
+// dispatch (workgroups 0); the step is executed by a blit of level currentLevel into currentLevel + 1.
+inline uint32_t blitDispatcher(const PyramidState& s, nvpyrPlanStep& step)
+{
+  step.workgroups   = 0;
+  step.pushConstant = s.currentLevel << 5 | 1u;
+  return 1;
+}
+
 // Equivalent of the 7-argument nvproCmdPyramidDispatch (dispatch.hpp:109-188)
 // with "record" replaced by "append to steps[]".  fast == nullptr means the fast
 // pipeline is unavailable.  Returns the number of steps, or -1 on overflow / bad

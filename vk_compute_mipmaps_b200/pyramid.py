@@ -16,14 +16,14 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import (FLAG_F16_SHARED, FLAG_SRGB_SHARED, FLAG_FORCE_GENERAL, FLAG_NONE, FLAG_PREMULTIPLY_ALPHA, FORMAT_RGBA32F, FORMAT_SRGBA8, Dispatcher,
+from ._lib import (FLAG_F16_SHARED, FLAG_SRGB_SHARED, FLAG_GENERAL_BLIT, FLAG_FORCE_GENERAL, FLAG_NONE, FLAG_PREMULTIPLY_ALPHA, FORMAT_RGBA32F, FORMAT_SRGBA8, Dispatcher,
                    DispatchDesc, Extent2D, NvpyrError, PlanOptions, PlanStep, check, lib)
 
 __all__ = [
     "PyramidPipelines", "cmd_pyramid_dispatch", "dispatch_batch", "level_count", "level_extent", "level_offset_texels",
     "chain_bytes", "chain_texels", "get_plan", "generate_host", "premultiply_alpha", "level_views", "launch_count", "init",
     "write_tga", "level_filename", "write_mipmaps_tga", "read_image",
-    "FORMAT_SRGBA8", "FORMAT_RGBA32F", "FLAG_NONE", "FLAG_FORCE_GENERAL", "FLAG_PREMULTIPLY_ALPHA", "FLAG_F16_SHARED", "FLAG_SRGB_SHARED", "NvpyrError",
+    "FORMAT_SRGBA8", "FORMAT_RGBA32F", "FLAG_NONE", "FLAG_FORCE_GENERAL", "FLAG_PREMULTIPLY_ALPHA", "FLAG_F16_SHARED", "FLAG_SRGB_SHARED", "FLAG_GENERAL_BLIT", "NvpyrError",
 ]
 
 
