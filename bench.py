@@ -560,7 +560,7 @@ def run_gpu_arm(args):
                    "batch_of_4096": batch},
         "inputs": {n: dict(v, description=described[n]) for n, v in per_input.items()},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "fastSrgba8Kernel<6> (TMA-staged level-0 slabs; level 0 -> levels 1..6)",
+                     "traffic": traffic, "kernel": "fastSrgba8Kernel<6> (TMA-staged level-0 slabs, lane-private decode and encode tables; level 0 -> levels 1..6)",
                      "input": worst, "algorithmic_bytes_per_launch": k_bytes, "us_per_launch": per_input[worst]["kernel_us"],
                      "per_launch": per_input[worst]["kernel_per_launch"], "peak_source": peak_src,
                      "per_input": {n: {"us_per_launch": v["kernel_us"], "frac": v["kernel_frac_of_hbm_peak"]}

@@ -346,6 +346,25 @@ def test_general_blit_variant_bit_exact(nv, cuda, oracle, size):
             gpu_chain(nv, cuda, l0, w, h, flags=nv.FLAG_GENERAL_BLIT | nv.FLAG_F16_SHARED)
 
 
+def test_slab_task_handoff_stress(nv, cuda):
+    """The slab-task mode hands a tile's level +3 sums from the warps that produce them to the warp that arrives last
+    through shared memory ordered by fences and a shared atomic (no barrier), and recycles stash slots through a
+    generation counter -- orderings compute-sanitizer's racecheck cannot model.  Evidence instead: thousands of chains
+    on varied sizes, in a process where the mode is forced onto every size (up to 8192^2: 110 tiles and four slot
+    generations per CTA), every repetition equal to the first, and the first equal to what a tile-mode process
+    (no hand-off at all) produces."""
+    import subprocess, sys
+    tool = os.path.join(_oracle.ROOT, "tools", "stress_slab.py")
+    outs = {}
+    for name, env in (("slab", {"NVPYR_SLAB_MAX_TILES_PER_WARP_X100": "1000000"}), ("tile", {"NVPYR_NO_SLAB_TASKS": "1"})):
+        r = subprocess.run([sys.executable, tool, "--reps", "400" if name == "slab" else "8"], capture_output=True, text=True,
+                           timeout=900, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[name] = {l.split()[0]: l.split()[-1] for l in r.stdout.strip().splitlines()}
+        assert all(" differing 0 " in l for l in r.stdout.strip().splitlines()), r.stdout
+    assert len(outs["slab"]) == 7 and outs["slab"] == outs["tile"], outs
+
+
 def test_partial_level_count(nv, cuda, oracle):
     w, h = 256, 256
     l0 = _oracle.random_level0(w, h, 6)
