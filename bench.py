@@ -277,11 +277,37 @@ def fill_gradient(level0, w, h):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def _cpulist(text):
+    cpus = []
+    for part in text.strip().split(","):
+        if part:
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
 def bind_to_gpu_numa_node(torch, local):
-    """Pin this rank's host threads to the CPUs next to its GPU (NVML's affinity mask) BEFORE any pinned host
-    memory is allocated, so that the staging buffers of the end-to-end leg live on the GPU's own NUMA node: with
-    one process per GPU the host side of the round trip otherwise crosses the socket interconnect for half of the
-    ranks.  Best effort: returns the number of CPUs bound to, or 0."""
+    """Pin this rank's host threads to the CPUs next to its GPU BEFORE any pinned host memory is allocated, so that
+    the staging buffers of the end-to-end leg live on the GPU's own NUMA node (first touch): with one process per
+    GPU the host side of the round trip otherwise crosses the socket interconnect for half of the ranks.  The node
+    is taken from sysfs (/sys/bus/pci/devices/<bus id>/numa_node -> /sys/devices/system/node/nodeN/cpulist) and, where
+    sysfs has no answer (-1: a VM without NUMA topology), from NVML's affinity mask.  Best effort: returns
+    {"cpus": how many CPUs the rank is bound to, "node": sysfs node or None, "source": ...}."""
+    info = {"cpus": 0, "node": None, "source": None}
+    allowed = set(os.sched_getaffinity(0))
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        info["node"] = node
+        if node >= 0:
+            cpus = [c for c in _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) if c in allowed]
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info.update(cpus=len(cpus), source="sysfs")
+                return info
+    except Exception:
+        pass
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -289,13 +315,13 @@ def bind_to_gpu_numa_node(torch, local):
         h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
         cpus = [64 * i + b for i, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
-        allowed = set(os.sched_getaffinity(0))
         cpus = [c for c in cpus if c in allowed]
         if cpus:
             os.sched_setaffinity(0, cpus)
-        return len(cpus)
+            info.update(cpus=len(cpus), source="nvml")
     except Exception:
-        return 0
+        pass
+    return info
 
 
 # Checksum of the 512 per-texture checksums of BASELINE configs[4] (texture k = uniform random bytes from seed
@@ -318,7 +344,7 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa_cpus = bind_to_gpu_numa_node(torch, local)
+    numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -501,7 +527,8 @@ def run_gpu_arm(args):
         t_h2d = timed(h2d_only)
         e2e = {"value": world * chain_bytes / t_inplace / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": l0_bytes, "d2h_bytes_per_step": chain_bytes - l0_bytes, "steps": e_steps,
-               "ms_per_step": 1e3 * t_inplace, "host_cpus_bound_to_gpu_numa_node": numa_cpus,
+               "ms_per_step": 1e3 * t_inplace, "host_cpus_bound_to_gpu_numa_node": numa["cpus"],
+               "gpu_numa_node_sysfs": numa["node"], "numa_binding_source": numa["source"],
                "api": "nvpyrGenerateHost in place on one pinned host chain (level 0 filled -> levels 1..14 filled), "
                       "upload / kernels / download overlapped in 32 MB bands",
                "separate_buffers": {"value": world * chain_bytes / t_separate / 1e9, "unit": UNIT,
