@@ -2,13 +2,15 @@
 # compute-sanitizer over a small but representative set of dispatches (all kernels, all schedule classes).
 # usage (GPU box): tools/sanitize.sh [memcheck|racecheck|initcheck|synccheck]
 TOOL=${1:-memcheck}
+SLAB=${2:-25}   # second argument 1000000: slab tasks (and stash-slot recycling) on every size in the second pass
 cat > /tmp/san_driver.py <<'PY'
 import sys, numpy as np, torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import vk_compute_mipmaps_b200 as nv, _oracle
 o = _oracle.load_oracle()
 cases = [(256, 256, 0, False), (1024, 512, 0, False), (255, 255, 0, False), (260, 260, 0, False), (136, 512, 0, False),
-         (777, 1031, 0, False), (1200, 900, 0, False), (64, 64, 1, False), (100, 37, 1, False), (96, 160, 0, True)]
+         (777, 1031, 0, False), (1200, 900, 0, False), (64, 64, 1, False), (100, 37, 1, False), (96, 160, 0, True),
+         (2560, 2048, 0, False)]  # the last one: 1280 tiles = the TMA-staged tile mode of the fast kernel
 for (w, h, fmt, fg) in cases:
     l0 = _oracle.random_level0(w, h, 5, fmt=fmt)
     dt = torch.uint8 if fmt == 0 else torch.float32
@@ -35,13 +37,21 @@ for (w, h) in [(1024, 768), (1023, 300)]:
     nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(), w, h, image=b, flags=nv.FLAG_PREMULTIPLY_ALPHA)
     torch.cuda.synchronize()
     assert (b.cpu().numpy() == o.shader_chain(o.premultiply(l0), w, h)[0]).all(), ('premultiply', w, h)
+for (w, h, fmt) in [(333, 97, 0), (260, 260, 0), (100, 37, 1)]:  # the blit fallback (NVPYR_FLAG_GENERAL_BLIT)
+    l0 = _oracle.random_level0(w, h, 70, fmt=fmt)
+    dt = torch.uint8 if fmt == 0 else torch.float32
+    b = torch.zeros(nv.chain_bytes(w, h, 0, fmt) // (1 if fmt == 0 else 4), dtype=dt, device='cuda'); b[:4 * w * h] = torch.from_numpy(l0).cuda()
+    nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(format=fmt), w, h, image=b, flags=nv.FLAG_GENERAL_BLIT)
+    torch.cuda.synchronize()
+    assert (b.cpu().numpy().view(np.uint8) == o.shader_chain(l0, w, h, fmt=fmt, general_blit=True)[0].view(np.uint8)).all(), ('blit', w, h)
 w, h = 512, 1088
 l0 = _oracle.random_level0(w, h, 60)
 assert (nv.generate_host(l0, w, h) == o.shader_chain(l0, w, h)[0]).all(), 'host pipeline'
 print('sanitize driver ok')
 PY
 for tail in 262144 0; do
-  echo "== $TOOL NVPYR_TAIL_MAX_TEXELS=$tail"
+  echo "== $TOOL NVPYR_TAIL_MAX_TEXELS=$tail (second pass: 24-warp build of the fast kernel, slab tasks forced onto every size)"
+  [ $tail = 0 ] && export NVPYR_FAST_WARPS_LARGE=24 NVPYR_SLAB_MAX_TILES_PER_WARP_X100=$SLAB
   NVPYR_HOST_BAND_BYTES=131072 NVPYR_TAIL_MAX_TEXELS=$tail compute-sanitizer --tool $TOOL --kernel-regex kns=nvpyr --print-limit 20 python /tmp/san_driver.py 2>&1 | tail -6
 done
 echo "== $TOOL examples/custom_functors (user-defined functor sets through include/nvpyr.cuh)"

@@ -506,10 +506,16 @@ const bool g_noLargeWarps = [] {
   const char* e = getenv("NVPYR_FAST_WARPS_LARGE");
   return e != nullptr && atoi(e) == 32;
 }();
+const bool g_alwaysLargeWarps = [] {  // NVPYR_FAST_WARPS_LARGE=24: the 24-warp build for every tile-mode launch (tests, sanitizer)
+  const char* e = getenv("NVPYR_FAST_WARPS_LARGE");
+  return e != nullptr && atoi(e) == kFastWarpsLarge;
+}();
 inline bool preferFewerWarps(const DeviceContext& ctx, uint64_t tiles)
 {
   if(g_noLargeWarps)
     return false;
+  if(g_alwaysLargeWarps)
+    return true;
   const uint64_t r32 = (tiles + uint64_t(ctx.smCount) * kFastWarps - 1) / (uint64_t(ctx.smCount) * kFastWarps);
   const uint64_t r24 = (tiles + uint64_t(ctx.smCount) * kFastWarpsLarge - 1) / (uint64_t(ctx.smCount) * kFastWarpsLarge);
   return r24 * 128u < r32 * 181u;

@@ -721,8 +721,9 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
     }
   };
   // TMA variant: this warp's staging buffer, its mbarrier and the phase the next wait expects
-  // (slab tasks keep the register path: measured with TMA staging, round 2, 2048^2 12.2 -> 15.5 us -- a warp runs one
-  // or two tasks there and the first copy of a CTA pays the tensor-map fetch on top of the DRAM latency)
+  // (slab tasks keep the register path: a warp runs one or two tasks there, so there is little to overlap, and the
+  // first copy of a CTA would pay the tensor-map fetch on top of the DRAM latency; TMA staging brought no gain outside
+  // the box-to-box noise of the 2048^2 config when tried in round 2)
   constexpr bool kTma = kFastTma && !kBatch && !kPremul && !kSlabTasks;
   uint32_t       tmaBar = 0u, tmaRing = 0u, tmaPhase = 0u;
   // Issues the row copies of slab s of tile t (rows cut at the image edges; nothing for a tile that does not exist).
@@ -797,7 +798,7 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
       myL3 = stashOf(sm, slot);
       // the slot's previous tile (local tile - kSlots) must have been finished before its stash is overwritten
       if(lane == 0u)
-        while(*reinterpret_cast<volatile uint32_t*>(&slotGeneration[slot]) != generation)
+        while(atomicAdd(&slotGeneration[slot], 0u) != generation)  // (an atomic read: the flag is written atomically too)
           ;
       __syncwarp();
     }
@@ -998,9 +999,9 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
       if(kSlabTasks && lane == 0u)
       {
         // hand the slot to local tile + kSlots: counter back to zero, then the generation (in this order)
-        tileArrivals[slot] = 0u;
+        atomicExch(&tileArrivals[slot], 0u);
         __threadfence_block();
-        *reinterpret_cast<volatile uint32_t*>(&slotGeneration[slot]) = generation + 1u;
+        atomicExch(&slotGeneration[slot], generation + 1u);
       }
     }
     // next unit of work
