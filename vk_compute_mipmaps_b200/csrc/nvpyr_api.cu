@@ -132,10 +132,10 @@ bool buildRowEncodeTable(uint32_t* out)
   const uint32_t* thr       = NVPYR_SRGB_ENCODE_THRESHOLD_BITS;
   const uint32_t  floorBits = rowEncFloorBits();
   if(rowOfBits(0u) != 0u || rowOfBits(floorBits) < 1u || rowOfBits(kEncMinBits) < 1u || floorBits > kEncMinBits
-     || rowOfBits(kEncMaxBits) != kRowEncRows - 1u)
+     || rowOfBits(kEncMaxBits) != kRowEncRows - 2u || rowOfBits(kRowEncTopBits) != kRowEncRows - 1u)
     return false;
   auto firstOfRow = [](uint32_t row) {  // rowOfBits is monotone over the non-negative floats
-    uint32_t lo = 0u, hi = kEncMaxBits + 1u;
+    uint32_t lo = 0u, hi = kRowEncTopBits + 1u;
     while(lo < hi)
     {
       const uint32_t mid = lo + (hi - lo) / 2u;
@@ -197,7 +197,7 @@ uint64_t checkRowEncodeTable()
   const uint32_t* thr  = NVPYR_SRGB_ENCODE_THRESHOLD_BITS;
   uint64_t        bad  = ((rows[0] + kRowEncZeroBits) >> 24) != 0u;
   uint32_t        code = 0;
-  for(uint32_t x = rowEncFloorBits(); x <= kEncMaxBits; ++x)
+  for(uint32_t x = rowEncFloorBits(); x <= kRowEncTopBits; ++x)
   {
     while(code < 255u && thr[code] <= x)
       ++code;

@@ -69,6 +69,7 @@ constexpr uint32_t kFastEncEntriesPadded = (kFastEncEntries + 3u) & ~3u;
 //     z = RN(x + kRowEncC),   row = (bits(z) >> 16) - kRowEncFirstKey        (sign/exponent + 7 mantissa bits of z)
 // instead of from x itself.  Adding the constant compresses the twelve low octaves of x, where the sRGB thresholds
 // are far apart, into the linear part of z's first octave, so 645 rows cover [0, 1] where keys on x need 1665 --
+// (646 with the row that takes the general pipeline's sums just above 1) --
 // few enough rows to give EVERY LANE ITS OWN COPY of every entry (a row = 32 lanes x 4 bytes): a warp-wide
 // look-up is one conflict-free wavefront whatever the data.  RN(x + c) is monotone in x, so a row is an interval
 // of x; it holds at most one threshold and spans less than 2^24 float patterns (checked when the table is built),
@@ -78,7 +79,8 @@ constexpr uint32_t kFastEncEntriesPadded = (kFastEncEntries + 3u) & ~3u;
 // entry is made for the bit pattern the kernel presents for a zero of level +1, the only level encoded unclamped).
 constexpr uint32_t kRowEncCBits    = 0x3CFF8000u;  // 1/32 - 2^-14
 constexpr uint32_t kRowEncFirstKey = kRowEncCBits >> 16;
-constexpr uint32_t kRowEncRows     = 645;          // keys 0x3CFF (x = 0) .. 0x3F83 (x = 1)
+constexpr uint32_t kRowEncTopBits  = 0x3F810000u;  // 1 + 2^-7: the general pipeline's weighted sums may exceed 1 by a few ulp
+constexpr uint32_t kRowEncRows     = 646;          // keys 0x3CFF (x = 0) .. 0x3F83 (x = 1), 0x3F84 (x up to kRowEncTopBits)
 constexpr int      kFastDecScaleExp = 100;         // the tuned fast kernel carries 2^-100 * 4^K * x
 constexpr uint32_t kRowEncZeroBits = uint32_t(kFastDecScaleExp - 2) << 23;  // what bits(0) + kAdd<1> presents
 

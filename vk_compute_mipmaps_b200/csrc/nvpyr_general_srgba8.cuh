@@ -58,7 +58,21 @@ constexpr uint32_t kGenEncodeMask = 0x10000u - kGenEncStride;
 constexpr uint32_t kGenEncodeAddr = (kGenEncMinKey * kGenEncStride) & kGenEncodeMask;  // window address of the first entry
 static_assert(((kGenEncMaxKey * kGenEncStride) & kGenEncodeMask) == kGenEncodeAddr + (kGenEncMaxKey - kGenEncMinKey) * kGenEncStride,
               "the key range must not wrap inside the 16-bit window");
-constexpr uint32_t kGenSmemBytes  = kGenDecodeAddr + 256u * 256u - kGenWindowBase;
+// NVPYR_GEN_ENC_ROWS = 1 (default, round 2): the strip kernels use the fast kernel's row table (nvpyr_functors.cuh):
+// ONE table of kRowEncRows rows x 256 bytes at window address 0x10000 -- bytes 0..127 of row r = the 32 lane copies of
+// linearFromSrgb(r) (r < 256), bytes 128..255 = the 32 lane copies of encode entry r -- so that the encode look-up is
+// as conflict-free as the decode (ncu, round 2: 31 % of the four-column kernel's shared-load wavefronts were bank
+// conflicts of the single-copy encode table).  Look-up: FADD (z = x + c), PRMT (key(z) << 8 | lane << 2), LDS with an
+// immediate that folds the table's window address, IADD.  The staging ring of the four-column kernel moves below the
+// table (3 stages per warp: 48 KB between the window base and 0x10000).
+#ifndef NVPYR_GEN_ENC_ROWS
+#define NVPYR_GEN_ENC_ROWS 1
+#endif
+constexpr bool     kGenRows       = NVPYR_GEN_ENC_ROWS != 0;
+constexpr uint32_t kGenRowsEnd    = kGenDecodeAddr + kRowEncRows * 256u;  // window address behind the row table
+constexpr int32_t  kGenRowEncImm  = int32_t(kGenDecodeAddr + 128u) - int32_t(kRowEncFirstKey << 8);  // LDS immediate of the encode look-up
+constexpr uint32_t kGenSmemBytes  = (kGenRows ? kGenRowsEnd : kGenDecodeAddr + 256u * 256u) - kGenWindowBase;
+static_assert(kGenRowsEnd <= kGenWindowBase + 227u * 1024u, "row table must end inside the largest dynamic window");
 static_assert(kGenEncodeAddr >= kGenWindowBase && kGenEncodeAddr + kGenEncEntries * kGenEncStride <= kGenDecodeAddr,
               "encode table must fit below the decode table");
 static_assert(kGenEncodeAddr % 16u == 0, "encode table is copied as uint4");
@@ -80,6 +94,23 @@ constexpr int kGenWarps = NVPYR_GEN_WARPS;  // one CTA of 24 warps per SM (80 re
 template <int kThreads = kGenWarps * 32>
 __device__ __forceinline__ void genSrgba8Init(unsigned char* smemRaw, const DeviceTables* t)
 {
+  if(kGenRows)
+  {
+    // thread -> (row, 16-byte column): eight consecutive threads write the 128 contiguous bytes of one half row
+    uint4* tab = reinterpret_cast<uint4*>(smemRaw + (kGenDecodeAddr - kGenWindowBase));  // 16 uint4 per row
+    for(uint32_t i = threadIdx.x; i < kRowEncRows * 8u; i += kThreads)
+    {
+      const uint32_t row = i >> 3, col = i & 7u;
+      const uint32_t e   = __ldg(&t->encodeRows[row]);
+      tab[row * 16u + 8u + col] = make_uint4(e, e, e, e);
+      if(row < 256u)
+      {
+        const uint32_t v = __float_as_uint(__ldg(&t->decode[row]));
+        tab[row * 16u + col] = make_uint4(v, v, v, v);
+      }
+    }
+    return;
+  }
   float*    decode = reinterpret_cast<float*>(smemRaw + (kGenDecodeAddr - kGenWindowBase));
   uint32_t* encode = reinterpret_cast<uint32_t*>(smemRaw + (kGenEncodeAddr - kGenWindowBase));
   for(uint32_t i = threadIdx.x; i < 512u; i += kThreads)
@@ -156,6 +187,17 @@ __device__ __forceinline__ V4 genReduce2(V4 v0, V4 v1)
 }
 
 // srgbFromLinear with both clamps (weighted sums may exceed 1 by an ulp); code in bits 16..23.
+// Row-table variant: code in bits 24..31.  laneAddr = kGenDecodeAddr | lane << 2 (byte 0 = lane << 2, byte 3 = 0).
+__device__ __forceinline__ uint32_t genEncChannelRows(float x, uint32_t laneAddr)
+{
+  // Weighted sums are >= 0 and stay below 1 + 2^-7 (the table's last row): only the lower clamp is needed.
+  const uint32_t b    = max(__float_as_uint(x), kEncMinBits);
+  const float    z    = __fadd_rn(__uint_as_float(b), __uint_as_float(kRowEncCBits));  // RN(x + c)
+  const uint32_t addr = __byte_perm(__float_as_uint(z), laneAddr, 0x7324);           // key(z) << 8 | lane << 2
+  uint32_t       e;
+  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(e) : "r"(addr), "n"(kGenRowEncImm));
+  return e + b;
+}
 __device__ __forceinline__ uint32_t genEncChannel(float x)
 {
   // Weighted sums stay below 1 + 2^-8, i.e. inside the table's last bucket (key of 1.0f): only the lower
@@ -170,9 +212,15 @@ __device__ __forceinline__ uint32_t genEncChannel(float x)
 }
 __device__ __forceinline__ uint32_t genEncWord(float4 v)
 {
-  const uint32_t r = genEncChannel(v.x), g = genEncChannel(v.y), b = genEncChannel(v.z);
   // uint(a * 255 + 0.5): a <= 1 + 2 ulp, so the truncation never exceeds 255
   const uint32_t a = __float_as_uint(__fadd_rz(__fadd_rn(__fmul_rn(v.w, 255.0f), 0.5f), 8388608.0f));
+  if(kGenRows)
+  {
+    const uint32_t laneAddr = kGenDecodeAddr | ((threadIdx.x & 31u) << 2);
+    const uint32_t r = genEncChannelRows(v.x, laneAddr), g = genEncChannelRows(v.y, laneAddr), b = genEncChannelRows(v.z, laneAddr);
+    return __byte_perm(__byte_perm(r, g, 0x0073), __byte_perm(b, a, 0x0043), 0x5410);
+  }
+  const uint32_t r = genEncChannel(v.x), g = genEncChannel(v.y), b = genEncChannel(v.z);
   return __byte_perm(__byte_perm(r, g, 0x0062), __byte_perm(b, a, 0x0042), 0x5410);
 }
 
@@ -466,11 +514,14 @@ constexpr int kGen4Warps = NVPYR_GEN4_WARPS;  // 16: 512 threads per CTA, one CT
 // into a 16-byte aligned stage of the warp's ring, and every lane then reads its four columns of both rows back with
 // two LDS.128.  No prefetch registers; kGenStages output rows are in flight ahead of the one being computed instead
 // of two.  Copies beyond the end of a row are suppressed (src-size 0: zero fill, no global access).
-constexpr uint32_t kGenStages     = 4;
+constexpr uint32_t kGenStages     = kGenRows ? 3 : 4;
 constexpr uint32_t kGenStageBytes = 1024;                     // two source rows x 128 texels
-constexpr uint32_t kGenRingAddr   = kGenDecodeAddr + 0x10000u;  // window address of the first warp's ring
-constexpr uint32_t kGenStagedSmemBytes = kGenRingAddr + kGen4Warps * kGenStages * kGenStageBytes - kGenWindowBase;
-static_assert(kGenRingAddr % 16u == 0 && kGenStagedSmemBytes + 1024u <= 227u * 1024u, "ring placement");
+// window address of the first warp's ring: behind the decode table, or (row table) below it
+constexpr uint32_t kGenRingAddr   = kGenRows ? kGenWindowBase : kGenDecodeAddr + 0x10000u;
+constexpr uint32_t kGenStagedSmemBytes =
+    kGenRows ? kGenSmemBytes : kGenRingAddr + kGen4Warps * kGenStages * kGenStageBytes - kGenWindowBase;
+static_assert(kGenRingAddr % 16u == 0 && kGenStagedSmemBytes + 1024u <= 228u * 1024u, "ring placement");
+static_assert(!kGenRows || kGenRingAddr + kGen4Warps * kGenStages * kGenStageBytes <= kGenDecodeAddr, "ring must end below the table");
 
 __device__ __forceinline__ void cpAsync4(uint32_t dst, const void* src, uint32_t srcBytes)
 {
@@ -506,7 +557,7 @@ __global__ void __launch_bounds__(kGen4Warps * 32, 1) generalStrip4Kernel(const 
 
   // staging ring of this warp: stage = (rows consumed so far) mod kGenStages
   const uint32_t ringBase = kGenRingAddr + warp * kGenStages * kGenStageBytes;
-  uint32_t       consumed = 0, issued = 0;
+  uint32_t       consumed = 0, issued = 0;  // stage indices (wrap at kGenStages)
 
   const uint32_t numTasks = p.stripsX * p.segsY;
   for(uint32_t task = blockIdx.x + gridDim.x * warp; task < numTasks; task += gridDim.x * kGen4Warps)
@@ -589,7 +640,7 @@ __global__ void __launch_bounds__(kGen4Warps * 32, 1) generalStrip4Kernel(const 
     auto stageIssue = [&](uint32_t yy) {
       if(yy <= yb)
       {
-        const uint32_t       dst = ringBase + (issued & (kGenStages - 1u)) * kGenStageBytes + lane * 4u;
+        const uint32_t       dst = ringBase + issued * kGenStageBytes + lane * 4u;
         const unsigned char* r0  = segSrc + size_t(kY3 ? 2u * yy + 1u : 2u * yy) * L0.pitch;
 #pragma unroll
         for(uint32_t j = 0; j < 4u; ++j)
@@ -599,7 +650,7 @@ __global__ void __launch_bounds__(kGen4Warps * 32, 1) generalStrip4Kernel(const 
         }
       }
       cpAsyncCommit();
-      ++issued;
+      issued = issued + 1u == kGenStages ? 0u : issued + 1u;
     };
     if(kStaged)
     {
@@ -627,8 +678,8 @@ __global__ void __launch_bounds__(kGen4Warps * 32, 1) generalStrip4Kernel(const 
         // rows, hand the stage back
         cpAsyncWait<kGenStages - 1>();
         __syncwarp();  // every lane's words of the stage have landed
-        const uint32_t mine = ringBase + (consumed & (kGenStages - 1u)) * kGenStageBytes + lane * 16u;
-        ++consumed;
+        const uint32_t mine = ringBase + consumed * kGenStageBytes + lane * 16u;
+        consumed            = consumed + 1u == kGenStages ? 0u : consumed + 1u;
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m.a.w0), "=r"(m.a.w1), "=r"(m.a.w2), "=r"(m.a.w3) : "r"(mine));
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+512];" : "=r"(m.b.w0), "=r"(m.b.w1), "=r"(m.b.w2), "=r"(m.b.w3) : "r"(mine));
         __syncwarp();  // all lanes have read the stage before anyone overwrites it
