@@ -122,7 +122,7 @@ uint32_t rowOfBits(uint32_t xbits)
   return (b >> 16) - kRowEncFirstKey;
 }
 // The smallest non-zero value a level +1 encode (the unclamped one) can see: linearFromSrgb(1) / 4.
-constexpr uint32_t rowEncFloorBits() { return NVPYR_SRGB_DECODE_BITS[1] - (2u << 23); }
+inline uint32_t rowEncFloorBits() { return NVPYR_SRGB_DECODE_BITS[1] - (2u << 23); }
 
 // entry[row] + bits(x) carries srgbFromLinear(x) in bits 24..31 for every x of the row that the kernel can present.
 // Fails (returns false) if a row held two thresholds or spanned 2^24 patterns or more -- impossible with the pinned

@@ -514,7 +514,10 @@ constexpr int kGen4Warps = NVPYR_GEN4_WARPS;  // 16: 512 threads per CTA, one CT
 // into a 16-byte aligned stage of the warp's ring, and every lane then reads its four columns of both rows back with
 // two LDS.128.  No prefetch registers; kGenStages output rows are in flight ahead of the one being computed instead
 // of two.  Copies beyond the end of a row are suppressed (src-size 0: zero fill, no global access).
-constexpr uint32_t kGenStages     = kGenRows ? 3 : 4;
+#ifndef NVPYR_GEN_STAGES
+#define NVPYR_GEN_STAGES (NVPYR_GEN_ENC_ROWS ? 3 : 4)
+#endif
+constexpr uint32_t kGenStages     = NVPYR_GEN_STAGES;
 constexpr uint32_t kGenStageBytes = 1024;                     // two source rows x 128 texels
 // window address of the first warp's ring: behind the decode table, or (row table) below it
 constexpr uint32_t kGenRingAddr   = kGenRows ? kGenWindowBase : kGenDecodeAddr + 0x10000u;

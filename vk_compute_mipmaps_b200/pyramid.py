@@ -10,6 +10,7 @@ command buffer is a CUDA stream, and the image is a packed linear chain in
 device memory (layout of include/mipmap_storage.hpp:53-76).
 """
 import ctypes as C
+import functools
 import os
 from dataclasses import dataclass
 
@@ -61,6 +62,7 @@ def level_offset_texels(width, height, level):
     return out.value
 
 
+@functools.lru_cache(maxsize=4096)
 def chain_bytes(width, height, levels=0, fmt=FORMAT_SRGBA8):
     out = C.c_uint64()
     check(lib.nvpyrGetChainBytes(Extent2D(width, height), levels, fmt, C.byref(out)), "nvpyrGetChainBytes")
