@@ -5,7 +5,8 @@
 // Python table is host-bound there, this one is not.
 // build: g++ -O2 -std=c++17 -I include -I /usr/local/cuda/include tools/bench_native.cpp -o tools/bench_native
 //            -L vk_compute_mipmaps_b200 -lnvpyr -L /usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/vk_compute_mipmaps_b200
-// usage: tools/bench_native [--batches 30] [--json out.json] [--peak GBps]
+// usage: tools/bench_native [--batches 30] [--json out.json] [--peak GBps] [--only substr] [--opaque]
+//        --opaque: alpha = 255 in every sRGBA8 texel (an image that came from a JPEG: the fast kernel's opaque path)
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -51,6 +52,7 @@ int main(int argc, char** argv)
   int         batches = 30;
   double      peak    = 6446.9;
   std::string json, only;
+  bool        opaque = false;
   for(int i = 1; i < argc; ++i)
   {
     if(!strcmp(argv[i], "--batches") && i + 1 < argc)
@@ -61,6 +63,8 @@ int main(int argc, char** argv)
       peak = atof(argv[++i]);
     else if(!strcmp(argv[i], "--only") && i + 1 < argc)
       only = argv[++i];
+    else if(!strcmp(argv[i], "--opaque"))
+      opaque = true;
   }
   if(nvpyrInit() != NVPYR_SUCCESS)
   {
@@ -90,7 +94,7 @@ int main(int argc, char** argv)
       for(uint64_t i = 0; i < l0; i += 4)
       {
         s = s * 1664525u + 1013904223u;
-        const uint32_t v = s ^ (s >> 13);
+        const uint32_t v = (s ^ (s >> 13)) | (opaque ? 0xFF000000u : 0u);
         memcpy(&host[i], &v, 4);
       }
     else
@@ -144,9 +148,9 @@ int main(int argc, char** argv)
     {
       fprintf(jf, "%s {\"config\": \"%s\", \"w\": %u, \"h\": %u, \"format\": \"%s\", \"launches\": %llu, \"min_ns\": %.0f, \"median_ns\": %.0f, "
                   "\"algorithmic_bytes\": %llu, \"GBps_at_median\": %.1f, \"frac_of_hbm_peak\": %.3f, \"rotating_buffers\": %d, "
-                  "\"harness\": \"C++ (tools/bench_native.cpp), 8 back-to-back nvpyrDispatchEx calls between two events\"}",
+                  "\"content\": \"%s\", \"harness\": \"C++ (tools/bench_native.cpp), 8 back-to-back nvpyrDispatchEx calls between two events\"}",
               first ? "" : ",\n", c.name, c.w, c.h, c.fmt == NVPYR_FORMAT_SRGBA8 ? "srgba8" : "rgba32f", (unsigned long long)launches, mn, med,
-              (unsigned long long)bytes, bytes / med, bytes / med / peak, nrot);
+              (unsigned long long)bytes, bytes / med, bytes / med / peak, nrot, opaque ? "uniform random colours, alpha 255" : "uniform random bytes");
       first = false;
     }
     for(void* b : bufs)
