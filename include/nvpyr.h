@@ -127,7 +127,8 @@ typedef struct nvpyrPlanStep
 
 typedef struct nvpyrPlanOptions
 {
-  uint32_t flags;                /* NVPYR_FLAG_FORCE_GENERAL honoured */
+  uint32_t flags;                /* NVPYR_FLAG_FORCE_GENERAL and NVPYR_FLAG_GENERAL_BLIT (pipeline 0 steps = one blit each,
+                                    workgroups 0) honoured */
   uint32_t fastDivisibility;     /* template arg DivisibilityRequirement; 0 = default 4 */
   uint32_t fastMaxLevels;        /* template arg MaxLevels (<= 6);        0 = default 6 */
 } nvpyrPlanOptions;

@@ -43,7 +43,7 @@ def test_oracle_blit_equals_vulkan_rule(oracle, size):
 def test_oracle_blit_loop_structure(oracle):
     """'generalblit' takes the fast pipeline where the default dispatcher would and blits single levels elsewhere;
     'blit' blits every level (mipmap_pipelines.cpp:376-453)."""
-    w, h = 260, 260  # fast 2 levels -> 65x65: blits down to 1x1
+    w, h = 260, 260  # fast 2 levels -> 65x65, one blit -> 32x32, fast 5 levels
     l0 = _oracle.random_level0(w, h, 3)
     _, stores_gb = oracle.shader_chain(l0, w, h, general_blit=True)
     _, stores_b = oracle.shader_chain(l0, w, h, general_blit=True, force_general=True)
@@ -54,6 +54,21 @@ def test_oracle_blit_loop_structure(oracle):
     d, _ = oracle.shader_chain(l0, w, h)
     n2 = 4 * (w * h + 130 * 130 + 65 * 65)
     assert (a[:n2] == d[:n2]).all() and (a[n2:] != d[n2:]).any()  # the two fast levels agree, the rest differs
+
+
+def test_plan_with_blit_fallback():
+    """nvpyrGetPlan with NVPYR_FLAG_GENERAL_BLIT: the loop of mipmap_pipelines.cpp:376-453 -- fast dispatches where the
+    default fast dispatcher accepts, single-level blits (no compute dispatch: workgroups 0) everywhere else."""
+    import vk_compute_mipmaps_b200 as nv
+    plan = nv.get_plan(260, 260, flags=nv.FLAG_GENERAL_BLIT)
+    # 260 -> 65 by the fast pipeline, 65 -> 32 by one blit, and 32 x 32 is eligible for the fast pipeline again
+    assert [(s["pipeline"], s["inputLevel"], s["levelCount"]) for s in plan] == [(1, 0, 2), (0, 2, 1), (1, 3, 5)]
+    assert plan[1]["workgroups"] == 0
+    plan = nv.get_plan(333, 97, flags=nv.FLAG_GENERAL_BLIT)
+    assert [(s["pipeline"], s["levelCount"]) for s in plan] == [(0, 1)] * 8
+    plan = nv.get_plan(64, 64, flags=nv.FLAG_GENERAL_BLIT | nv.FLAG_FORCE_GENERAL)
+    assert [(s["pipeline"], s["levelCount"]) for s in plan] == [(0, 1)] * 6
+    assert [(s["pipeline"], s["levelCount"]) for s in nv.get_plan(64, 64, flags=nv.FLAG_GENERAL_BLIT)] == [(1, 6)]
 
 
 def test_constant_image_stays_constant_under_blit(oracle):

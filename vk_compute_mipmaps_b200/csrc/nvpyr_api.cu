@@ -1679,7 +1679,8 @@ nvpyrStatus nvpyrGetPlan(nvpyrExtent2D e, uint32_t levelCount, const nvpyrPlanOp
     if(fast == nullptr)
       return NVPYR_ERROR_UNSUPPORTED;
   }
-  const int n = buildPlan(e.width, e.height, levelCount, defaultGeneralDispatcher, fast, steps, maxSteps);
+  const dispatcher_t general = (o.flags & NVPYR_FLAG_GENERAL_BLIT) ? blitDispatcher : defaultGeneralDispatcher;
+  const int          n       = buildPlan(e.width, e.height, levelCount, general, fast, steps, maxSteps);
   if(n < 0)
     return NVPYR_ERROR_INVALID_VALUE;
   *count = uint32_t(n);

@@ -1,31 +1,35 @@
 // nvpyr_fast_srgba8.cuh -- the hot kernel: sRGBA8 fast pipeline, 2..6 levels per launch.
 //
 // Same float32 expression trees as fastKernel<Srgba8, M> (nvpyr_kernels.cuh) and therefore
-// the same bits, but arranged for the B200's instruction budget.  At HBM speed the SMs can
-// issue only ~118 warp-lane instructions per 2x2 input quad (16 bytes), and the LSU can
-// serve ~30 shared-memory wavefronts per 32 quads, so this kernel is issue/LSU bound, not
-// DRAM bound (DESIGN.md "Why the fast kernel is not DRAM-bound yet"):
+// the same bits, but arranged for the B200's instruction and shared-memory budgets.  At HBM speed an SM may
+// spend 121 cycles on a 64x8 slab (2 KB in, 0.67 KB out): 484 warp-instruction issue slots and 121 LSU
+// wavefronts.  The exact path needs 48 table decodes and 16 channel encodes per lane and slab, so this kernel
+// is issue / LSU bound, not DRAM bound; as measured (round 2): 405 instructions and ~106
+// wavefronts per slab, 0.94 of the measured HBM peak for the launch, on any content.
 //
 //  * decode: one PRMT builds the shared-memory address (code << 8 | lane << 2) straight from
 //    the packed texel word, one LDS reads the lane-private copy of the 256-entry table
 //    (stride 256 B per code: no bank conflict for any data).  Alpha goes through I2F (XU
 //    pipe) + FMUL to keep the LSU free.
+//  * encode (round 2, NVPYR_FAST_ENC_ROWS): the bucket is the key of z = RN(x + 1/32 - 2^-14) instead of the key of
+//    x: 645 rows cover [0, 1], few enough for a lane-private copy of every entry, so the look-up -- FFMA, PRMT, LDS,
+//    IADD3 -- is one conflict-free wavefront like the decode.  Decode and encode share one table of 646 rows x 256
+//    bytes (low half rows: decode copies / level +3 stashes, high half rows: encode copies).  Level +1 (12 of every
+//    16 encodes) needs no clamp: exact zero has a row to itself.
 //  * deferred normalisation: 0.25*((a+b)+(c+d)) is carried as the un-normalised sum
 //    S = (a+b)+(c+d) = 4^k * value, and the decode table is pre-scaled by 2^-100.  Scaling
 //    by a power of two commutes with rounding (nothing here is subnormal or overflows), so
-//    every deeper sum and every stored code is bit-identical; the FMULs disappear and the
-//    encode of levels +1 and +2 (15 of every 16 encodes) needs no clamp: the bucket table is
-//    extended downwards to their smallest non-zero sum, and an exact zero (bit pattern 0)
-//    indexes a dedicated word placed in the unused half of a decode-table row.  Deeper
-//    levels clamp with one FMNMX.  Alpha uses the exact constant 255 / 4^k.
+//    every deeper sum and every stored code is bit-identical; the FMULs disappear.  Alpha uses the exact
+//    constant 255 / 4^k.
 //  * level +3 is a "transpose-reduce": in two shuffle steps the four threads of a 2x2 block
 //    end up holding ONE channel each of the common result (3 SHFL + 3 FADD per thread
 //    instead of 12 + 12), encode it in parallel and gather the four bytes with two PRMTs.
 //  * warp-autonomous tiles: one WARP owns a 64 x max(8, 2^M) input tile and walks it as
-//    64x8 slabs (lane = 4x4 texels), keeping the level +3 sums in a 1 KB warp-private shared
-//    tile; levels +4..+M are finished by the same warp.  No CTA-wide barrier exists after
-//    the table set-up (the v2 kernel lost 13 % of its warp time at one).  Tiles are only as
-//    tall as the step needs, so steps with M < 6 expose 2-8x more independent warp tasks.
+//    64x8 slabs (lane = 4x4 texels), keeping the level +3 sums in a 1 KB warp-private stash;
+//    levels +4..+M are finished by the same warp.  No CTA-wide barrier exists after
+//    the table set-up.  Tiles are only as tall as the step needs, so steps with M < 6 expose 2-8x more
+//    independent warp tasks.  The warp index is taken through a shuffle so that the compiler keeps the tile
+//    bookkeeping, the TMA coordinates and the mbarrier address in uniform registers (no spill, no ELECT/R2UR loops).
 //  * packed adds: FADD2 (add.rn.f32x2) performs two IEEE float32 additions per issue slot;
 //    the sums run on (R, G) and (B, A) pairs.
 //  * the level-0 slab of a warp is staged in shared memory by the TMA unit (one 2-D tensor-map
@@ -33,15 +37,14 @@
 //    processed; the batch / fused-premultiply / slab-task kernels prefetch the next slab's four
 //    16-byte rows into registers instead.
 //
-//  * the encode bucket table (bucket = exponent + 7 mantissa bits) is stored 8-way bank-partitioned
-//    (entry k occupies 32 bytes, lane l reads copy l & 7): lanes with different l & 7 can never
-//    collide on a bank.  Measured on 16384^2, uniform-random input: 328 us un-replicated, 284 us
-//    4-way (8 mantissa bits), 273 us 8-way.
-//
-// CTA = 1024 threads = 32 warps sharing the tables; one CTA per SM.  160 KB of tables and stashes
+// CTA = 32 or 24 warps (template parameter) sharing the tables; one CTA per SM; 161.5 KB of tables and stashes
 // + 64 KB of TMA ring for the kernels that use it.  With LDG loads, shared memory beyond ~200 KB
 // leaves the SM too little L1 for the loads in flight (a 213 KB variant of the register path ran
 // 19 % slower); loads staged by the TMA unit do not pass through L1.
+//
+// The compile-time switches below select measured-and-rejected variants (each with its numbers) for A/B runs; the
+// round-1 bucket tables (NVPYR_FAST_ENC_ROWS = 0: NVPYR_ENC_WAYS, NVPYR_FAST_ENC_CLAMP, ..._LOW_OCTAVES,
+// NVPYR_FAST_L3_IN_DECODE) are among them.
 #pragma once
 #include <stddef.h>
 
