@@ -346,6 +346,20 @@ def test_general_blit_variant_bit_exact(nv, cuda, oracle, size):
             gpu_chain(nv, cuda, l0, w, h, flags=nv.FLAG_GENERAL_BLIT | nv.FLAG_F16_SHARED)
 
 
+def test_external_memory_fd_import_live(nv, cuda):
+    """nvpyrImportExternalMemoryFd with a LIVE file descriptor (the CUDA half of the Vulkan interop):
+    device memory created through CUDA's virtual-memory API is exported as a POSIX fd -- the GPU boxes have no Vulkan
+    implementation to call vkGetMemoryFdKHR on (profiles/r2_vulkan_probe.txt) -- the fd goes through the library's import
+    (cudaImportExternalMemory, opaque fd: the call a Vulkan fd takes), the chain is generated in the imported buffer
+    and must equal the oracle's bit for bit; mixed schedule (1920x1080), fast + general + fast (260x260), NPOT."""
+    import subprocess, sys
+    tool = os.path.join(_oracle.ROOT, "tools", "extmem_probe.py")
+    for w, h in ((1920, 1080), (260, 260), (333, 97)):
+        r = subprocess.run([sys.executable, tool, str(w), str(h)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "imported: device pointer" in r.stdout and "== oracle" in r.stdout, r.stdout
+
+
 def test_slab_task_handoff_stress(nv, cuda):
     """The slab-task mode hands a tile's level +3 sums from the warps that produce them to the warp that arrives last
     through shared memory ordered by fences and a shared atomic (no barrier), and recycles stash slots through a
