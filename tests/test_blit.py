@@ -3,6 +3,7 @@ restatement against Vulkan's scaled-blit rule evaluated in exact rational arithm
 encode table self-test of the tuned fast kernel (host only)."""
 from fractions import Fraction
 import math
+import os
 
 import numpy as np
 import pytest
@@ -69,6 +70,40 @@ def test_plan_with_blit_fallback():
     plan = nv.get_plan(64, 64, flags=nv.FLAG_GENERAL_BLIT | nv.FLAG_FORCE_GENERAL)
     assert [(s["pipeline"], s["levelCount"]) for s in plan] == [(0, 1)] * 6
     assert [(s["pipeline"], s["levelCount"]) for s in nv.get_plan(64, 64, flags=nv.FLAG_GENERAL_BLIT)] == [(1, 6)]
+
+
+# file, worst delta vs the CPU generator that the reference RECORDED for its "blit" and "generalblit" alternatives
+# (demo_app/rtx3090.json: vkCmdBlitImage on an RTX 3090), worst delta of OUR pinned blit arithmetic (oracle restatement)
+# on the PIL-decoded, premultiplied image vs the real CPU generator, computed in the build container
+RECORDED_BLIT_DELTAS = [
+    ("1080p.jpg", 83, 83, 83, 83), ("1440p.jpg", 61, 61, 60, 61), ("4094.jpg", 206, 206, 206, 206),
+    ("4095.jpg", 218, 218, 218, 218), ("4096.jpg", 2, 2, 1, 2), ("4k.jpg", 89, 89, 89, 89),
+    ("alpha1080p.png", 57, 58, 59, 58), ("alpha2048.png", 3, 4, 4, 4), ("alpha2052.png", 98, 98, 95, 95),
+    ("lunch_2047.jpg", 87, 87, 87, 87), ("lunch_with_friend.jpg", 2, 2, 1, 2), ("mandelbrots.png", 67, 67, 66, 66),
+    ("tall.jpg", 200, 200, 200, 200)]
+
+
+@pytest.mark.parametrize("name,rec_blit,rec_gblit,our_blit,our_gblit", RECORDED_BLIT_DELTAS, ids=[r[0] for r in RECORDED_BLIT_DELTAS])
+def test_blit_reproduces_the_reference_recorded_deltas(oracle, name, rec_blit, rec_gblit, our_blit, our_gblit):
+    """A Vulkan blit's arithmetic is implementation-defined, but its ERROR against the correct down-sampler is mostly
+    structural (two taps per axis whatever the scale), and the reference recorded that error on real hardware for its 13
+    test images.  Our pinned blit, run on the same images, lands on the recorded worst delta exactly for 9 (generalblit)
+    and within 3 code values for all 13: the loop and the sampling rule are the reference's."""
+    from PIL import Image
+    ref = _oracle.load_ref()
+    path = os.path.join(os.path.dirname(__file__), "golden", "test_images", name)
+    im = Image.open(path).convert("RGBA")
+    w, h = im.size
+    l0 = oracle.premultiply(np.asarray(im, dtype=np.uint8).reshape(-1).copy())  # mipmaps_app.cpp:606
+    cpu = ref.cpu_chain(oracle.new_chain(l0, w, h), w, h) if ref is not None else oracle.cpu_chain(l0, w, h)
+    gblit = oracle.compare(oracle.shader_chain(l0, w, h, general_blit=True)[0], cpu, w, h).worst
+    blit = oracle.compare(oracle.shader_chain(l0, w, h, general_blit=True, force_general=True)[0], cpu, w, h).worst
+    assert (blit, gblit) == (our_blit, our_gblit), (name, blit, gblit)
+    assert abs(blit - rec_blit) <= 3 and abs(gblit - rec_gblit) <= 3, (name, blit, gblit, rec_blit, rec_gblit)
+
+
+def test_blit_recorded_deltas_exact_on_most_images():
+    assert sum(1 for r in RECORDED_BLIT_DELTAS if r[2] == r[4]) >= 9  # generalblit: 9 of 13 exactly as recorded
 
 
 def test_constant_image_stays_constant_under_blit(oracle):

@@ -9,13 +9,14 @@ between two timestamps (CUDA events here), the first batch discarded, min / medi
 (cpuGenerateMipmaps_sRGBA, the real one from oracle/_ref when it was built, else its restatement) on the same
 premultiplied level 0 -- the number the reference records as its own test result (`worstDeltaArray`, :812-821).
 
-Images: the reference's 13 test images are not redistributable with this repo and do not exist on the GPU box, so
-each is replaced by a synthetic image of the same size and alpha class (smooth colour fields plus noise; alpha images
-get a varying alpha channel and are premultiplied like mipmaps_app.cpp:606 does).  With --images DIR the real files
-are used (needs PIL).  Alternatives: those of demo_app/pipeline_alternative.cpp that this library offers --
+Images: with --images DIR (default: tests/golden/test_images when it exists) the reference's 13 test images are used
+(needs PIL); otherwise each is replaced by a synthetic image of the same size and alpha class (smooth colour fields plus
+noise; alpha images get a varying alpha channel and are premultiplied like mipmaps_app.cpp:606 does).  Alternatives: those of demo_app/pipeline_alternative.cpp that this library offers --
 default, generalonly (no fast pipeline), levels_1_5 / levels_1_6 (fast dispatcher <2,5> / <2,6>), f16Shared, srgbShared,
-noBilinear (= default here: the software 4-tap first reduction is the only one).  blit / generalblit / onelevel /
-levels_1_3 / levels_3_3 / workgroup1024 are not offered and are left out.
+noBilinear (= default here: the software 4-tap first reduction is the only one), blit / generalblit
+(NVPYR_FLAG_GENERAL_BLIT).  onelevel / levels_1_3 / levels_3_3 / workgroup1024 are not offered and
+are left out.  Timings go through the Python wrapper (10-20 us of host time per call: host-bound for the small images;
+tools/bench_native.cpp measures the default alternative from C++).
 This tool is bench/test infrastructure: it is the one place outside tests/ and bench.py that calls oracle/.
 """
 import argparse, json, os, sys
@@ -37,7 +38,8 @@ IMAGES = [  # name, w, h, has alpha   (test_images/, docs/test_images.txt)
 ALTERNATIVES = [  # label, flags, fast divisibility, fast max levels
     ("default", nv.FLAG_NONE, 0, 0), ("generalonly", nv.FLAG_FORCE_GENERAL, 0, 0), ("levels_1_5", nv.FLAG_NONE, 2, 5),
     ("levels_1_6", nv.FLAG_NONE, 2, 6), ("srgbShared", nv.FLAG_SRGB_SHARED, 0, 0), ("f16Shared", nv.FLAG_F16_SHARED, 0, 0),
-    ("noBilinear", nv.FLAG_NONE, 0, 0),
+    ("noBilinear", nv.FLAG_NONE, 0, 0), ("blit", nv.FLAG_GENERAL_BLIT | nv.FLAG_FORCE_GENERAL, 0, 0),
+    ("generalblit", nv.FLAG_GENERAL_BLIT, 0, 0),
 ]
 
 
@@ -59,6 +61,9 @@ def main():
     ap.add_argument("--out")
     ap.add_argument("--images", help="directory holding the reference's test_images (optional)")
     a = ap.parse_args()
+    default_images = os.path.join(ROOT, "tests", "golden", "test_images")
+    if not a.images and os.path.isdir(default_images):
+        a.images = default_images
     oracle, ref = _oracle.load_oracle(), _oracle.load_ref()
     st = torch.cuda.current_stream()
     lines = ["{"]
