@@ -235,6 +235,7 @@ struct DeviceContext
   // nvpyrDispatchBatch: ring of device words holding the chain base pointers of batched launches.  A slice stays
   // reserved until the event recorded behind the batch's last kernel has completed.
   const unsigned char** batchBases = nullptr;
+  CUtensorMap*          batchMaps  = nullptr;  // same ring positions: one tensor map (level 0) per image; allocated by the first fused batch
   struct BatchSlice
   {
     uint64_t    begin, end;  // positions in the unwrapped ring
@@ -441,6 +442,20 @@ TensorMapEncodeFn tensorMapEncoder()
   return encode;
 }
 
+// cuTensorMapReplaceAddress (CUDA 12.0+): the maps of a batch differ in their base address only.
+using TensorMapReplaceFn = CUresult (*)(CUtensorMap*, void*);
+TensorMapReplaceFn tensorMapReplacer()
+{
+  static const TensorMapReplaceFn replace = [] {
+    void*                           f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if(cudaGetDriverEntryPoint("cuTensorMapReplaceAddress", &f, cudaEnableDefault, &q) != cudaSuccess)
+      f = nullptr;
+    return reinterpret_cast<TensorMapReplaceFn>(f);
+  }();
+  return replace;
+}
+
 // NVPYR_NO_SLAB_TASKS=1: always one warp per tile in the tuned fast kernel (A/B timing).
 const bool g_noSlabTasks = [] {
   const char* e = getenv("NVPYR_NO_SLAB_TASKS");
@@ -458,7 +473,7 @@ template <int M, bool kBatch, bool kPremul, bool kSlabTasks, int kWarps>
 nvpyrStatus launchFastSrgba8W(const DeviceContext& ctx, const FastParams& p, const FastBatch& b, uint64_t work,
                               cudaStream_t stream)
 {
-  const size_t smem = fastSmemBytes(kFastTma && !kBatch && !kPremul && !kSlabTasks);
+  const size_t smem = fastSmemBytes(kFastTma && !kPremul && !kSlabTasks);
   int          grid = 1;
   nvpyrStatus  st   = persistentGrid(fastSrgba8Kernel<M, kBatch, kPremul, kSlabTasks, kWarps>, smem, ctx, work, &grid, kWarps * 32);
   if(st != NVPYR_SUCCESS)
@@ -538,7 +553,7 @@ nvpyrStatus launchFastSrgba8T(const DeviceContext& ctx, FastParams p, cudaStream
   constexpr uint32_t tileH = M >= 3 ? (1u << M) : 8u;  // one warp per 64 x tileH tile
   p.tilesX                 = (p.lv[0].w + 63u) / 64u;
   p.tilesY                 = (p.lv[0].h + tileH - 1u) / tileH;
-  FastBatch b              = batch ? *batch : FastBatch{nullptr, 0u, 0u};
+  FastBatch b              = batch ? *batch : FastBatch{nullptr, 0u, 0u, nullptr};
   b.tilesPerImage          = p.tilesX * p.tilesY;
   const uint64_t work      = uint64_t(b.tilesPerImage) * (batch ? b.count : 1u);
   if(work > 0xFFFFFFFFull)
@@ -1184,6 +1199,8 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
       const uint64_t tail = ctx.batchInFlight.empty() ? begin : ctx.batchInFlight.front().begin;
       if(begin + count - tail <= kBatchRing)
       {
+        if(ctx.batchMaps == nullptr)  // first fused batch on this device
+          NVPYR_CUDA(cudaMalloc(&ctx.batchMaps, size_t(kBatchRing) * sizeof(CUtensorMap)));
         ctx.batchHead = begin + count;
         devBases      = ctx.batchBases + begin % kBatchRing;
         if(ctx.batchEventPool.empty())
@@ -1216,6 +1233,39 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
   *handled = true;  // from here on errors are real errors
 
   const bool premul = a.flags & NVPYR_FLAG_PREMULTIPLY_ALPHA;  // fused into the level-0 read of the big step
+  // TMA staging of the batch kernel: one 2-D tensor map per image (level 0: W x H texels, box 64 x 8), encoded on the
+  // host and uploaded next to the base pointers (the premultiplying variant rewrites level 0 and keeps the register path).
+  const CUtensorMap* devMaps = nullptr;
+#if NVPYR_FAST_TMA == 2
+  if(!premul)
+  {
+    const TensorMapEncodeFn encode = tensorMapEncoder();
+    if(encode == nullptr)
+      return NVPYR_ERROR_UNSUPPORTED;
+    std::vector<CUtensorMap> hostMaps(count);
+    const cuuint64_t         dims[2]    = {a.lv[0].w, a.lv[0].h};
+    const cuuint64_t         strides[1] = {a.lv[0].pitch};
+    const cuuint32_t         box[2] = {64u, 8u}, estr[2] = {1u, 1u};
+    const TensorMapReplaceFn replace = tensorMapReplacer();
+    for(uint32_t i = 0; i < count; ++i)
+    {
+      // the maps differ in their base address only: encode the first one, then copy + replace the address
+      if(i > 0 && replace != nullptr)
+      {
+        hostMaps[i] = hostMaps[0];
+        if(replace(&hostMaps[i], r[i].lv[0].ptr) == CUDA_SUCCESS)
+          continue;
+      }
+      if(encode(&hostMaps[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, r[i].lv[0].ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+         != CUDA_SUCCESS)
+        return NVPYR_ERROR_CUDA;
+    }
+    CUtensorMap* dst = ctx.batchMaps + (devBases - ctx.batchBases);
+    NVPYR_CUDA(cudaMemcpyAsync(dst, hostMaps.data(), size_t(count) * sizeof(CUtensorMap), cudaMemcpyHostToDevice, a.stream));
+    devMaps = dst;
+  }
+#endif
 
   auto offsetView = [&](uint32_t level) {
     LevelView v = a.lv[level];
@@ -1226,7 +1276,7 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
   for(uint32_t k = 0; k <= steps[0].levelCount; ++k)
     p.lv[k] = offsetView(k);
   p.tables = ctx.tables;
-  FastBatch   b{devBases, 0u, count};
+  FastBatch   b{devBases, 0u, count, devMaps};
   nvpyrStatus st;
   switch(steps[0].levelCount)
   {
@@ -1943,6 +1993,7 @@ nvpyrStatus nvpyrShutdown(void)
     cudaFree(c->tables);
     cudaFree(c->tickets);
     cudaFree(c->batchBases);
+    cudaFree(c->batchMaps);
     for(HostPipeline* hp : c->hostIdle)
       destroyHostPipeline(hp);
     for(DeviceContext::BatchSlice& f : c->batchInFlight)

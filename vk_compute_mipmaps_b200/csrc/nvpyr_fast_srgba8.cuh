@@ -106,8 +106,8 @@ namespace nvpyr {
 // as slab s has been read into registers (a proxy fence orders the reads before the asynchronous writes).  The ring
 // of the 32 warps is 64 KB, which only fits next to the 3-low-octave encode table (224.6 KB of the 227 KB a CTA may
 // have); with the loads no longer passing through L1 the large carve-out is harmless.  The host encodes the tensor
-// map of the step's input level per launch (a kernel parameter).  Tile mode only: batches, the fused premultiply and
-// slab tasks keep the register path (and do not allocate the ring).
+// map of the step's input level per launch (a kernel parameter); a batch launch gets one map per image in device memory
+// (FastBatch::maps).  The fused premultiply and slab tasks keep the register path (and do not allocate the ring).
 // Measured at 16384^2 against the register path with the same table (us, 6-level kernel): Julia 242.3 -> 237.2
 // (92.3 % of HBM peak), smooth gradient 247.7 -> 245.7, uniform-random bytes 273.5 -> 278.0; the other sizes of the
 // config table within +-1 %.
@@ -635,6 +635,7 @@ struct FastBatch
 {
   const unsigned char* const* bases;
   uint32_t                    tilesPerImage, count;
+  const CUtensorMap*          maps;  // one tensor map per image (its level 0), in device memory: the batch kernel's TMA staging
 };
 
 // kPremul: level 0 holds straight (un-premultiplied) alpha; it is premultiplied on the fly, written back in
@@ -740,18 +741,20 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
   // (slab tasks keep the register path: a warp runs one or two tasks there, so there is little to overlap, and the
   // first copy of a CTA would pay the tensor-map fetch on top of the DRAM latency; TMA staging brought no gain outside
   // the box-to-box noise of the 2048^2 config when tried in round 2)
-  constexpr bool kTma = kFastTma && !kBatch && !kPremul && !kSlabTasks;
+  constexpr bool kTma = kFastTma && !kPremul && !kSlabTasks;  // (batches: one tensor map per image, FastBatch::maps)
   uint32_t       tmaBar = 0u, tmaRing = 0u, tmaPhase = 0u;
   // Issues the row copies of slab s of tile t (rows cut at the image edges; nothing for a tile that does not exist).
   auto tmaIssue = [&](uint32_t t, uint32_t s) {
     if(t >= numTiles)
       return;
-    const uint32_t xt = (t % p.tilesX) * 64u, ys = (t / p.tilesX) * kTileH + s * 8u;
+    const uint32_t tt = kBatch ? t % batch.tilesPerImage : t;  // tile inside its image
+    const uint32_t xt = (tt % p.tilesX) * 64u, ys = (tt / p.tilesX) * kTileH + s * 8u;
 #if NVPYR_FAST_TMA == 2
+    const CUtensorMap* map = kBatch ? batch.maps + t / batch.tilesPerImage : &tmap.map;
     if(lane == 0u)
     {
       mbarExpectTx(tmaBar, 2048u);  // the whole box, zero-filled outside the image
-      tensorCopy2D(tmaRing, &tmap.map, xt, ys, tmaBar);
+      tensorCopy2D(tmaRing, map, xt, ys, tmaBar);
     }
 #else
     const uint32_t rowBytes = min(64u, W - xt) * 4u, rows = min(8u, H - ys);
