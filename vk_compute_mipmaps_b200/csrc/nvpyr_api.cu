@@ -959,11 +959,18 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
   {
     const nvpyrPlanStep& s  = steps[i];
     TailStep&            ts = tp.steps[i];
-    ts.pipeline             = s.pipeline;
+    const bool           isBlit = s.pipeline == 0 && (r.flags & NVPYR_FLAG_GENERAL_BLIT);
+    ts.pipeline             = isBlit ? 2u : s.pipeline;
     ts.levels               = s.levelCount;
     for(uint32_t k = 0; k <= s.levelCount; ++k)
       ts.lv[k] = r.lv[s.inputLevel + k];
-    if(s.pipeline == 1)
+    if(isBlit)
+    {
+      // thread-strided over the destination texels: "tiles" = chunks of kTailThreads texels
+      ts.tilesX = uint32_t((uint64_t(ts.lv[1].w) * ts.lv[1].h + uint64_t(kTailThreads) - 1u) / uint64_t(kTailThreads));
+      ts.tilesY = 1u;
+    }
+    else if(s.pipeline == 1)
     {
       ts.vec    = fastVectorOk<F>(ts.lv) ? 1u : 0u;
       ts.tilesX = (ts.lv[0].w + 63u) / 64u;
@@ -978,7 +985,7 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
   }
   uint64_t work = uint64_t(tp.steps[0].tilesX) * tp.steps[0].tilesY;
   if(tp.steps[0].pipeline == 1 && tp.steps[0].levels == 1)  // fastLoop1 is thread-strided, not tiled
-    work = (uint64_t(tp.steps[0].lv[1].w) * tp.steps[0].lv[1].h + 255u) / 256u;
+    work = (uint64_t(tp.steps[0].lv[1].w) * tp.steps[0].lv[1].h + uint64_t(kTailThreads) - 1u) / uint64_t(kTailThreads);
   // The whole-level buffers of the solo steps are only allocated by launches that use them (a small footprint lets
   // the next kernel's CTAs move in early); the opt-in and the grid size are those of the larger footprint.
   const size_t smemSolo = ((sizeof(TailSmem<TF>) + 15u) & ~size_t(15)) + sizeof(SoloSmem);
@@ -1019,15 +1026,17 @@ nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0
   if(n < 0)
     return NVPYR_ERROR_INVALID_VALUE;
   auto texels = [&](int i) { return uint64_t(steps[i].srcWidth) * steps[i].srcHeight; };
-  const bool blit = (r.flags & NVPYR_FLAG_GENERAL_BLIT) != 0;  // general steps are one-level blits (never fused into a tail)
+  const bool blit = (r.flags & NVPYR_FLAG_GENERAL_BLIT) != 0;  // general steps are one-level blits (tailKernel pipeline 2 when small)
+  constexpr uint64_t kSoloMaxTexelsBlit = 128ull * 128ull;      // a blit of a level this small runs solo (<= 8 texels per thread)
+  for(int i = firstStep; i < n; ++i)
+    if(blit && steps[i].pipeline == 0 && steps[i].levelCount != 1)
+      return NVPYR_ERROR_INVALID_VALUE;  // (a user dispatcher together with the blit flag must fill one level per step)
   for(int i = firstStep; i < n;)
   {
     const nvpyrPlanStep& s = steps[i];
     nvpyrStatus          st;
-    if(blit && s.pipeline == 0)
+    if(blit && s.pipeline == 0 && (g_noTailFusion || texels(i) > kTailMaxTexels))
     {
-      if(s.levelCount != 1)
-        return NVPYR_ERROR_INVALID_VALUE;
       st = launchBlit<F>(ctx, r.lv[s.inputLevel], r.lv[s.inputLevel + 1], r.stream);
       ++i;
     }
@@ -1035,9 +1044,11 @@ nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0
     {
       // grid step i, then as many solo steps as follow (level sizes only shrink)
       int count = 1;
-      while(i + count < n && count < int(kMaxTailSteps) && !(blit && steps[i + count].pipeline == 0)
+      while(i + count < n && count < int(kMaxTailSteps)
             && (steps[i + count].pipeline == 1
                     ? texels(i + count) <= kSoloMaxTexelsFast
+                : blit
+                    ? texels(i + count) <= kSoloMaxTexelsBlit
                     : (std::max(steps[i + count].srcWidth, steps[i + count].srcHeight) <= kSoloMaxEdgeGeneral
                        || soloSmemOk<typename TailFunctors<F>::type>(steps[i + count].srcWidth, steps[i + count].srcHeight,
                                                                      steps[i + count].levelCount))))

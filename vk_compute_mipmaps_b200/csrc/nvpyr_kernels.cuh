@@ -468,6 +468,50 @@ __global__ void __launch_bounds__(256) generalKernel(const GeneralParams p)
 }
 
 // ---------------------------------------------------------------------------
+// Linear-filter blit of one level into the next (NVPYR_FLAG_GENERAL_BLIT; demo_app/mipmap_pipelines.cpp:418-426:
+// vkCmdBlitImage(level -> level + 1, whole extents, VK_FILTER_LINEAR)).  Vulkan's blit rule: the centre of destination
+// texel (i, j) maps to source coordinates ((i + 0.5) * srcW / dstW, (j + 0.5) * srcH / dstH), which are sampled with
+// an unnormalised, clamp-to-edge linear filter: texels floor(u - 0.5) and floor(u - 0.5) + 1 with weights (1 - a, a),
+// a = frac(u - 0.5).  Arithmetic pinned here (Vulkan leaves it implementation-defined): float32; scale = srcW / dstW
+// (IEEE division); u = (i + 0.5) * scale - 0.5 (two roundings); the three lerps go through the functor set's own
+// REDUCE as reduce(1 - a, p, a, q, 0, q): horizontally in both rows, then vertically -- so the blit works for any
+// functor set and an sRGB image is filtered in linear space, like a texture unit does it.
+__device__ __forceinline__ void blitTap(uint32_t i, float scale, uint32_t srcSize, uint32_t& i0, uint32_t& i1, float& a)
+{
+  const float u = __fsub_rn(__fmul_rn(__fadd_rn(float(i), 0.5f), scale), 0.5f);
+  const float f = floorf(u);
+  a             = __fsub_rn(u, f);
+  const int   k = int(f), last = int(srcSize) - 1;
+  i0            = uint32_t(min(max(k, 0), last));
+  i1            = uint32_t(min(max(k + 1, 0), last));
+}
+// Destination texels first, first + stride, ... (thread indices), by the calling thread.
+template <class F>
+__device__ __forceinline__ void blitLoop(const LevelView& src, const LevelView& dst, const typename F::Shared& tables, uint64_t first,
+                                         uint64_t stride)
+{
+  using V                = typename F::Value;
+  constexpr uint32_t TB  = F::kTexelBytes;
+  const float        sx  = __fdiv_rn(float(src.w), float(dst.w)), sy = __fdiv_rn(float(src.h), float(dst.h));
+  const uint64_t     n   = uint64_t(dst.w) * dst.h;
+  for(uint64_t t = first; t < n; t += stride)
+  {
+    const uint32_t y = uint32_t(t / dst.w), x = uint32_t(t - uint64_t(y) * dst.w);
+    uint32_t       x0, x1, y0, y1;
+    float          a, b;
+    blitTap(x, sx, src.w, x0, x1, a);
+    blitTap(y, sy, src.h, y0, y1, b);
+    const unsigned char* r0  = src.ptr + size_t(y0) * src.pitch;
+    const unsigned char* r1  = src.ptr + size_t(y1) * src.pitch;
+    const V              t00 = F::load(tables, r0 + size_t(x0) * TB), t10 = F::load(tables, r0 + size_t(x1) * TB);
+    const V              t01 = F::load(tables, r1 + size_t(x0) * TB), t11 = F::load(tables, r1 + size_t(x1) * TB);
+    const float          ia = __fsub_rn(1.0f, a), ib = __fsub_rn(1.0f, b);
+    const V              top = F::reduce(ia, t00, a, t10, 0.0f, t10), bot = F::reduce(ia, t01, a, t11, 0.0f, t11);
+    F::template store<true>(tables, dst.ptr + size_t(y) * dst.pitch + size_t(x) * TB, F::reduce(ib, top, b, bot, 0.0f, bot));
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Tail kernel: several consecutive small steps of a plan in ONE launch.
 //
 // The reference records one dispatch + pipeline barrier per step
@@ -487,7 +531,7 @@ constexpr int kTailThreads = NVPYR_TAIL_THREADS;
 
 struct TailStep
 {
-  uint32_t  pipeline;  // 1 fast, 0 general
+  uint32_t  pipeline;  // 1 fast, 0 general, 2 one level by a linear-filter blit (NVPYR_FLAG_GENERAL_BLIT)
   uint32_t  levels;
   uint32_t  vec;       // fast: vector loads/stores allowed
   uint32_t  soloSmem;  // solo general step that runs on whole levels held in shared memory (soloGeneralSmem)
@@ -611,7 +655,9 @@ template <class F, bool kSolo>
 __device__ __forceinline__ void tailRunStep(const TailStep& st, TailSmem<F>& sm, const DeviceTables* tables,
                                             uint32_t first, uint32_t stride)
 {
-  if(st.pipeline == 1u)
+  if(st.pipeline == 2u)
+    blitLoop<F>(st.lv[0], st.lv[1], sm.tables, uint64_t(first) * blockDim.x + threadIdx.x, uint64_t(stride) * blockDim.x);
+  else if(st.pipeline == 1u)
   {
     FastParams p;
 #pragma unroll
@@ -737,28 +783,12 @@ __global__ void __launch_bounds__(kTailThreads) tailBatchKernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------
-// Linear-filter blit of one level into the next (NVPYR_FLAG_GENERAL_BLIT; demo_app/mipmap_pipelines.cpp:418-426:
-// vkCmdBlitImage(level -> level + 1, whole extents, VK_FILTER_LINEAR)).  Vulkan's blit rule: the centre of destination
-// texel (i, j) maps to source coordinates ((i + 0.5) * srcW / dstW, (j + 0.5) * srcH / dstH), which are sampled with
-// an unnormalised, clamp-to-edge linear filter: texels floor(u - 0.5) and floor(u - 0.5) + 1 with weights (1 - a, a),
-// a = frac(u - 0.5).  Arithmetic pinned here (Vulkan leaves it implementation-defined): float32; scale = srcW / dstW
-// (IEEE division); u = (i + 0.5) * scale - 0.5 (two roundings); the three lerps go through the functor set's own
-// REDUCE as reduce(1 - a, p, a, q, 0, q): horizontally in both rows, then vertically -- so the blit works for any
-// functor set and an sRGB image is filtered in linear space, like a texture unit does it.
+// Stand-alone blit of one (large) level; small levels are blitted by tailKernel (pipeline 2).
 struct BlitParams
 {
   LevelView           src, dst;
   const DeviceTables* tables;
 };
-__device__ __forceinline__ void blitTap(uint32_t i, float scale, uint32_t srcSize, uint32_t& i0, uint32_t& i1, float& a)
-{
-  const float u = __fsub_rn(__fmul_rn(__fadd_rn(float(i), 0.5f), scale), 0.5f);
-  const float f = floorf(u);
-  a             = __fsub_rn(u, f);
-  const int   k = int(f), last = int(srcSize) - 1;
-  i0            = uint32_t(min(max(k, 0), last));
-  i1            = uint32_t(min(max(k + 1, 0), last));
-}
 template <class F>
 __global__ void __launch_bounds__(256) blitKernel(const BlitParams p)
 {
@@ -768,25 +798,7 @@ __global__ void __launch_bounds__(256) blitKernel(const BlitParams p)
   __syncthreads();
   gridDependencyWait();
   gridLaunchDependents();
-  using V                = typename F::Value;
-  constexpr uint32_t TB  = F::kTexelBytes;
-  const float        sx  = __fdiv_rn(float(p.src.w), float(p.dst.w)), sy = __fdiv_rn(float(p.src.h), float(p.dst.h));
-  const uint64_t     n   = uint64_t(p.dst.w) * p.dst.h;
-  for(uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += uint64_t(gridDim.x) * blockDim.x)
-  {
-    const uint32_t y = uint32_t(t / p.dst.w), x = uint32_t(t - uint64_t(y) * p.dst.w);
-    uint32_t       x0, x1, y0, y1;
-    float          a, b;
-    blitTap(x, sx, p.src.w, x0, x1, a);
-    blitTap(y, sy, p.src.h, y0, y1, b);
-    const unsigned char* r0  = p.src.ptr + size_t(y0) * p.src.pitch;
-    const unsigned char* r1  = p.src.ptr + size_t(y1) * p.src.pitch;
-    const V              t00 = F::load(tables, r0 + size_t(x0) * TB), t10 = F::load(tables, r0 + size_t(x1) * TB);
-    const V              t01 = F::load(tables, r1 + size_t(x0) * TB), t11 = F::load(tables, r1 + size_t(x1) * TB);
-    const float          ia = __fsub_rn(1.0f, a), ib = __fsub_rn(1.0f, b);
-    const V              top = F::reduce(ia, t00, a, t10, 0.0f, t10), bot = F::reduce(ia, t01, a, t11, 0.0f, t11);
-    F::template store<true>(tables, p.dst.ptr + size_t(y) * p.dst.pitch + size_t(x) * TB, F::reduce(ib, top, b, bot, 0.0f, bot));
-  }
+  blitLoop<F>(p.src, p.dst, tables, uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, uint64_t(gridDim.x) * blockDim.x);
 }
 
 // ---------------------------------------------------------------------------
