@@ -135,6 +135,56 @@ def test_standalone_kernels_on_small_levels(nv, cuda, oracle):
     assert out.returncode == 0 and "standalone ok" in out.stdout, (out.stdout[-500:], out.stderr[-2000:])
 
 
+@pytest.mark.parametrize("knobs", [{}, {"NVPYR_CASCADE_AREA_MAX": "40000"}, {"NVPYR_CASCADE_COST_FACTOR": "100", "NVPYR_CASCADE_COST_FLOOR": "100000000"},
+                                   {"NVPYR_CASCADE_SOLO_MAX_TEXELS": "17000", "NVPYR_CASCADE_ROUND_COST": "0"}],
+                         ids=["default-knobs", "small-area-raw-staging", "deepest-groups", "large-solo-many-rounds"])
+def test_cascade_tail_bit_exact(nv, cuda, oracle, knobs):
+    """NVPYR_CASCADE=1: the general dispatches of a chain's small levels run as cascades (cascadeRun: several
+    dispatches per launch on shared-memory tiles with recomputed halos, then the rest of the chain solo on one CTA;
+    off by default because it is no faster).  Same bits as the oracle for sRGBA8 (with and without
+    the fast pipeline, both lossy shared types) and rgba32f, with the geometry knobs pushed to their corners: tiny
+    areas (raw staging, many tiles per CTA), the deepest groups, whole 127^2 levels solo."""
+    import subprocess
+    import sys
+    sizes = [(1023, 1023), (1022, 766), (511, 300), (513, 513), (255, 255), (254, 254), (127, 129), (100, 37), (63, 63),
+             (1920, 1080), (1080, 512), (2052, 1028), (773, 247), (17, 513), (301, 7), (7, 301), (1, 37), (64, 1), (5, 5),
+             (3, 3), (2, 2), (260, 260), (640, 360), (2047, 700)]
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import vk_compute_mipmaps_b200 as nv, _oracle\n"
+        "o = _oracle.load_oracle()\n"
+        "n = 0\n"
+        "for (w, h) in %r:\n"
+        "  if w * h > %d: continue\n"
+        "  l0 = _oracle.random_level0(w, h, w * 13 + h)\n"
+        "  for fg in (False, True):\n"
+        "    for flags in (0, nv.FLAG_F16_SHARED, nv.FLAG_SRGB_SHARED):\n"
+        "      if flags and (fg or w * h > 300000): continue\n"
+        "      buf = torch.zeros(nv.chain_bytes(w, h), dtype=torch.uint8, device='cuda')\n"
+        "      buf[:4 * w * h] = torch.from_numpy(l0).cuda()\n"
+        "      nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(fast_pipeline=not fg), w, h, image=buf, flags=flags)\n"
+        "      torch.cuda.synchronize()\n"
+        "      want = o.shader_chain(l0, w, h, force_general=fg, f16_shared=bool(flags & nv.FLAG_F16_SHARED),\n"
+        "                            srgb_shared=bool(flags & nv.FLAG_SRGB_SHARED))[0]\n"
+        "      got = buf.cpu().numpy()\n"
+        "      assert (got == want).all(), (w, h, fg, flags, int((got != want).sum()))\n"
+        "      n += 1\n"
+        "  if w * h <= 300000:\n"
+        "    f0 = _oracle.random_level0(w, h, w + h, fmt=1)\n"
+        "    fb = torch.zeros(nv.chain_bytes(w, h, 0, 1) // 4, dtype=torch.float32, device='cuda')\n"
+        "    fb[:4 * w * h] = torch.from_numpy(np.ascontiguousarray(f0)).cuda().view(-1)\n"
+        "    nv.cmd_pyramid_dispatch(None, nv.PyramidPipelines(format=1), w, h, image=fb)\n"
+        "    torch.cuda.synchronize()\n"
+        "    wantf = o.shader_chain(f0, w, h, fmt=1)[0]\n"
+        "    assert (fb.cpu().numpy().view(np.uint32) == wantf.view(np.uint32)).all(), ('rgba32f', w, h)\n"
+        "    n += 1\n"
+        "print('cascade ok', n)\n") % (_oracle.ROOT, os.path.join(_oracle.ROOT, "tests"), sizes, 600000 if knobs else 1 << 30)
+    env = dict(os.environ, NVPYR_CASCADE="1", **knobs)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "cascade ok" in out.stdout, (out.stdout[-500:], out.stderr[-2000:])
+
+
 @pytest.mark.parametrize("size", [(64, 64), (256, 256), (96, 160), (100, 37), (260, 260), (1, 9)],
                          ids=lambda s: f"{s[0]}x{s[1]}")
 def test_force_general_bit_exact(nv, cuda, oracle, size):

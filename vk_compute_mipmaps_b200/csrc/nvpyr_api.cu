@@ -943,6 +943,55 @@ struct TailFunctors<Srgba8>
   using type = Srgba8Lite;  // small levels: 1 KB decode table, cheap to set up
 };
 
+// NVPYR_TAIL_DEBUG_CLOCKS=1 (development): every tail launch is followed by a synchronisation and prints the clock64()
+// stamps of its first CTA and of the CTA that ran the solo steps (cycles since the CTA started).
+const bool g_tailDebugClocks = [] {
+  const char* e = getenv("NVPYR_TAIL_DEBUG_CLOCKS");
+  return e != nullptr && e[0] == '1';
+}();
+long long* tailDebugBuffer()
+{
+  static long long* buf = nullptr;
+  if(g_tailDebugClocks && buf == nullptr)
+    cudaMalloc(&buf, 1024 * 32 * sizeof(long long));
+  if(buf != nullptr)
+    cudaMemset(buf, 0, 1024 * 32 * sizeof(long long));
+  return buf;
+}
+void tailDebugPrint(const TailParams& tp, int grid, cudaStream_t stream)
+{
+  if(tp.debugClocks == nullptr)
+    return;
+  cudaStreamSynchronize(stream);
+  std::vector<long long> h(size_t(grid) * 32u);
+  cudaMemcpy(h.data(), tp.debugClocks, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  int last = 0;
+  for(int b = 0; b < grid; ++b)
+    if(h[size_t(b) * 32u + 4u] != 0)
+      last = b;
+  for(int b : {0, last})
+  {
+    fprintf(stderr, "nvpyr tail clocks: grid %d steps %u cta %d:", grid, tp.numSteps, b);
+    for(int k = 1; k < 32; ++k)
+      if(h[size_t(b) * 32u + k] != 0)
+        fprintf(stderr, " [%d] %lld", k, h[size_t(b) * 32u + k] - h[size_t(b) * 32u]);
+    fprintf(stderr, "\n");
+    if(last == 0)
+      break;
+  }
+}
+
+// NVPYR_NO_FAST_TINY=1: the last tiny fast steps of a chain run through fastTileLoop as before (A/B timing).
+const bool g_noFastTiny = [] {
+  const char* e = getenv("NVPYR_NO_FAST_TINY");
+  return e != nullptr && e[0] == '1';
+}();
+// TailStep::vec bit 1: a (solo) fast step small enough for fastTinyStep.
+inline uint32_t fastTinyBit(const TailStep& ts)
+{
+  return !g_noFastTiny && ts.levels <= 3u && ts.lv[0].w <= kFastTinyMaxEdge && ts.lv[0].h <= kFastTinyMaxEdge ? 2u : 0u;
+}
+
 // One tail launch: steps[0] on the whole grid, steps[1..count) solo.
 template <class F>
 nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPlanStep* steps, int count)
@@ -972,7 +1021,7 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
     }
     else if(s.pipeline == 1)
     {
-      ts.vec    = fastVectorOk<F>(ts.lv) ? 1u : 0u;
+      ts.vec    = (fastVectorOk<F>(ts.lv) ? 1u : 0u) | fastTinyBit(ts);
       ts.tilesX = (ts.lv[0].w + 63u) / 64u;
       ts.tilesY = (ts.lv[0].h + 63u) / 64u;
     }
@@ -988,13 +1037,257 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
     work = (uint64_t(tp.steps[0].lv[1].w) * tp.steps[0].lv[1].h + uint64_t(kTailThreads) - 1u) / uint64_t(kTailThreads);
   // The whole-level buffers of the solo steps are only allocated by launches that use them (a small footprint lets
   // the next kernel's CTAs move in early); the opt-in and the grid size are those of the larger footprint.
-  const size_t smemSolo = ((sizeof(TailSmem<TF>) + 15u) & ~size_t(15)) + sizeof(SoloSmem);
+  const size_t smemBase = (sizeof(TailSmem<TF>) + 15u) & ~size_t(15);
+  const size_t smemSolo = smemBase + sizeof(SoloSmem);
+  const size_t smemMax  = smemBase + std::max<size_t>(sizeof(SoloSmem), kCascadeAreaMax);  // the opt-in is made once per kernel
   const size_t smem     = anySoloSmem ? smemSolo : sizeof(TailSmem<TF>);
   int          grid = 1;
-  nvpyrStatus  st   = persistentGrid(tailKernel<TF>, smemSolo, ctx, work, &grid, kTailThreads);
+  nvpyrStatus  st   = persistentGrid(tailKernel<TF>, smemMax, ctx, work, &grid, kTailThreads);
   if(st != NVPYR_SUCCESS)
     return st;
+  tp.debugClocks = tailDebugBuffer();
   NVPYR_CUDA(launchKernel(tailKernel<TF>, grid, kTailThreads, smem, r.stream, tp));
+  tailDebugPrint(tp, grid, r.stream);
+  ++g_launchCount;
+  return NVPYR_SUCCESS;
+}
+
+// ------------------------------------------------------------------ cascades (cascadeRun, nvpyr_kernels.cuh)
+// NVPYR_CASCADE=1 switches the cascades on.  They are OFF by default: bit-exact on the whole GPU suite, but measured
+// no faster than one dispatch per grid step (a level costs ~0.5 us of dependent latency on one CTA
+// whichever kernel runs it, and the launch boundary a cascade saves costs no more than the staging and the halo it adds).
+const bool g_noCascade = [] {
+  const char* e = getenv("NVPYR_CASCADE");
+  return !(e != nullptr && e[0] == '1');
+}();
+// Largest input level (texels) of a general step that STARTS a tail launch as a cascade over the whole grid
+// (NVPYR_CASCADE_MAX_TEXELS); larger levels take the strip kernels.
+const uint64_t g_cascadeMaxTexels = [] {
+  const char* e = getenv("NVPYR_CASCADE_MAX_TEXELS");
+  return e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : 1100ull * 1100ull;
+}();
+// Largest input level (texels) of a cascade that ONE CTA runs alone after the grid step (NVPYR_CASCADE_SOLO_MAX_TEXELS).
+const uint64_t g_cascadeSoloMaxTexels = [] {
+  const char* e = getenv("NVPYR_CASCADE_SOLO_MAX_TEXELS");
+  return e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : 64ull * 64ull;
+}();
+// A deeper grid cascade (more dispatches per launch, more halo recomputed) is taken while the texels one SM stages
+// stay below max(g_cascadeCostFactor x its fair share of the input level, g_cascadeCostFloor).
+const double g_cascadeCostFactor = [] {
+  const char* e = getenv("NVPYR_CASCADE_COST_FACTOR");
+  return e != nullptr ? atof(e) : 2.5;
+}();
+const uint64_t g_cascadeCostFloor = [] {
+  const char* e = getenv("NVPYR_CASCADE_COST_FLOOR");
+  return e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : 4096ull;
+}();
+
+const bool g_cascadeDebug = [] {
+  const char* e = getenv("NVPYR_CASCADE_DEBUG");
+  return e != nullptr && e[0] == '1';
+}();
+// Largest cascade area a launch may use (NVPYR_CASCADE_AREA_MAX, at most kCascadeAreaMax): a small footprint lets the
+// CTAs start -- and set up their tables -- while the previous kernel still occupies the SMs.
+const uint64_t g_cascadeAreaMax = [] {
+  const char* e = getenv("NVPYR_CASCADE_AREA_MAX");
+  return std::min<uint64_t>(kCascadeAreaMax, e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : uint64_t(kCascadeAreaMax));
+}();
+struct CascadeGeom
+{
+  uint32_t tileW = 0, tileH = 0, tilesX = 0, tilesY = 0, atStage = 0, off0 = 0, offA = 0, offB = 0;
+  size_t   areaBytes = 0;
+  uint64_t cost      = 0;  // texels of the input level the busiest SM stages
+  uint64_t rounds    = 0;  // tiles the busiest CTA walks
+};
+// What a round of a cascade costs besides its texels (staging round trip, a CTA barrier per level), in texels.
+const uint64_t g_cascadeRoundCost = [] {
+  const char* e = getenv("NVPYR_CASCADE_ROUND_COST");
+  return e != nullptr ? uint64_t(strtoull(e, nullptr, 10)) : 8192ull;
+}();
+
+// Shared-memory layout and cost of a cascade over lv[0..n] whose CTAs own tw x th tiles of level n.
+template <class TF>
+bool cascadeGeometry(const LevelView* lv, uint32_t n, uint32_t tw, uint32_t th, uint32_t smCount, CascadeGeom& g)
+{
+  auto     taps = [](uint32_t size) { return size == 1u ? 1u : (2u | (size & 1u)); };
+  uint32_t fx[7], fy[7];
+  fx[n] = std::min(tw, lv[n].w), fy[n] = std::min(th, lv[n].h);
+  for(int l = int(n) - 1; l >= 0; --l)
+  {
+    fx[l] = std::min(2u * (fx[l + 1] - 1u) + taps(lv[l].w), lv[l].w);
+    fy[l] = std::min(2u * (fy[l + 1] - 1u) + taps(lv[l].h), lv[l].h);
+  }
+  auto         align16 = [](uint64_t b) { return (b + 15u) & ~uint64_t(15); };
+  const size_t vb = sizeof(typename TF::Value), tb = TF::kTexelBytes;
+  const uint64_t a  = n >= 2u ? align16(uint64_t(fx[1]) * fy[1] * vb) : 0u;  // levels 1, 3, 5 (the last level is not kept)
+  const uint64_t b  = n >= 3u ? align16(uint64_t(fx[2]) * fy[2] * vb) : 0u;  // levels 2, 4
+  const uint64_t v0 = align16(uint64_t(fx[0]) * fy[0] * vb), r0 = align16(uint64_t(fx[0]) * fy[0] * tb);
+  uint64_t       s0;
+  if(kCascadeHeaderBytes + v0 + a + b <= g_cascadeAreaMax)
+    g.atStage = 1u, s0 = v0;
+  else if(kCascadeHeaderBytes + r0 + a + b <= g_cascadeAreaMax)
+    g.atStage = 0u, s0 = r0;
+  else
+    return false;
+  g.tileW = fx[n], g.tileH = fy[n];
+  g.tilesX = (lv[n].w + fx[n] - 1u) / fx[n], g.tilesY = (lv[n].h + fy[n] - 1u) / fy[n];
+  g.off0      = kCascadeHeaderBytes;
+  g.offA      = uint32_t(g.off0 + s0);
+  g.offB      = uint32_t(g.offA + a);
+  g.areaBytes = size_t(g.offB + b);
+  const uint64_t tiles = uint64_t(g.tilesX) * g.tilesY;
+  g.rounds             = (tiles + smCount - 1u) / smCount;
+  g.cost               = g.rounds * uint64_t(fx[0]) * fy[0];
+  return true;
+}
+
+// The cheapest tile size for a grid cascade over lv[0..n].
+template <class TF>
+bool cascadeBestGrid(const LevelView* lv, uint32_t n, uint32_t smCount, CascadeGeom& best)
+{
+  bool found = false;
+  for(uint32_t t = 1; t <= 256u; ++t)
+  {
+    CascadeGeom g;
+    if(!cascadeGeometry<TF>(lv, n, t, t, smCount, g))
+      break;  // footprints only grow with t
+    if(!found || g.cost + g.rounds * g_cascadeRoundCost < best.cost + best.rounds * g_cascadeRoundCost)
+      best = g, found = true;
+    if(t >= lv[n].w && t >= lv[n].h)
+      break;
+  }
+  return found;
+}
+
+void fillCascadeStep(TailStep& ts, const ResolvedDesc& r, const nvpyrPlanStep* steps, int count, const CascadeGeom& g)
+{
+  ts          = TailStep{};
+  ts.pipeline = 3u;
+  uint32_t n  = 0;
+  ts.lv[0]    = r.lv[steps[0].inputLevel];
+  for(int k = 0; k < count; ++k)
+  {
+    for(uint32_t j = 1; j <= steps[k].levelCount; ++j)
+      ts.lv[n + j] = r.lv[steps[k].inputLevel + j];
+    n += steps[k].levelCount;
+    ts.boundaryMask |= 1u << n;
+  }
+  ts.levels = n;
+  ts.tileW = g.tileW, ts.tileH = g.tileH, ts.tilesX = g.tilesX, ts.tilesY = g.tilesY;
+  ts.atStage = g.atStage, ts.off0 = g.off0, ts.offA = g.offA, ts.offB = g.offB;
+}
+
+// One tail launch that starts at plan step steps[0] (at most `avail` steps follow): general steps run as cascades --
+// the first as a grid cascade of as many dispatches as the cost limit allows, the following ones solo.  *consumed =
+// plan steps taken.
+template <class F>
+nvpyrStatus launchTailCascade(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPlanStep* steps, int avail, int* consumed)
+{
+  using TF = typename TailFunctors<F>::type;
+  TailParams tp{};
+  tp.tables        = ctx.tables;
+  nvpyrStatus tst  = acquireTicket(ctx, r.stream, &tp.ticket);
+  if(tst != NVPYR_SUCCESS)
+    return tst;
+  size_t   areaBytes = 0;
+  int      i         = 0;
+  uint32_t items     = 0;
+  uint64_t work      = 1;
+  auto     texels    = [&](int k) { return uint64_t(steps[k].srcWidth) * steps[k].srcHeight; };
+  // consecutive general steps from k on, at most three dispatches and six levels: lv[] and level count
+  auto gather = [&](int k, int maxSteps, LevelView* lv, int* stepLevels) {
+    int      cnt = 0;
+    uint32_t n   = 0;
+    lv[0]        = r.lv[steps[k].inputLevel];
+    while(k + cnt < avail && cnt < maxSteps && steps[k + cnt].pipeline == 0 && n + steps[k + cnt].levelCount <= 6u)
+    {
+      for(uint32_t j = 1; j <= steps[k + cnt].levelCount; ++j)
+        lv[n + j] = r.lv[steps[k + cnt].inputLevel + j];
+      n += steps[k + cnt].levelCount;
+      stepLevels[cnt++] = int(n);
+    }
+    return cnt;
+  };
+  while(i < avail && items < kMaxTailSteps)
+  {
+    const nvpyrPlanStep& s  = steps[i];
+    TailStep&            ts = tp.steps[items];
+    if(s.pipeline == 1)
+    {
+      if(items > 0 && texels(i) > kSoloMaxTexelsFast)
+        break;
+      ts          = TailStep{};
+      ts.pipeline = 1u;
+      ts.levels   = s.levelCount;
+      for(uint32_t k = 0; k <= s.levelCount; ++k)
+        ts.lv[k] = r.lv[s.inputLevel + k];
+      ts.vec    = (fastVectorOk<F>(ts.lv) ? 1u : 0u) | fastTinyBit(ts);
+      ts.tilesX = (ts.lv[0].w + 63u) / 64u;
+      ts.tilesY = (ts.lv[0].h + 63u) / 64u;
+      if(items == 0)
+      {
+        work = uint64_t(ts.tilesX) * ts.tilesY;
+        if(ts.levels == 1)  // fastLoop1 is thread-strided, not tiled
+          work = (uint64_t(ts.lv[1].w) * ts.lv[1].h + uint64_t(kTailThreads) - 1u) / uint64_t(kTailThreads);
+      }
+      ++i;
+    }
+    else
+    {
+      LevelView   lv[7];
+      int         stepLevels[3];
+      CascadeGeom g;
+      int         take = 0;
+      if(items == 0)
+      {
+        const int cnt = gather(i, 3, lv, stepLevels);
+        const double fair = double(texels(i)) / double(ctx.smCount);
+        const uint64_t limit = std::max<uint64_t>(uint64_t(g_cascadeCostFactor * fair), g_cascadeCostFloor);
+        for(int d = cnt; d >= 1 && take == 0; --d)
+        {
+          CascadeGeom c;
+          if(cascadeBestGrid<TF>(lv, uint32_t(stepLevels[d - 1]), uint32_t(ctx.smCount), c) && (d == 1 || c.cost <= limit))
+            g = c, take = d;
+        }
+        if(take == 0)
+          return NVPYR_ERROR_UNSUPPORTED;  // (a one-texel tile of a one-dispatch cascade always fits)
+        work = uint64_t(g.tilesX) * g.tilesY;
+      }
+      else
+      {
+        if(texels(i) > g_cascadeSoloMaxTexels)
+          break;
+        const int cnt = gather(i, 3, lv, stepLevels);
+        for(int d = cnt; d >= 1 && take == 0; --d)
+        {
+          const uint32_t n = uint32_t(stepLevels[d - 1]);
+          if(cascadeGeometry<TF>(lv, n, lv[n].w, lv[n].h, uint32_t(ctx.smCount), g))
+            take = d;
+        }
+        if(take == 0)
+          break;
+      }
+      fillCascadeStep(ts, r, steps + i, take, g);
+      if(g_cascadeDebug)
+        fprintf(stderr, "nvpyr cascade: %s %ux%u -> %ux%u (%d dispatches, %u levels) tile %ux%u, %ux%u tiles, %s, %zu bytes, cost %llu\n",
+                items == 0 ? "grid" : "solo", ts.lv[0].w, ts.lv[0].h, ts.lv[ts.levels].w, ts.lv[ts.levels].h, take, ts.levels, g.tileW,
+                g.tileH, g.tilesX, g.tilesY, g.atStage ? "values" : "raw", g.areaBytes, (unsigned long long)g.cost);
+      areaBytes = std::max(areaBytes, g.areaBytes);
+      i += take;
+    }
+    ++items;
+  }
+  tp.numSteps = items;
+  *consumed   = i;
+  const size_t smemBase = (sizeof(TailSmem<TF>) + 15u) & ~size_t(15);
+  const size_t smemMax  = smemBase + std::max<size_t>(sizeof(SoloSmem), kCascadeAreaMax);
+  int          grid     = 1;
+  nvpyrStatus  st       = persistentGrid(tailKernel<TF>, smemMax, ctx, work, &grid, kTailThreads);
+  if(st != NVPYR_SUCCESS)
+    return st;
+  tp.debugClocks = tailDebugBuffer();
+  NVPYR_CUDA(launchKernel(tailKernel<TF>, grid, kTailThreads, areaBytes ? smemBase + areaBytes : sizeof(TailSmem<TF>), r.stream, tp));
+  tailDebugPrint(tp, grid, r.stream);
   ++g_launchCount;
   return NVPYR_SUCCESS;
 }
@@ -1039,6 +1332,14 @@ nvpyrStatus runPlan(DeviceContext& ctx, const ResolvedDesc& r, int firstStep = 0
     {
       st = launchBlit<F>(ctx, r.lv[s.inputLevel], r.lv[s.inputLevel + 1], r.stream);
       ++i;
+    }
+    else if(!g_noTailFusion && !g_noCascade && !blit
+            && (s.pipeline == 0 ? texels(i) <= std::max(g_cascadeMaxTexels, kTailMaxTexels) : texels(i) <= kTailMaxTexels))
+    {
+      // small steps with the general ones as cascades: several dispatches per launch, no boundary between them
+      int consumed = 0;
+      st           = launchTailCascade<F>(ctx, r, steps + i, n - i, &consumed);
+      i += consumed;
     }
     else if(!g_noTailFusion && texels(i) <= kTailMaxTexels)
     {
@@ -1318,7 +1619,7 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
     }
     if(s.pipeline == 1)
     {
-      ts.vec    = fastVectorOk<Srgba8>(real) ? 1u : 0u;  // every base is 16-byte aligned: same answer for all images
+      ts.vec    = (fastVectorOk<Srgba8>(real) ? 1u : 0u) | fastTinyBit(ts);  // every base is 16-byte aligned: same answer for all images
       ts.tilesX = (ts.lv[0].w + 63u) / 64u;
       ts.tilesY = (ts.lv[0].h + 63u) / 64u;
     }

@@ -281,6 +281,51 @@ __device__ __forceinline__ void fastLoop1(const FastParams& p, const typename F:
   }
 }
 
+// A fast step of at most three levels on an input level of at most 8 x 8 texels (the last dispatch of a power-of-two
+// chain: 4 x 4 -> 1 after the 256^2 tail of 16384^2, 2 x 2 -> 1 for 8192^2), by ONE warp with one lane per texel of
+// level +1.  fastTileLoop would give the whole level to a single thread -- some 700 dependent instructions, 4 us on
+// B200 -- here a lane does 1/16 of that.  Same expression trees: level +1 pairs vertically (k = 1), the later levels
+// as fastPairingIsHorizontal says, over lanes arranged 4 x 4 (x neighbour = lane ^ 1, y neighbour = lane ^ 4) with
+// the even/even lane holding (ul, ur, ll, lr) in this order.  No barrier inside; lanes >= 32 return at once.
+template <class F>
+__device__ __forceinline__ void fastTinyStep(const LevelView* lv, uint32_t M, const typename F::Shared& tables)
+{
+  using V               = typename F::Value;
+  constexpr uint32_t TB = F::kTexelBytes;
+  if(threadIdx.x >= 32u)
+    return;
+  const uint32_t lane = threadIdx.x, x = lane & 3u, y = (lane >> 2) & 3u;
+  const bool     valid = lane < 16u && x < lv[1].w && y < lv[1].h;
+  V              l1{};
+  if(valid)
+  {
+    const unsigned char* s = lv[0].ptr + size_t(2u * y) * lv[0].pitch + size_t(2u * x) * TB;
+    if constexpr(HasLoadReduce4<F>::value)
+      l1 = F::loadReduce4(tables, s, lv[0].pitch, 2u * x, 2u * y, lv[0].level);
+    else
+    {
+      const V ul = F::load(tables, s), ur = F::load(tables, s + TB);
+      const V ll = F::load(tables, s + lv[0].pitch), lr = F::load(tables, s + lv[0].pitch + TB);
+      l1         = F::reduce4(ul, ll, ur, lr);
+    }
+    F::template store<false>(tables, lv[1].ptr + size_t(y) * lv[1].pitch + size_t(x) * TB, l1);
+  }
+  if(M < 2u)
+    return;
+  const V        sx = shflXor(l1, 1), sy = shflXor(l1, 4), sxy = shflXor(l1, 5);
+  const V        l2 = reduce4Paired<F>(fastPairingIsHorizontal(2, int(M)), l1, sx, sy, sxy);
+  const bool     even = !(x & 1u) && !(y & 1u);
+  if(valid && even)
+    F::template store<false>(tables, lv[2].ptr + size_t(y >> 1) * lv[2].pitch + size_t(x >> 1) * TB, l2);
+  if(M < 3u)
+    return;
+  const V tx = shflXor(l2, 2), ty = shflXor(l2, 8), txy = shflXor(l2, 10);
+  const V l3 = reduce4Paired<F>(fastPairingIsHorizontal(3, int(M)), l2, tx, ty, txy);
+  if(valid && lane == 0u)
+    F::template store<false>(tables, lv[3].ptr, l3);
+}
+constexpr uint32_t kFastTinyMaxEdge = 8;  // fastTinyStep: input levels up to 8 x 8, at most three levels
+
 template <class F>
 __global__ void __launch_bounds__(256) fastKernel1(const FastParams p)
 {
@@ -531,12 +576,19 @@ constexpr int kTailThreads = NVPYR_TAIL_THREADS;
 
 struct TailStep
 {
-  uint32_t  pipeline;  // 1 fast, 0 general, 2 one level by a linear-filter blit (NVPYR_FLAG_GENERAL_BLIT)
+  uint32_t  pipeline;  // 1 fast, 0 general, 2 one level by a linear-filter blit (NVPYR_FLAG_GENERAL_BLIT),
+                       // 3 cascade: SEVERAL consecutive general dispatches, `levels` levels in all (cascadeRun)
   uint32_t  levels;
-  uint32_t  vec;       // fast: vector loads/stores allowed
+  uint32_t  vec;       // fast: bit 0 vector loads/stores allowed, bit 1 solo step small enough for fastTinyStep
   uint32_t  soloSmem;  // solo general step that runs on whole levels held in shared memory (soloGeneralSmem)
   uint32_t  tilesX, tilesY;
   LevelView lv[7];
+  // cascade only
+  uint32_t  tileW, tileH;    // tile of the LAST level that one CTA owns (solo: the whole level)
+  uint32_t  boundaryMask;    // bit l: level l ends a reference dispatch (the next level re-reads it as stored texels)
+  uint32_t  atStage;         // level 0 footprint is decoded while it is staged (values in shared memory), else raw texels
+  uint32_t  off0, offA, offB;  // byte offsets of the three buffers inside the cascade area
+  uint32_t  pad_;
 };
 
 struct TailParams
@@ -544,8 +596,12 @@ struct TailParams
   uint32_t            numSteps;
   uint32_t*           ticket;  // zero on entry, reset to zero by the last CTA
   const DeviceTables* tables;
+  long long*          debugClocks;  // NVPYR_TAIL_DEBUG_CLOCKS=1: 32 clock64() stamps per CTA (phase timeline); else null
   TailStep            steps[kMaxTailSteps];
 };
+#define NVPYR_TAIL_STAMP(k)                                                                                          \
+  if(tp.debugClocks != nullptr && threadIdx.x == 0)                                                                  \
+  tp.debugClocks[blockIdx.x * 32u + (k)] = clock64()
 
 template <class F>
 struct TailSmem
@@ -650,13 +706,256 @@ __device__ __forceinline__ void soloGeneralSmem(const TailStep& st, const typena
   }
 }
 
+// ---------------------------------------------------------------------------
+// Cascade: several consecutive GENERAL dispatches on shared-memory tiles, no launch boundary between them.
+//
+// An NPOT chain ends in five to seven general dispatches on levels of 1023^2 texels and less.  One launch per
+// dispatch costs more in launch boundaries (2-3 us each, even with programmatic dependent launch) than in work.
+// Here ONE CTA owns a tile of the LAST level of a group of up to three dispatches (up to six levels) and computes
+// everything that tile depends on by itself: its footprint on the group's input level is staged in shared memory
+// once, every level between is produced into shared memory for exactly the footprint the tile needs (halo
+// texels are recomputed by the neighbouring CTA -- the same expression on the same inputs, hence the same bits, just
+// as the reference's overlapping work groups recompute them), and each CTA writes to global memory
+// the part of every level that lies above its own tile.  No CTA waits for another.  What the reference's dispatch
+// boundaries mean is kept: INSIDE a dispatch the first level is handed to the second as float32 values
+// (sharedLevel_, glsl:555,664,717: F::sharedRound); ACROSS a dispatch boundary the next level sees what was stored,
+// so the value goes through F::store and F::load (for sRGBA8: encode to 8 bits, decode again) -- in registers.
+// With a tile that covers the whole last level the same function is the "solo" continuation of the chain on one CTA.
+struct CascadeRects
+{
+  uint32_t x0[7], y0[7], w[7], h[7];  // footprint of the CTA's tile on level l of the group (texels)
+  uint32_t ownX1[7], ownY1[7];        // the CTA writes texels [x0, ownX1) x [y0, ownY1) of level l to global memory
+};
+constexpr uint32_t kCascadeHeaderBytes = 256;         // CascadeRects at the start of the cascade area
+constexpr uint32_t kCascadeAreaMax     = 200u * 1024u;  // the area's largest size (host: cascadeGeometry)
+static_assert(sizeof(CascadeRects) <= kCascadeHeaderBytes, "cascade header");
+
+// t / d for t, d < 2^16 with magic = ceil(2^32 / d) (exact: t * (magic * d - 2^32) < 2^32); d = 1 has no 32-bit magic.
+__device__ __forceinline__ uint32_t cascadeMagic(uint32_t d)
+{
+  return d > 1u ? 0xFFFFFFFFu / d + 1u : 0u;  // = ceil(2^32 / d), also when d divides 2^32
+}
+__device__ __forceinline__ uint32_t cascadeDivide(uint32_t t, uint32_t d, uint32_t magic)
+{
+  return d > 1u ? __umulhi(t, magic) : t;
+}
+
+// The weights of one axis of a level: everything of taps3() that does not depend on the destination index.
+struct CascadeAxis
+{
+  int   taps;
+  float fn, rcp, w1;
+};
+__device__ __forceinline__ CascadeAxis cascadeAxis(uint32_t srcSize, uint32_t dstSize)
+{
+  CascadeAxis a;
+  a.taps = kernelTaps(srcSize);
+  a.fn   = float(dstSize);
+  a.rcp  = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(2.0f, a.fn), 1.0f));
+  a.w1   = __fmul_rn(a.rcp, a.fn);
+  return a;
+}
+// reduceSample() with the per-level part of the weights precomputed (the same operations on the same values).
+template <class F, class Fetch>
+__device__ __forceinline__ typename F::Value cascadeSample(const CascadeAxis& ax, const CascadeAxis& ay, uint32_t dx, uint32_t dy,
+                                                           Fetch fetch)
+{
+  using V = typename F::Value;
+  V     hcol[3];
+  float w0 = 0.f, w2 = 0.f;
+  if(ay.taps == 3)
+  {
+    w0 = __fmul_rn(ay.rcp, __fsub_rn(ay.fn, float(dy)));
+    w2 = __fsub_rn(__fsub_rn(1.0f, w0), ay.w1);
+  }
+#pragma unroll
+  for(int c = 0; c < 3; ++c)
+  {
+    if(c < ax.taps)
+    {
+      const V v0 = fetch(c, 0);
+      if(ay.taps == 3)
+        hcol[c] = F::reduce(w0, v0, ay.w1, fetch(c, 1), w2, fetch(c, 2));
+      else if(ay.taps == 2)
+        hcol[c] = F::reduce2(v0, fetch(c, 1));
+      else
+        hcol[c] = v0;
+    }
+  }
+  if(ax.taps == 3)
+  {
+    w0 = __fmul_rn(ax.rcp, __fsub_rn(ax.fn, float(dx)));
+    w2 = __fsub_rn(__fsub_rn(1.0f, w0), ax.w1);
+    return F::reduce(w0, hcol[0], ax.w1, hcol[1], w2, hcol[2]);
+  }
+  if(ax.taps == 2)
+    return F::reduce2(hcol[0], hcol[1]);
+  return hcol[0];
+}
+
+template <class F>
+__device__ __forceinline__ void cascadeRun(const TailStep& st, const typename F::Shared& tables, unsigned char* area,
+                                           uint32_t firstTile, uint32_t tileStride, long long* dbg = nullptr)
+{
+  uint32_t dbgSlot = 16u;
+#define NVPYR_CASCADE_STAMP()                                                                                        \
+  if(dbg != nullptr && threadIdx.x == 0 && dbgSlot < 32u)                                                            \
+  dbg[dbgSlot++] = clock64()
+  using V                  = typename F::Value;
+  constexpr uint32_t TB    = F::kTexelBytes;
+  static_assert(TB % 4u == 0 && TB <= 16u, "texels are staged as 4- or 16-byte words");
+  constexpr uint32_t kWord = TB % 16u == 0 ? 16u : 4u;
+  CascadeRects&      R     = *reinterpret_cast<CascadeRects*>(area);
+  unsigned char*     raw0  = area + st.off0;
+  V*                 buf0  = reinterpret_cast<V*>(area + st.off0);
+  V*                 bufA  = reinterpret_cast<V*>(area + st.offA);
+  V*                 bufB  = reinterpret_cast<V*>(area + st.offB);
+  const uint32_t     n = st.levels, numTiles = st.tilesX * st.tilesY;
+
+  for(uint32_t tile = firstTile; tile < numTiles; tile += tileStride)
+  {
+    __syncthreads();  // the previous tile (or step) is done with the area
+    if(threadIdx.x < 2u)
+    {
+      // thread 0: x ranges, thread 1: y ranges.  Level l + 1 texel i reads texels 2i .. 2i + taps - 1 of level l.
+      const bool     isY  = threadIdx.x == 1u;
+      const uint32_t t    = isY ? tile / st.tilesX : tile % st.tilesX;
+      const uint32_t tsz  = isY ? st.tileH : st.tileW;
+      const uint32_t endN = isY ? st.lv[n].h : st.lv[n].w;
+      uint32_t*      x0   = isY ? R.y0 : R.x0;
+      uint32_t*      w    = isY ? R.h : R.w;
+      uint32_t*      own  = isY ? R.ownY1 : R.ownX1;
+      const uint32_t a = t * tsz, b = min(a + tsz, endN);
+      x0[n] = a, w[n] = b - a, own[n] = b;
+      for(int l = int(n) - 1; l >= 0; --l)
+      {
+        const uint32_t size = isY ? st.lv[l].h : st.lv[l].w;
+        const uint32_t lo = 2u * x0[l + 1], hi = min(2u * (x0[l + 1] + w[l + 1] - 1u) + uint32_t(kernelTaps(size)), size);
+        x0[l]  = lo;
+        w[l]   = hi - lo;
+        own[l] = b == endN ? size : min(size, b << (n - uint32_t(l)));
+      }
+    }
+    __syncthreads();
+    NVPYR_CASCADE_STAMP();
+
+    // Stage the footprint on the group's input level (written by an earlier launch, or by other CTAs of this one
+    // before the ticket: read through L2).
+    {
+      const LevelView      L0 = st.lv[0];
+      const uint32_t       perRow = st.atStage ? R.w[0] : R.w[0] * TB / kWord, magic = cascadeMagic(perRow), total = perRow * R.h[0];
+      const unsigned char* g0 = L0.ptr + size_t(R.y0[0]) * L0.pitch + size_t(R.x0[0]) * TB;
+      if(st.atStage)
+      {
+        // kStageBatch loads of a thread in flight before the first is decoded (the footprint is a few texels per
+        // thread: one L2 round trip instead of one per texel)
+        constexpr uint32_t kStageBatch = 8;
+        for(uint32_t base = threadIdx.x; base < total; base += blockDim.x * kStageBatch)
+        {
+          alignas(16) uint32_t texel[kStageBatch][TB / 4u];
+#pragma unroll
+          for(uint32_t k = 0; k < kStageBatch; ++k)
+          {
+            const uint32_t i = base + k * blockDim.x;
+            if(i < total)
+            {
+              const uint32_t       y = cascadeDivide(i, perRow, magic), x = i - y * perRow;
+              const unsigned char* g = g0 + size_t(y) * L0.pitch + size_t(x) * TB;
+              if(kWord == 16u)
+                *reinterpret_cast<uint4*>(texel[k]) = __ldcg(reinterpret_cast<const uint4*>(g));
+              else
+              {
+#pragma unroll
+                for(uint32_t j = 0; j < TB / 4u; ++j)
+                  texel[k][j] = __ldcg(reinterpret_cast<const uint32_t*>(g) + j);
+              }
+            }
+          }
+#pragma unroll
+          for(uint32_t k = 0; k < kStageBatch; ++k)
+          {
+            const uint32_t i = base + k * blockDim.x;
+            if(i < total)
+              buf0[i] = F::load(tables, texel[k]);
+          }
+        }
+      }
+      else
+      {
+        // raw texels: asynchronous copies straight into shared memory (LDGSTS), all in flight at once
+        const uint32_t dst0 = uint32_t(__cvta_generic_to_shared(raw0));
+        for(uint32_t i = threadIdx.x; i < total; i += blockDim.x)
+        {
+          const uint32_t       y = cascadeDivide(i, perRow, magic), x = i - y * perRow;
+          const unsigned char* g = g0 + size_t(y) * L0.pitch + size_t(x) * kWord;
+          if(kWord == 16u)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + i * 16u), "l"(g) : "memory");
+          else
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + i * 4u), "l"(g) : "memory");
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+      }
+    }
+    __syncthreads();
+    NVPYR_CASCADE_STAMP();
+
+    const V* in = buf0;
+    for(uint32_t l = 1; l <= n; ++l)
+    {
+      V*                out = (l & 1u) ? bufA : bufB;
+      const LevelView   Lo  = st.lv[l];
+      const CascadeAxis ax = cascadeAxis(st.lv[l - 1u].w, Lo.w), ay = cascadeAxis(st.lv[l - 1u].h, Lo.h);
+      const uint32_t    inW = R.w[l - 1u], outW = R.w[l], total = outW * R.h[l], magic = cascadeMagic(outW);
+      const uint32_t    ox = R.x0[l], oy = R.y0[l], ownX1 = R.ownX1[l], ownY1 = R.ownY1[l];
+      const bool        rawInput = l == 1u && !st.atStage, isLast = l == n, boundary = (st.boundaryMask >> l) & 1u;
+      for(uint32_t t = threadIdx.x; t < total; t += blockDim.x)
+      {
+        const uint32_t ly = cascadeDivide(t, outW, magic), lx = t - ly * outW;
+        const uint32_t x = ox + lx, y = oy + ly;
+        V              v;
+        if(rawInput)
+        {
+          const unsigned char* s = raw0 + (2u * ly * inW + 2u * lx) * TB;
+          v = cascadeSample<F>(ax, ay, x, y, [&](int dx, int dy) { return F::load(tables, s + (uint32_t(dy) * inW + uint32_t(dx)) * TB); });
+        }
+        else
+        {
+          const V* m = in + (2u * ly * inW + 2u * lx);
+          v          = cascadeSample<F>(ax, ay, x, y, [&](int dx, int dy) { return m[uint32_t(dy) * inW + uint32_t(dx)]; });
+        }
+        if(x < ownX1 && y < ownY1)
+          F::template store<true>(tables, Lo.ptr + size_t(y) * Lo.pitch + size_t(x) * TB, v);
+        if(!isLast)
+        {
+          if(boundary)
+          {
+            alignas(16) uint32_t texel[TB / 4u];  // what the next dispatch reads back: the stored texel
+            F::template store<true>(tables, texel, v);
+            out[t] = F::load(tables, texel);
+          }
+          else
+            out[t] = F::sharedRound(v);  // sharedLevel_ (glsl:717)
+        }
+      }
+      __syncthreads();
+      NVPYR_CASCADE_STAMP();
+      in = out;
+    }
+  }
+#undef NVPYR_CASCADE_STAMP
+}
+
 // kSolo: the step is run by one CTA alone (its general tiles were counted for soloTile2).
 template <class F, bool kSolo>
 __device__ __forceinline__ void tailRunStep(const TailStep& st, TailSmem<F>& sm, const DeviceTables* tables,
-                                            uint32_t first, uint32_t stride)
+                                            uint32_t first, uint32_t stride, unsigned char* area = nullptr, long long* dbg = nullptr)
 {
-  if(st.pipeline == 2u)
+  if(st.pipeline == 3u)
+    cascadeRun<F>(st, sm.tables, area, first, stride, dbg);
+  else if(st.pipeline == 2u)
     blitLoop<F>(st.lv[0], st.lv[1], sm.tables, uint64_t(first) * blockDim.x + threadIdx.x, uint64_t(stride) * blockDim.x);
+  else if(st.pipeline == 1u && kSolo && (st.vec & 2u))
+    fastTinyStep<F>(st.lv, st.levels, sm.tables);
   else if(st.pipeline == 1u)
   {
     FastParams p;
@@ -668,7 +967,7 @@ __device__ __forceinline__ void tailRunStep(const TailStep& st, TailSmem<F>& sm,
     p.tables = tables;
 #define NVPYR_TAIL_FAST(m)                                                                                        \
   case m:                                                                                                         \
-    if(st.vec)                                                                                                    \
+    if(st.vec & 1u)                                                                                               \
       fastTileLoop<F, m, true>(p, sm.tables, sm.l3, first, stride);                                               \
     else                                                                                                          \
       fastTileLoop<F, m, false>(p, sm.tables, sm.l3, first, stride);                                              \
@@ -706,12 +1005,19 @@ __global__ void __launch_bounds__(kTailThreads) tailKernel(const __grid_constant
 {
   extern __shared__ __align__(128) unsigned char smemRaw[];
   TailSmem<F>& sm = *reinterpret_cast<TailSmem<F>*>(smemRaw);
+  NVPYR_TAIL_STAMP(0);
   F::sharedInit(sm.tables, tp.tables);
   __syncthreads();
+  NVPYR_TAIL_STAMP(1);
   gridDependencyWait();    // the previous kernel's levels are complete and visible
   gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
+  NVPYR_TAIL_STAMP(2);
 
-  tailRunStep<F, false>(tp.steps[0], sm, tp.tables, blockIdx.x, gridDim.x);
+  // (launched with sizeof(TailSmem<F>) + the solo buffers or the cascade area when a step needs them)
+  unsigned char* area = smemRaw + ((sizeof(TailSmem<F>) + 15u) & ~size_t(15));
+  long long* dbg = tp.debugClocks != nullptr ? tp.debugClocks + blockIdx.x * 32u : nullptr;
+  tailRunStep<F, false>(tp.steps[0], sm, tp.tables, blockIdx.x, gridDim.x, area, dbg);
+  NVPYR_TAIL_STAMP(3);
   if(tp.numSteps == 1u)
     return;
 
@@ -729,9 +1035,9 @@ __global__ void __launch_bounds__(kTailThreads) tailKernel(const __grid_constant
   if(!sm.isLast)
     return;
   __threadfence();  // acquire side of the ticket
+  NVPYR_TAIL_STAMP(4);
 
-  // (launched with sizeof(TailSmem<F>) + sizeof(SoloSmem) bytes when a step has soloSmem set)
-  SoloSmem&            solo = *reinterpret_cast<SoloSmem*>(smemRaw + ((sizeof(TailSmem<F>) + 15u) & ~size_t(15)));
+  SoloSmem&            solo = *reinterpret_cast<SoloSmem*>(area);
   const unsigned char* levelInSmem = nullptr;  // the previous step's last level, if that step left it in shared memory
   uint32_t             pingPong = 0;
   for(uint32_t s = 1; s < tp.numSteps; ++s)
@@ -745,11 +1051,12 @@ __global__ void __launch_bounds__(kTailThreads) tailKernel(const __grid_constant
     }
     else
     {
-      tailRunStep<F, true>(tp.steps[s], sm, tp.tables, 0u, 1u);
+      tailRunStep<F, true>(tp.steps[s], sm, tp.tables, 0u, 1u, area, dbg);
       levelInSmem = nullptr;
     }
     __threadfence_block();
     __syncthreads();  // the reference's inter-dispatch pipeline barrier (one CTA: a CTA barrier suffices)
+    NVPYR_TAIL_STAMP(4u + min(s, 9u));
   }
 }
 
