@@ -315,19 +315,41 @@ static_assert(EncConst<1>::kAdd == kRowEncZeroBits, "row 0 of the encode table i
 // Address bias of the encode half-rows: row key k lives at byte (k - kRowEncFirstKey) * 256 + 128 of the table.
 constexpr int32_t kRowEncBias = int32_t(kRowEncFirstKey << 8) - 128;
 
+// kThreads = threads of the CTA.  Every load of a thread is in flight before its first store: the set-up is pure
+// latency (five to seven table entries per thread, each an L2 round trip if taken one after the other), and it is on the
+// critical path of every chain whose main launch is short -- the next chain's CTAs build their tables while the tail of
+// this one runs, and the CTA on the SM that was freed last finishes building after that tail has ended.
+template <int kThreads>
 __device__ __forceinline__ void srgba8FastInit(Srgba8FastSmem& sm, const DeviceTables* t)
 {
   // thread -> (row, 16-byte column): eight consecutive threads write the 128 contiguous bytes of one half row
-  uint4* tab = reinterpret_cast<uint4*>(sm.decode);  // 16 uint4 per row: 0..7 decode / stash, 8..15 encode
-  for(uint32_t i = threadIdx.x; i < kRowEncRows * 8u; i += blockDim.x)
+  uint4*             tab    = reinterpret_cast<uint4*>(sm.decode);  // 16 uint4 per row: 0..7 decode / stash, 8..15 encode
+  constexpr uint32_t kItems = kRowEncRows * 8u, kPerThread = (kItems + kThreads - 1) / kThreads;
+  uint32_t           e[kPerThread];
+  float              d[kPerThread];
+#pragma unroll
+  for(uint32_t k = 0; k < kPerThread; ++k)
   {
-    const uint32_t row = i >> 3, col = i & 7u;
-    const uint32_t e   = __ldg(&t->encodeRows[row]);
-    tab[row * 16u + 8u + col] = make_uint4(e, e, e, e);
-    if(row < 256u)
+    const uint32_t i = threadIdx.x + k * kThreads, row = i >> 3;
+    if(i < kItems)
     {
-      const uint32_t v = __float_as_uint(__fmul_rn(__ldg(&t->decode[row]), 7.888609052210118e-31f));  // * 2^-100, exact
-      tab[row * 16u + col] = make_uint4(v, v, v, v);
+      e[k] = __ldg(&t->encodeRows[row]);
+      if(row < 256u)
+        d[k] = __ldg(&t->decode[row]);
+    }
+  }
+#pragma unroll
+  for(uint32_t k = 0; k < kPerThread; ++k)
+  {
+    const uint32_t i = threadIdx.x + k * kThreads, row = i >> 3, col = i & 7u;
+    if(i < kItems)
+    {
+      tab[row * 16u + 8u + col] = make_uint4(e[k], e[k], e[k], e[k]);
+      if(row < 256u)
+      {
+        const uint32_t v = __float_as_uint(__fmul_rn(d[k], 7.888609052210118e-31f));  // * 2^-100, exact
+        tab[row * 16u + col] = make_uint4(v, v, v, v);
+      }
     }
   }
 }
@@ -356,6 +378,7 @@ __device__ __forceinline__ void putZeroWord(Srgba8FastSmem& sm)
       sm.decode[EncConst<K>::kZeroIndex + w] = __uint_as_float(0u - EncConst<K>::kAdd);
 }
 
+template <int kThreads>
 __device__ __forceinline__ void srgba8FastInit(Srgba8FastSmem& sm, const DeviceTables* t)
 {
   // 512 threads: thread -> (code, half): 16 lane slots = 4 x float4
@@ -602,7 +625,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastCtasPerSm)
 {
   extern __shared__ __align__(128) unsigned char smemRaw[];
   Srgba8FastSmem& sm = *reinterpret_cast<Srgba8FastSmem*>(smemRaw);
-  srgba8FastInit(sm, tables);
+  srgba8FastInit<kFastWarps * 32>(sm, tables);
   __syncthreads();
   gridDependencyWait();
   gridLaunchDependents();
@@ -672,7 +695,7 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
   Srgba8FastSmem& sm = *reinterpret_cast<Srgba8FastSmem*>(smemRaw);
   if(kSlabTasks && threadIdx.x < kSlots)
     tileArrivals[threadIdx.x] = 0u, slotGeneration[threadIdx.x] = 0u;
-  srgba8FastInit(sm, p.tables);
+  srgba8FastInit<kWarps * 32>(sm, p.tables);
   __syncthreads();  // the only CTA-wide barrier
   gridDependencyWait();    // the previous kernel's levels are complete and visible
   gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free

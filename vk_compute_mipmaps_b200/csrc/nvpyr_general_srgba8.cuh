@@ -97,16 +97,30 @@ __device__ __forceinline__ void genSrgba8Init(unsigned char* smemRaw, const Devi
   if(kGenRows)
   {
     // thread -> (row, 16-byte column): eight consecutive threads write the 128 contiguous bytes of one half row
-    uint4* tab = reinterpret_cast<uint4*>(smemRaw + (kGenDecodeAddr - kGenWindowBase));  // 16 uint4 per row
-    for(uint32_t i = threadIdx.x; i < kRowEncRows * 8u; i += kThreads)
+    // (every load of a thread in flight before its first store, as in srgba8FastInit: the set-up is pure latency)
+    uint4*             tab    = reinterpret_cast<uint4*>(smemRaw + (kGenDecodeAddr - kGenWindowBase));  // 16 uint4 per row
+    constexpr uint32_t kItems = kRowEncRows * 8u, kPerThread = (kItems + kThreads - 1) / kThreads;
+    uint32_t           e[kPerThread], d[kPerThread];
+#pragma unroll
+    for(uint32_t k = 0; k < kPerThread; ++k)
     {
-      const uint32_t row = i >> 3, col = i & 7u;
-      const uint32_t e   = __ldg(&t->encodeRows[row]);
-      tab[row * 16u + 8u + col] = make_uint4(e, e, e, e);
-      if(row < 256u)
+      const uint32_t i = threadIdx.x + k * kThreads, row = i >> 3;
+      if(i < kItems)
       {
-        const uint32_t v = __float_as_uint(__ldg(&t->decode[row]));
-        tab[row * 16u + col] = make_uint4(v, v, v, v);
+        e[k] = __ldg(&t->encodeRows[row]);
+        if(row < 256u)
+          d[k] = __float_as_uint(__ldg(&t->decode[row]));
+      }
+    }
+#pragma unroll
+    for(uint32_t k = 0; k < kPerThread; ++k)
+    {
+      const uint32_t i = threadIdx.x + k * kThreads, row = i >> 3, col = i & 7u;
+      if(i < kItems)
+      {
+        tab[row * 16u + 8u + col] = make_uint4(e[k], e[k], e[k], e[k]);
+        if(row < 256u)
+          tab[row * 16u + col] = make_uint4(d[k], d[k], d[k], d[k]);
       }
     }
     return;
