@@ -54,5 +54,7 @@ for tail in 262144 0; do
   [ $tail = 0 ] && export NVPYR_FAST_WARPS_LARGE=24 NVPYR_SLAB_MAX_TILES_PER_WARP_X100=$SLAB
   NVPYR_HOST_BAND_BYTES=131072 NVPYR_TAIL_MAX_TEXELS=$tail compute-sanitizer --tool $TOOL --kernel-regex kns=nvpyr --print-limit 20 python /tmp/san_driver.py 2>&1 | tail -6
 done
+echo "== $TOOL NVPYR_CASCADE=1 (general dispatches of the small levels as cascades: cascadeRun, off by default)"
+NVPYR_CASCADE=1 NVPYR_HOST_BAND_BYTES=131072 compute-sanitizer --tool $TOOL --kernel-regex kns=nvpyr --print-limit 20 python /tmp/san_driver.py 2>&1 | tail -6
 echo "== $TOOL examples/custom_functors (user-defined functor sets through include/nvpyr.cuh)"
 compute-sanitizer --tool $TOOL --print-limit 20 ./examples/custom_functors 2>&1 | tail -4
