@@ -949,6 +949,12 @@ const bool g_tailDebugClocks = [] {
   const char* e = getenv("NVPYR_TAIL_DEBUG_CLOCKS");
   return e != nullptr && e[0] == '1';
 }();
+// NVPYR_TAIL_DEFER_WAIT: 0 = tailKernel waits for the previous kernel at its entry, 1 = right before the grid step's
+// first load, 2 = the same and the next kernel is let go (griddepcontrol.launch_dependents) at the kernel's entry.
+const uint32_t g_tailDeferWait = [] {
+  const char* e = getenv("NVPYR_TAIL_DEFER_WAIT");
+  return e != nullptr ? uint32_t(atoi(e)) : 1u;
+}();
 long long* tailDebugBuffer()
 {
   static long long* buf = nullptr;
@@ -1046,6 +1052,7 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
   if(st != NVPYR_SUCCESS)
     return st;
   tp.debugClocks = tailDebugBuffer();
+  tp.deferWait   = g_tailDeferWait;
   NVPYR_CUDA(launchKernel(tailKernel<TF>, grid, kTailThreads, smem, r.stream, tp));
   tailDebugPrint(tp, grid, r.stream);
   ++g_launchCount;
@@ -1286,6 +1293,7 @@ nvpyrStatus launchTailCascade(DeviceContext& ctx, const ResolvedDesc& r, const n
   if(st != NVPYR_SUCCESS)
     return st;
   tp.debugClocks = tailDebugBuffer();
+  tp.deferWait   = g_tailDeferWait;
   NVPYR_CUDA(launchKernel(tailKernel<TF>, grid, kTailThreads, areaBytes ? smemBase + areaBytes : sizeof(TailSmem<TF>), r.stream, tp));
   tailDebugPrint(tp, grid, r.stream);
   ++g_launchCount;

@@ -697,8 +697,8 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
     tileArrivals[threadIdx.x] = 0u, slotGeneration[threadIdx.x] = 0u;
   srgba8FastInit<kWarps * 32>(sm, p.tables);
   __syncthreads();  // the only CTA-wide barrier
-  gridDependencyWait();    // the previous kernel's levels are complete and visible
-  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
+  // (the wait for the previous kernel comes right before the first access to a level, below: the lane constants and
+  // the mbarrier set-up need nothing the previous kernel wrote)
   const unsigned char* dec = reinterpret_cast<const unsigned char*>(sm.decode);
   const unsigned char* enc = encBaseOf(sm);
 
@@ -788,7 +788,6 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
       bulkCopyG2S(tmaRing + lane * 256u, p.lv[0].ptr + size_t(ys + lane) * pitch0 + size_t(xt) * 4u, rowBytes, tmaBar);
 #endif
   };
-  Cursor nxt = tileCursor(tile, slab0);
   if(kTma)
   {
 #if NVPYR_FAST_TMA
@@ -800,8 +799,12 @@ __global__ void __launch_bounds__(kWarps * 32, kFastCtasPerSm)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fenceProxyAsync();
     __syncwarp();
-    tmaIssue(tile, slab0);
   }
+  gridDependencyWait();    // the previous kernel's levels are complete and visible
+  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
+  Cursor nxt = tileCursor(tile, slab0);
+  if(kTma)
+    tmaIssue(tile, slab0);
   else if(kFastPrefetch)
     loadRows(nxt);
 

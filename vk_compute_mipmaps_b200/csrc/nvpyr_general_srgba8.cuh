@@ -317,9 +317,6 @@ __global__ void __launch_bounds__(C::kWarps * 32, 1) generalStripKernel(const Ge
     genSrgba8Init(smemRaw, p.tables);
     __syncthreads();
   }
-  gridDependencyWait();    // the previous kernel's levels are complete and visible
-  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
-
   const uint32_t  lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, laneAddr = kGenDecodeAddr | (lane * 4u);
   const LevelView L0 = p.lv[0], L1 = p.lv[1], L2 = p.lv[2];
   const float     fH1 = float(L1.h), fW1 = float(L1.w);
@@ -330,6 +327,8 @@ __global__ void __launch_bounds__(C::kWarps * 32, 1) generalStripKernel(const Ge
   const float rcpY2 = y3b ? genRcp(L2.h) : 0.f, rcpX2 = x3b ? genRcp(L2.w) : 0.f;
 
   const uint32_t numTasks = p.stripsX * p.segsY;
+  gridDependencyWait();    // the previous kernel's levels are complete and visible (the constants above need none of them)
+  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
   for(uint32_t task = blockIdx.x + gridDim.x * warp; task < numTasks; task += gridDim.x * kWarps)
   {
     const uint32_t sx = task % p.stripsX, sy = task / p.stripsX;
@@ -559,9 +558,6 @@ __global__ void __launch_bounds__(kGen4Warps * 32, 1) generalStrip4Kernel(const 
     __trap();  // the absolute table addresses assume this window layout: fail loudly, never silently
   genSrgba8Init<kGen4Warps * 32>(smemRaw, p.tables);
   __syncthreads();
-  gridDependencyWait();    // the previous kernel's levels are complete and visible
-  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
-
   const uint32_t  lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, laneAddr = kGenDecodeAddr | (lane * 4u);
   const LevelView L0 = p.lv[0], L1 = p.lv[1], L2 = p.lv[2];
   const float     fH1 = float(L1.h), fW1 = float(L1.w);
@@ -577,6 +573,8 @@ __global__ void __launch_bounds__(kGen4Warps * 32, 1) generalStrip4Kernel(const 
   uint32_t       consumed = 0, issued = 0;  // stage indices (wrap at kGenStages)
 
   const uint32_t numTasks = p.stripsX * p.segsY;
+  gridDependencyWait();    // the previous kernel's levels are complete and visible (the constants above need none of them)
+  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
   for(uint32_t task = blockIdx.x + gridDim.x * warp; task < numTasks; task += gridDim.x * kGen4Warps)
   {
     const uint32_t sx = task % p.stripsX, sy = task / p.stripsX;

@@ -115,7 +115,7 @@ struct FastSmem
 template <class F, int M, bool kVec>
 __device__ __forceinline__ void fastTileLoop(const FastParams& p, const typename F::Shared& tables,
                                              typename F::Value (*l3buf)[8][8], uint32_t firstTile,
-                                             uint32_t tileStride)
+                                             uint32_t tileStride, uint32_t deferredWait = 0u)
 {
   static_assert(M >= 2 && M <= 6, "fastTileLoop handles 2..6 levels");
   using V = typename F::Value;
@@ -132,6 +132,16 @@ __device__ __forceinline__ void fastTileLoop(const FastParams& p, const typename
     // 256 threads (tailKernel): the extra ones only take part in the barriers.
     const bool active = tid < 256u && x0 < W && y0 < H;
 
+    // deferredWait (tailKernel's grid step): the wait for the previous kernel comes HERE, right before the first load
+    // of a level it wrote -- the parameter reads, the tile arithmetic and the instruction fetches up to this point
+    // (~800 cycles, cold) then overlap the previous kernel's last CTAs instead of following them.
+    if(deferredWait)
+    {
+      gridDependencyWait();
+      if(deferredWait == 1u)
+        gridLaunchDependents();
+      deferredWait = 0u;
+    }
     V l1[2][2];
     V l2{};
     if(active)
@@ -240,6 +250,12 @@ __device__ __forceinline__ void fastTileLoop(const FastParams& p, const typename
       // l3buf is double buffered: the next iteration writes the other half, and the
       // barrier of that iteration orders this read before the overwrite after it.
     }
+  }
+  if(deferredWait)  // (a CTA without a tile)
+  {
+    gridDependencyWait();
+    if(deferredWait == 1u)
+      gridLaunchDependents();
   }
 }
 
@@ -437,7 +453,7 @@ __device__ __forceinline__ typename F::Value reduceSample(int kx, int ky, uint32
 template <class F, int T2>
 __device__ __forceinline__ void generalTileLoop(const GeneralParams& p, const typename F::Shared& tables,
                                                 GenTile<T2, typename F::Value>& scratch, uint32_t firstTile,
-                                                uint32_t tileStride)
+                                                uint32_t tileStride, uint32_t deferredWait = 0u)
 {
   using V                             = typename F::Value;
   V(*l1buf)[GenTile<T2, V>::kPitch] = scratch.l1;
@@ -448,6 +464,13 @@ __device__ __forceinline__ void generalTileLoop(const GeneralParams& p, const ty
   for(uint32_t tile = firstTile; tile < numTiles; tile += tileStride)
   {
     const uint32_t tileX = tile % p.tilesX, tileY = tile / p.tilesX;
+    if(deferredWait)  // (see fastTileLoop)
+    {
+      gridDependencyWait();
+      if(deferredWait == 1u)
+        gridLaunchDependents();
+      deferredWait = 0u;
+    }
     if(p.levels == 1)
     {
       // (2 T2) x (2 T2) tile of level +1, no carry needed.
@@ -497,6 +520,12 @@ __device__ __forceinline__ void generalTileLoop(const GeneralParams& p, const ty
       F::template store<true>(tables, L2.ptr + size_t(y2a + ly) * L2.pitch + size_t(x2a + lx) * F::kTexelBytes,
                               out);
     }
+  }
+  if(deferredWait)  // (a CTA without a tile)
+  {
+    gridDependencyWait();
+    if(deferredWait == 1u)
+      gridLaunchDependents();
   }
 }
 
@@ -596,6 +625,7 @@ struct TailParams
   uint32_t            numSteps;
   uint32_t*           ticket;  // zero on entry, reset to zero by the last CTA
   const DeviceTables* tables;
+  uint32_t            deferWait;    // the grid step's tile loop executes griddepcontrol.wait itself (NVPYR_TAIL_DEFER_WAIT=0: at kernel entry)
   long long*          debugClocks;  // NVPYR_TAIL_DEBUG_CLOCKS=1: 32 clock64() stamps per CTA (phase timeline); else null
   TailStep            steps[kMaxTailSteps];
 };
@@ -948,7 +978,8 @@ __device__ __forceinline__ void cascadeRun(const TailStep& st, const typename F:
 // kSolo: the step is run by one CTA alone (its general tiles were counted for soloTile2).
 template <class F, bool kSolo>
 __device__ __forceinline__ void tailRunStep(const TailStep& st, TailSmem<F>& sm, const DeviceTables* tables,
-                                            uint32_t first, uint32_t stride, unsigned char* area = nullptr, long long* dbg = nullptr)
+                                            uint32_t first, uint32_t stride, unsigned char* area = nullptr, long long* dbg = nullptr,
+                                            uint32_t deferredWait = 0u)
 {
   if(st.pipeline == 3u)
     cascadeRun<F>(st, sm.tables, area, first, stride, dbg);
@@ -968,9 +999,9 @@ __device__ __forceinline__ void tailRunStep(const TailStep& st, TailSmem<F>& sm,
 #define NVPYR_TAIL_FAST(m)                                                                                        \
   case m:                                                                                                         \
     if(st.vec & 1u)                                                                                               \
-      fastTileLoop<F, m, true>(p, sm.tables, sm.l3, first, stride);                                               \
+      fastTileLoop<F, m, true>(p, sm.tables, sm.l3, first, stride, deferredWait);                                 \
     else                                                                                                          \
-      fastTileLoop<F, m, false>(p, sm.tables, sm.l3, first, stride);                                              \
+      fastTileLoop<F, m, false>(p, sm.tables, sm.l3, first, stride, deferredWait);                                \
     break;
     switch(st.levels)
     {
@@ -996,7 +1027,7 @@ __device__ __forceinline__ void tailRunStep(const TailStep& st, TailSmem<F>& sm,
     if(kSolo)
       generalTileLoop<F, SoloTile2<typename F::Value>::value>(p, sm.tables, sm.soloTile, first, stride);
     else
-      generalTileLoop<F, kGenTile2Small>(p, sm.tables, sm.tile, first, stride);
+      generalTileLoop<F, kGenTile2Small>(p, sm.tables, sm.tile, first, stride, deferredWait);
   }
 }
 
@@ -1009,14 +1040,19 @@ __global__ void __launch_bounds__(kTailThreads) tailKernel(const __grid_constant
   F::sharedInit(sm.tables, tp.tables);
   __syncthreads();
   NVPYR_TAIL_STAMP(1);
-  gridDependencyWait();    // the previous kernel's levels are complete and visible
-  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
+  // Tile steps wait for the previous kernel themselves, right before their first load (see fastTileLoop).
+  // (tp.deferWait 2: the next kernel is let go at once, 1: after the wait as in the other kernels)
+  const uint32_t deferWait = tp.steps[0].pipeline == 0u || (tp.steps[0].pipeline == 1u && tp.steps[0].levels >= 2u) ? tp.deferWait : 0u;
+  if(deferWait == 0u)
+    gridDependencyWait();  // the previous kernel's levels are complete and visible
+  if(deferWait != 1u)
+    gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
   NVPYR_TAIL_STAMP(2);
 
   // (launched with sizeof(TailSmem<F>) + the solo buffers or the cascade area when a step needs them)
   unsigned char* area = smemRaw + ((sizeof(TailSmem<F>) + 15u) & ~size_t(15));
   long long* dbg = tp.debugClocks != nullptr ? tp.debugClocks + blockIdx.x * 32u : nullptr;
-  tailRunStep<F, false>(tp.steps[0], sm, tp.tables, blockIdx.x, gridDim.x, area, dbg);
+  tailRunStep<F, false>(tp.steps[0], sm, tp.tables, blockIdx.x, gridDim.x, area, dbg, deferWait);
   NVPYR_TAIL_STAMP(3);
   if(tp.numSteps == 1u)
     return;
