@@ -266,9 +266,8 @@ __global__ void __launch_bounds__(256) fastKernel(const FastParams p)
   FastSmem<F>& sm = *reinterpret_cast<FastSmem<F>*>(smemRaw);
   F::sharedInit(sm.tables, p.tables);
   __syncthreads();
-  gridDependencyWait();    // the previous kernel's levels are complete and visible
-  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
-  fastTileLoop<F, M, kVec>(p, sm.tables, sm.l3, blockIdx.x, gridDim.x);
+  // (the tile loop waits for the previous kernel right before its first load and lets the next one go: deferredWait 1)
+  fastTileLoop<F, M, kVec>(p, sm.tables, sm.l3, blockIdx.x, gridDim.x, 1u);
 }
 
 // M = 1 (glsl:345-357 with levelCount_ == 1): one thread per output texel, grid-strided from
@@ -536,9 +535,8 @@ __global__ void __launch_bounds__(256) generalKernel(const GeneralParams p)
   GeneralSmem<F>& sm = *reinterpret_cast<GeneralSmem<F>*>(smemRaw);
   F::sharedInit(sm.tables, p.tables);
   __syncthreads();
-  gridDependencyWait();    // the previous kernel's levels are complete and visible
-  gridLaunchDependents();  // the next kernel may start its own set-up as SMs become free
-  generalTileLoop<F, kGenTile2>(p, sm.tables, sm.tile, blockIdx.x, gridDim.x);
+  // (the tile loop waits for the previous kernel right before its first load and lets the next one go: deferredWait 1)
+  generalTileLoop<F, kGenTile2>(p, sm.tables, sm.tile, blockIdx.x, gridDim.x, 1u);
 }
 
 // ---------------------------------------------------------------------------
