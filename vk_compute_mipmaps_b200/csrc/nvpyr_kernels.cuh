@@ -1055,20 +1055,29 @@ __global__ void __launch_bounds__(kTailThreads) tailKernel(const __grid_constant
   if(tp.numSteps == 1u)
     return;
 
-  // Publish this CTA's part of step 0, then find out whether it was the last one.
-  __threadfence();
-  __syncthreads();
-  if(threadIdx.x == 0)
+  // Publish this CTA's part of step 0, then find out whether it was the last one.  (A grid of one CTA -- images of a
+  // few thousand texels -- needs neither the fences nor the atomic, ~1 us: a barrier orders the CTA's own accesses.)
+  if(gridDim.x != 1u)
   {
-    const uint32_t t = atomicAdd(tp.ticket, 1u);
-    sm.isLast        = t == gridDim.x - 1u;
-    if(sm.isLast)
-      *tp.ticket = 0u;  // every CTA has taken its ticket: safe to recycle the counter
+    __threadfence();
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+      const uint32_t t = atomicAdd(tp.ticket, 1u);
+      sm.isLast        = t == gridDim.x - 1u;
+      if(sm.isLast)
+        *tp.ticket = 0u;  // every CTA has taken its ticket: safe to recycle the counter
+    }
+    __syncthreads();
+    if(!sm.isLast)
+      return;
+    __threadfence();  // acquire side of the ticket
   }
-  __syncthreads();
-  if(!sm.isLast)
-    return;
-  __threadfence();  // acquire side of the ticket
+  else
+  {
+    __threadfence_block();
+    __syncthreads();
+  }
   NVPYR_TAIL_STAMP(4);
 
   SoloSmem&            solo = *reinterpret_cast<SoloSmem*>(area);
