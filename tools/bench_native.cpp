@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "nvpyr.h"
@@ -122,15 +123,19 @@ int main(int argc, char** argv)
       return 3;
     const uint64_t launches = nvpyrGetLaunchCount() - launches0;
     CK(cudaStreamSynchronize(stream));
-    std::vector<double> ns;
+    std::vector<double> ns, hostNs;  // device time per chain (events) and host time to enqueue one chain
     for(int b = 0; b <= batches; ++b)
     {
       CK(cudaEventRecord(e0, stream));
+      const auto h0 = std::chrono::steady_clock::now();
       for(int i = 0; i < 8; ++i)
       {
         d.base = bufs[(b * 8 + i) % nrot];
         nvpyrDispatchEx(&d);
       }
+      const auto h1 = std::chrono::steady_clock::now();
+      if(b)
+        hostNs.push_back(std::chrono::duration<double, std::nano>(h1 - h0).count() / 8);
       CK(cudaEventRecord(e1, stream));
       CK(cudaStreamSynchronize(stream));
       float ms = 0;
@@ -139,10 +144,11 @@ int main(int argc, char** argv)
         ns.push_back(ms * 1e6 / 8);
     }
     std::sort(ns.begin(), ns.end());
-    const double mn = ns.front(), med = ns[ns.size() / 2];
-    printf("%-20s %5ux%-5u %-8s launches %2llu  min %9.1f us  median %9.1f us  %8.1f GB/s  (%.1f%% of HBM peak)\n", c.name, c.w,
+    std::sort(hostNs.begin(), hostNs.end());
+    const double mn = ns.front(), med = ns[ns.size() / 2], hostMed = hostNs[hostNs.size() / 2];
+    printf("%-20s %5ux%-5u %-8s launches %2llu  min %9.1f us  median %9.1f us  %8.1f GB/s  (%.1f%% of HBM peak)  host enqueue %5.1f us\n", c.name, c.w,
            c.h, c.fmt == NVPYR_FORMAT_SRGBA8 ? "srgba8" : "rgba32f", (unsigned long long)launches, mn / 1e3, med / 1e3, bytes / med,
-           100.0 * bytes / med / peak);
+           100.0 * bytes / med / peak, hostMed / 1e3);
     fflush(stdout);
     if(jf)
     {
