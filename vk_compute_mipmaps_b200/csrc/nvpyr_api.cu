@@ -1036,6 +1036,7 @@ nvpyrStatus launchTail(DeviceContext& ctx, const ResolvedDesc& r, const nvpyrPla
       generalTiles(ts.lv, s.levelCount, i == 0 ? kGenTile2Small : SoloTile2<typename TF::Value>::value, &ts.tilesX, &ts.tilesY);
       ts.soloSmem = i > 0 && soloSmemOk<TF>(ts.lv[0].w, ts.lv[0].h, s.levelCount) ? 1u : 0u;
       anySoloSmem |= ts.soloSmem != 0u;
+      fillTailStepReciprocals(ts);
     }
   }
   uint64_t work = uint64_t(tp.steps[0].tilesX) * tp.steps[0].tilesY;
@@ -1182,6 +1183,7 @@ void fillCascadeStep(TailStep& ts, const ResolvedDesc& r, const nvpyrPlanStep* s
   ts.levels = n;
   ts.tileW = g.tileW, ts.tileH = g.tileH, ts.tilesX = g.tilesX, ts.tilesY = g.tilesY;
   ts.atStage = g.atStage, ts.off0 = g.off0, ts.offA = g.offA, ts.offB = g.offB;
+  fillTailStepReciprocals(ts);
 }
 
 // One tail launch that starts at plan step steps[0] (at most `avail` steps follow): general steps run as cascades --
@@ -1632,7 +1634,10 @@ nvpyrStatus dispatchBatchFused(DeviceContext& ctx, const std::vector<ResolvedDes
       ts.tilesY = (ts.lv[0].h + 63u) / 64u;
     }
     else
+    {
       generalTiles(ts.lv, s.levelCount, SoloTile2<TF::Value>::value, &ts.tilesX, &ts.tilesY);  // every batch-tail step is solo
+      fillTailStepReciprocals(ts);
+    }
   }
   const size_t smem = sizeof(TailSmem<TF>);
   int          grid = 1;

@@ -362,6 +362,12 @@ struct GeneralParams
   uint32_t            levels; // 1 or 2
   uint32_t            tilesX, tilesY;
   const DeviceTables* tables;
+  // 1 / (2 n + 1) for n = width / height of lv[1], lv[2], divided on the host (the same IEEE float32 division); 0 =
+  // not supplied, the kernel divides.  The small steps at the end of a chain run cold code once, and there an IEEE
+  // division -- a call into a slow-path subroutine somewhere else in the instruction stream -- costs several hundred
+  // cycles per output texel (tools/tail_clocks.sh: level +2 of a 15 x 15 -> 7 x 7 -> 3 x 3 step, two divisions per
+  // texel, 2200-4400 cycles; of 15 x 8 -> 7 x 4 -> 3 x 2, one division, 700).
+  float               rcpW[3] = {0.f, 0.f, 0.f}, rcpH[3] = {0.f, 0.f, 0.f};
 };
 
 constexpr int kGenTile2 = 16;  // tile edge in level +2 of the stand-alone general kernel
@@ -402,10 +408,10 @@ __device__ __forceinline__ int kernelTaps(uint32_t size)
 
 // Weights of the 3-tap kernel for destination index i of n (glsl:582-586, :639-643):
 // (n - i, n, 1 + i) / (2n + 1) with w2 evaluated as 1 - w0 - w1.
-__device__ __forceinline__ void taps3(uint32_t n, uint32_t i, float& w0, float& w1, float& w2)
+__device__ __forceinline__ void taps3(uint32_t n, uint32_t i, float& w0, float& w1, float& w2, float hostRcp = 0.f)
 {
   const float fn  = float(n);
-  const float rcp = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(2.0f, fn), 1.0f));
+  const float rcp = hostRcp != 0.f ? hostRcp : __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(2.0f, fn), 1.0f));
   w0              = __fmul_rn(rcp, __fsub_rn(fn, float(i)));
   w1              = __fmul_rn(rcp, fn);
   w2              = __fsub_rn(__fsub_rn(1.0f, w0), w1);
@@ -416,13 +422,14 @@ __device__ __forceinline__ void taps3(uint32_t n, uint32_t i, float& w0, float& 
 // sample at (srcX + dx, srcY + dy).
 template <class F, class Fetch>
 __device__ __forceinline__ typename F::Value reduceSample(int kx, int ky, uint32_t dstW, uint32_t dstH,
-                                                          uint32_t dx, uint32_t dy, Fetch fetch)
+                                                          uint32_t dx, uint32_t dy, Fetch fetch, float rcpW = 0.f,
+                                                          float rcpH = 0.f)
 {
   using V = typename F::Value;
   V     hcol[3];
   float w0 = 0.f, w1 = 0.f, w2 = 0.f;
   if(ky == 3)
-    taps3(dstH, dy, w0, w1, w2);
+    taps3(dstH, dy, w0, w1, w2, rcpH);
 #pragma unroll
   for(int c = 0; c < 3; ++c)
   {
@@ -439,7 +446,7 @@ __device__ __forceinline__ typename F::Value reduceSample(int kx, int ky, uint32
   }
   if(kx == 3)
   {
-    taps3(dstW, dx, w0, w1, w2);
+    taps3(dstW, dx, w0, w1, w2, rcpW);
     return F::reduce(w0, hcol[0], w1, hcol[1], w2, hcol[2]);
   }
   if(kx == 2)
@@ -481,7 +488,7 @@ __device__ __forceinline__ void generalTileLoop(const GeneralParams& p, const ty
         const unsigned char* s   = L0.ptr + size_t(2 * y) * L0.pitch + size_t(2 * x) * F::kTexelBytes;
         const V              out = reduceSample<F>(k1x, k1y, L1.w, L1.h, x, y, [&](int dx, int dy) {
           return F::load(tables, s + size_t(dy) * L0.pitch + size_t(dx) * F::kTexelBytes);
-        });
+        }, p.rcpW[1], p.rcpH[1]);
         F::template store<true>(tables, L1.ptr + size_t(y) * L1.pitch + size_t(x) * F::kTexelBytes, out);
       }
       continue;
@@ -503,7 +510,7 @@ __device__ __forceinline__ void generalTileLoop(const GeneralParams& p, const ty
       const unsigned char* s   = L0.ptr + size_t(2 * y) * L0.pitch + size_t(2 * x) * F::kTexelBytes;
       const V              out = reduceSample<F>(k1x, k1y, L1.w, L1.h, x, y, [&](int dx, int dy) {
         return F::load(tables, s + size_t(dy) * L0.pitch + size_t(dx) * F::kTexelBytes);
-      });
+      }, p.rcpW[1], p.rcpH[1]);
       // The halo column/row is also produced (with identical bits) by the neighbouring
       // tile, exactly like the reference's overlapping work groups.
       F::template store<true>(tables, L1.ptr + size_t(y) * L1.pitch + size_t(x) * F::kTexelBytes, out);
@@ -515,7 +522,7 @@ __device__ __forceinline__ void generalTileLoop(const GeneralParams& p, const ty
     {
       const uint32_t lx = t % tw, ly = t / tw;
       const V        out = reduceSample<F>(k2x, k2y, L2.w, L2.h, x2a + lx, y2a + ly,
-                                           [&](int dx, int dy) { return l1buf[2 * ly + dy][2 * lx + dx]; });
+                                           [&](int dx, int dy) { return l1buf[2 * ly + dy][2 * lx + dx]; }, p.rcpW[2], p.rcpH[2]);
       F::template store<true>(tables, L2.ptr + size_t(y2a + ly) * L2.pitch + size_t(x2a + lx) * F::kTexelBytes,
                               out);
     }
@@ -616,7 +623,19 @@ struct TailStep
   uint32_t  atStage;         // level 0 footprint is decoded while it is staged (values in shared memory), else raw texels
   uint32_t  off0, offA, offB;  // byte offsets of the three buffers inside the cascade area
   uint32_t  pad_;
+  // general steps: 1 / (2 n + 1) for n = width / height of lv[k], k >= 1, divided on the host (GeneralParams::rcpW)
+  float     rcpW[7], rcpH[7];
 };
+// (host) fills the reciprocals of a step whose lv[1 .. levels] are set
+inline void fillTailStepReciprocals(TailStep& ts)
+{
+  for(uint32_t k = 0; k < 7u; ++k)
+  {
+    const bool used = k >= 1u && k <= ts.levels;
+    ts.rcpW[k]      = used ? 1.0f / (2.0f * float(ts.lv[k].w) + 1.0f) : 0.f;
+    ts.rcpH[k]      = used ? 1.0f / (2.0f * float(ts.lv[k].h) + 1.0f) : 0.f;
+  }
+}
 
 struct TailParams
 {
@@ -712,7 +731,8 @@ __device__ __forceinline__ void soloGeneralSmem(const TailStep& st, const typena
     const uint32_t       y = t / L1.w, x = t - y * L1.w;
     const unsigned char* s = inSmem + size_t(2u * y) * pitchIn + size_t(2u * x) * TB;
     const V out = reduceSample<F>(k1x, k1y, L1.w, L1.h, x, y,
-                                  [&](int dx, int dy) { return F::load(tables, s + size_t(dy) * pitchIn + size_t(dx) * TB); });
+                                  [&](int dx, int dy) { return F::load(tables, s + size_t(dy) * pitchIn + size_t(dx) * TB); },
+                                  st.rcpW[1], st.rcpH[1]);
     F::template store<true>(tables, L1.ptr + size_t(y) * L1.pitch + size_t(x) * TB, out);
     if(st.levels == 2u)
       mid[t] = F::sharedRound(out);  // sharedLevel_ (glsl:717)
@@ -727,7 +747,8 @@ __device__ __forceinline__ void soloGeneralSmem(const TailStep& st, const typena
     {
       const uint32_t y = t / L2.w, x = t - y * L2.w;
       const V*       m = mid + size_t(2u * y) * L1.w + 2u * x;
-      const V        out = reduceSample<F>(k2x, k2y, L2.w, L2.h, x, y, [&](int dx, int dy) { return m[size_t(dy) * L1.w + dx]; });
+      const V        out = reduceSample<F>(k2x, k2y, L2.w, L2.h, x, y, [&](int dx, int dy) { return m[size_t(dy) * L1.w + dx]; },
+                                           st.rcpW[2], st.rcpH[2]);
       F::template store<true>(tables, L2.ptr + size_t(y) * L2.pitch + size_t(x) * TB, out);
       F::template store<true>(tables, outSmem + size_t(t) * TB, out);
     }
@@ -774,12 +795,12 @@ struct CascadeAxis
   int   taps;
   float fn, rcp, w1;
 };
-__device__ __forceinline__ CascadeAxis cascadeAxis(uint32_t srcSize, uint32_t dstSize)
+__device__ __forceinline__ CascadeAxis cascadeAxis(uint32_t srcSize, uint32_t dstSize, float hostRcp = 0.f)
 {
   CascadeAxis a;
   a.taps = kernelTaps(srcSize);
   a.fn   = float(dstSize);
-  a.rcp  = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(2.0f, a.fn), 1.0f));
+  a.rcp  = hostRcp != 0.f ? hostRcp : __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(2.0f, a.fn), 1.0f));
   a.w1   = __fmul_rn(a.rcp, a.fn);
   return a;
 }
@@ -932,7 +953,7 @@ __device__ __forceinline__ void cascadeRun(const TailStep& st, const typename F:
     {
       V*                out = (l & 1u) ? bufA : bufB;
       const LevelView   Lo  = st.lv[l];
-      const CascadeAxis ax = cascadeAxis(st.lv[l - 1u].w, Lo.w), ay = cascadeAxis(st.lv[l - 1u].h, Lo.h);
+      const CascadeAxis ax = cascadeAxis(st.lv[l - 1u].w, Lo.w, st.rcpW[l]), ay = cascadeAxis(st.lv[l - 1u].h, Lo.h, st.rcpH[l]);
       const uint32_t    inW = R.w[l - 1u], outW = R.w[l], total = outW * R.h[l], magic = cascadeMagic(outW);
       const uint32_t    ox = R.x0[l], oy = R.y0[l], ownX1 = R.ownX1[l], ownY1 = R.ownY1[l];
       const bool        rawInput = l == 1u && !st.atStage, isLast = l == n, boundary = (st.boundaryMask >> l) & 1u;
@@ -1022,6 +1043,7 @@ __device__ __forceinline__ void tailRunStep(const TailStep& st, TailSmem<F>& sm,
     p.tilesX = st.tilesX;
     p.tilesY = st.tilesY;
     p.tables = tables;
+    p.rcpW[1] = st.rcpW[1], p.rcpW[2] = st.rcpW[2], p.rcpH[1] = st.rcpH[1], p.rcpH[2] = st.rcpH[2];
     if(kSolo)
       generalTileLoop<F, SoloTile2<typename F::Value>::value>(p, sm.tables, sm.soloTile, first, stride);
     else
