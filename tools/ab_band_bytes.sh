@@ -1,0 +1,3 @@
+for b in 8388608 16777216 33554432 67108864 134217728; do
+  NVPYR_HOST_BAND_BYTES=$b python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-other-inputs --no-batch --input julia 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); e=d['e2e']; print('band $b e2e_ms %.3f GB/s %.2f separate_ms %.3f h2d_only_ms %.3f' % (e['ms_per_step'], e['value'], e['separate_buffers']['ms_per_step'], e['h2d_only']['ms']))"
+done
