@@ -1775,6 +1775,11 @@ const uint32_t g_hostBandLevels = [] {
   const char* e = getenv("NVPYR_HOST_BAND_LEVELS");
   return e != nullptr ? std::max(1u, uint32_t(atoi(e))) : 6u;
 }();
+// NVPYR_HOST_TAPER=0: the last band of the pipelined round trip is not cut into smaller ones (A/B timing).
+const bool g_hostTaper = [] {
+  const char* e = getenv("NVPYR_HOST_TAPER");
+  return !(e != nullptr && e[0] == '0');
+}();
 // Host threads that move a pageable caller's bands into / out of the pinned staging chain (NVPYR_HOST_COPY_THREADS).
 const unsigned kHostCopyThreads = [] {
   const char* e = getenv("NVPYR_HOST_COPY_THREADS");
@@ -1848,11 +1853,12 @@ nvpyrStatus generateHostPipelined(DeviceContext& ctx, HostPipeline& hp, const Re
   if(n < 0)
     return NVPYR_ERROR_INVALID_VALUE;
 
-  uint32_t bandRows = 0, M = 0;
+  uint32_t bandRows = 0, M = 0, bandUnit = 0;
   if(n > 0 && steps[0].pipeline == 1 && steps[0].levelCount >= 2 && kHostBandBytes != 0 && level0Bytes >= 2 * kHostBandBytes)
   {
     M                   = steps[0].levelCount;
     const uint32_t unit = std::max(8u, 1u << M);  // tile height of the fast kernels
+    bandUnit            = unit;
     uint64_t       rows = std::max<uint64_t>(1, kHostBandBytes / rowBytes);
     rows                = (rows + unit - 1) / unit * unit;
     const uint64_t minRows = (uint64_t(r.h) + kMaxHostBands - 1) / kMaxHostBands;
@@ -1940,10 +1946,16 @@ nvpyrStatus generateHostPipelined(DeviceContext& ctx, HostPipeline& hp, const Re
       }
     });
 
-  uint32_t band = 0;
-  for(uint32_t row0 = 0; row0 < r.h; row0 += bandRows, ++band)
+  // In place the LAST band is cut into halves of halves (down to one tile row): what remains to be done after the last
+  // upload -- that band's kernel and the download of its levels -- shrinks with it.
+  const bool taper = !level0Back && g_hostTaper && (r.h + bandRows - 1) / bandRows + 10u <= kMaxHostBands;
+  uint32_t   band = 0, rows = 0;
+  for(uint32_t row0 = 0; row0 < r.h; row0 += rows, ++band)
   {
-    const uint32_t rows = std::min(bandRows, r.h - row0);
+    const uint32_t remaining = r.h - row0;
+    rows                     = std::min(bandRows, remaining);
+    if(taper && remaining <= bandRows && remaining > bandUnit)
+      rows = std::max(bandUnit, remaining / 2u / bandUnit * bandUnit);
     if(stageIn)
       parallelCopy(hp.stage + row0 * rowBytes, hin + row0 * rowBytes, rows * rowBytes);
     NVPYR_CUDA(cudaMemcpyAsync(dev + row0 * rowBytes, upSrc + row0 * rowBytes, rows * rowBytes, cudaMemcpyHostToDevice, hp.up));
